@@ -1,0 +1,220 @@
+/*
+ * paris_b200.h -- C ABI of the B200-native FDK backend (libparis_b200.so).
+ *
+ * This is the drop-in boundary for the hot path of hzdr/PARIS: everything the
+ * reference's compile-time backend contract (src/backend.h:26-46, canonical text
+ * src/generic/backend.h:42-88) asks of a backend, as plain C entry points -- no C++
+ * types, no torch types, plain pointers and sizes.  The C++ namespace paris::b200
+ * (paris_b200/cpp/b200/backend.h) is a set of <=10-line forwarders onto these, and
+ * INTEGRATION.md shows the three-line change that selects it inside the reference.
+ *
+ * Conventions
+ *  - every call returns 0 on success, else a PARIS_B200_E* code; paris_b200_last_error()
+ *    gives the text for the calling thread.  Nothing throws, nothing calls exit().
+ *  - a context (paris_b200_ctx) belongs to one device and one host thread at a time,
+ *    like the reference's per-device thread (src/main.cpp:157-169).  All work of a
+ *    context is ordered on its compute stream; H2D/D2H copies use a second stream and
+ *    are ordered against compute with events.
+ *  - "d_" pointers are device memory of the context's device, "h_" pointers are host.
+ *  - projections are dim_x = n_row samples per detector row (fastest) times dim_y = n_col
+ *    rows, contiguous (src/projection.h:31-46); volumes are x fastest, z slowest,
+ *    contiguous (src/volume.h:31-45).  All samples float32.
+ *  - there is NO CPU fallback: every entry point that computes launches sm_100a kernels
+ *    and fails with PARIS_B200_ECUDA when no such device is present.
+ */
+#ifndef PARIS_B200_H_
+#define PARIS_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define PARIS_B200_OK 0
+#define PARIS_B200_EINVAL 1   /* bad argument */
+#define PARIS_B200_ECUDA 2    /* CUDA runtime / driver error (text in last_error) */
+#define PARIS_B200_ENOMEM 3   /* allocation failed */
+#define PARIS_B200_ESTATE 4   /* call not valid in the context's current state */
+
+/* src/geometry.h:30-47 */
+typedef struct paris_b200_detector_geometry
+{
+    uint32_t n_row;   /* pixels per detector row */
+    uint32_t n_col;   /* number of detector rows */
+    float l_px_row;   /* pixel size along a row [mm] */
+    float l_px_col;   /* pixel size across rows [mm] */
+    float delta_s;    /* horizontal detector offset [px] */
+    float delta_t;    /* vertical detector offset [px] */
+    float d_so;       /* source -> object [mm] */
+    float d_od;       /* object -> detector [mm] */
+    float delta_phi;  /* angle step [deg] */
+} paris_b200_detector_geometry;
+
+/* src/geometry.h:49-58 */
+typedef struct paris_b200_volume_geometry
+{
+    uint32_t dim_x, dim_y, dim_z;
+    float l_vx_x, l_vx_y, l_vx_z;
+} paris_b200_volume_geometry;
+
+/* src/region_of_interest.h:30-38 */
+typedef struct paris_b200_roi
+{
+    uint32_t x1, x2, y1, y2, z1, z2;
+} paris_b200_roi;
+
+/* src/subvolume_information.h:30-34 with src/geometry.h:60-69 flattened */
+typedef struct paris_b200_subvolume_info
+{
+    uint32_t dim_x, dim_y, dim_z;
+    uint32_t remainder; /* extra slices carried by the LAST slab (src/make_volume.cpp:32-34) */
+    int32_t num;        /* number of slabs */
+} paris_b200_subvolume_info;
+
+typedef struct paris_b200_ctx paris_b200_ctx;       /* per-device state */
+typedef struct paris_b200_filter paris_b200_filter; /* device-resident ramp-filter table */
+
+/* ---- library / devices ------------------------------------------------------------------ */
+
+const char* paris_b200_last_error(void);
+const char* paris_b200_version(void);
+
+/* get_devices / set_device: src/generic/backend.h:84-86, src/cuda/device.cpp:38-47 */
+int paris_b200_device_count(int* count);
+int paris_b200_ctx_create(int device, paris_b200_ctx** ctx);
+int paris_b200_ctx_destroy(paris_b200_ctx* ctx);
+int paris_b200_ctx_device(const paris_b200_ctx* ctx, int* device);
+/* make the context's device current for the calling thread (set_device) */
+int paris_b200_ctx_bind(paris_b200_ctx* ctx);
+/* block until all work of the context (both streams) is complete */
+int paris_b200_ctx_sync(paris_b200_ctx* ctx);
+/* the context's compute stream as a cudaStream_t, for callers that time with CUDA events */
+int paris_b200_ctx_stream(paris_b200_ctx* ctx, void** stream);
+/* counters since ctx_create: kernels launched by this library on this context */
+int paris_b200_ctx_launch_count(const paris_b200_ctx* ctx, uint64_t* launches);
+
+/* Tunables.  "bp_batch": projections accumulated per backprojection launch (default 32);
+ * "bp_kernel": 0 = auto, 1 = generic L1-gather kernel, 2 = TMA-staged kernel. */
+int paris_b200_ctx_set_option(paris_b200_ctx* ctx, const char* name, int64_t value);
+
+/* ---- geometry (host-side, pure arithmetic) ------------------------------------------------ */
+
+/* calculate_volume_geometry: src/geometry.cpp:36-84 */
+int paris_b200_calculate_volume_geometry(const paris_b200_detector_geometry* det, paris_b200_volume_geometry* vol);
+/* apply_roi: src/geometry.cpp:86-130 (an invalid ROI leaves the geometry unchanged, as the reference does) */
+int paris_b200_apply_roi(const paris_b200_volume_geometry* vol, const paris_b200_roi* roi,
+                         paris_b200_volume_geometry* out);
+/* filter_size = 2 * 2^ceil(log2(n_row)): src/filtering.cpp:38 */
+uint32_t paris_b200_filter_size(uint32_t n_row);
+/* make_subvolume_information: src/cuda/subvolume_information.cpp:63-118.  num_slabs > 0 forces that many
+ * equal z-slabs (remainder on the last); num_slabs == 0 sizes slabs by the free memory of the
+ * context's device like the reference (volume + 10 projections must fit, halve until it does). */
+int paris_b200_make_subvolume_information(paris_b200_ctx* ctx, const paris_b200_volume_geometry* vol,
+                                          const paris_b200_detector_geometry* det, int num_slabs,
+                                          paris_b200_subvolume_info* out);
+
+/* ---- memory: make_* / copy_* of the backend contract (src/openmp/memory.cpp:33-79,
+ *      src/cuda/memory.cpp:34-102) ----------------------------------------------------------- */
+
+/* pinned host memory (make_projection_host / make_volume_host); zero == nonzero clears it */
+int paris_b200_host_alloc(size_t bytes, int zero, void** h_ptr);
+int paris_b200_host_free(void* h_ptr);
+/* stream-ordered device memory (make_projection_device); freeing is ordered after queued work */
+int paris_b200_dev_alloc(paris_b200_ctx* ctx, size_t bytes, void** d_ptr);
+int paris_b200_dev_free(paris_b200_ctx* ctx, void* d_ptr);
+/* make_volume_device: zero-initialised dim_x*dim_y*dim_z floats */
+int paris_b200_volume_alloc(paris_b200_ctx* ctx, uint32_t dim_x, uint32_t dim_y, uint32_t dim_z, float** d_vol);
+int paris_b200_volume_free(paris_b200_ctx* ctx, float* d_vol);
+
+/* copy_h2d(projection): asynchronous when h_src is pinned; later work of the context waits for it.
+ * The host buffer must stay valid until paris_b200_h2d_done() reports completion (or ctx_sync). */
+int paris_b200_proj_h2d(paris_b200_ctx* ctx, const float* h_src, float* d_dst, uint32_t dim_x, uint32_t dim_y);
+/* nonzero *done when every H2D copy issued so far has finished */
+int paris_b200_h2d_done(paris_b200_ctx* ctx, int* done);
+/* copy_d2h(projection): returns when the data is in h_dst */
+int paris_b200_proj_d2h(paris_b200_ctx* ctx, const float* d_src, float* h_dst, uint32_t dim_x, uint32_t dim_y);
+/* copy_h2d / copy_d2h(volume).  vol_d2h first flushes pending backprojections into d_src
+ * (it is the only observer of the volume, sink.cpp:77) and returns when the data is in h_dst. */
+int paris_b200_vol_h2d(paris_b200_ctx* ctx, const float* h_src, float* d_dst, size_t n_voxels);
+int paris_b200_vol_d2h(paris_b200_ctx* ctx, const float* d_src, float* h_dst, size_t n_voxels);
+
+/* ---- pipeline stages --------------------------------------------------------------------- */
+
+/* backend::weight (src/openmp/weighting.cpp:32-57): in place,
+ * p[s + t*dim_x] *= d_sd / sqrt(d_sd^2 + h_s^2 + v_t^2) */
+int paris_b200_weight(paris_b200_ctx* ctx, float* d_proj, uint32_t dim_x, uint32_t dim_y,
+                      float h_min, float v_min, float d_sd, float l_px_row, float l_px_col);
+
+/* backend::make_filter (src/openmp/filtering.cpp:139-165): K[x] = tau*|DFT(r)[x]|, x = 0..size/2,
+ * r the spatial Ram-Lak taps of :52-73.  size must be a power of two, 32..8192. */
+int paris_b200_filter_create(paris_b200_ctx* ctx, uint32_t size, float tau, paris_b200_filter** filter);
+int paris_b200_filter_destroy(paris_b200_filter* filter);
+/* copy the size/2+1 table entries to the host (tests) */
+int paris_b200_filter_read(paris_b200_ctx* ctx, const paris_b200_filter* filter, float* h_k);
+
+/* backend::apply_filter (src/openmp/filtering.cpp:167-219): per detector row zero-pad to
+ * filter_size, DFT, scale by K, inverse DFT, keep the first dim_x samples, divide by filter_size.
+ * In place.  n_col must equal dim_y. */
+int paris_b200_apply_filter(paris_b200_ctx* ctx, float* d_proj, uint32_t dim_x, uint32_t dim_y,
+                            const paris_b200_filter* filter, uint32_t filter_size, uint32_t n_col);
+
+/* weight + apply_filter fused in one kernel (the weighted row never reaches HBM).  In place. */
+int paris_b200_weight_filter(paris_b200_ctx* ctx, float* d_proj, uint32_t dim_x, uint32_t dim_y,
+                             float h_min, float v_min, float d_sd, float l_px_row, float l_px_col,
+                             const paris_b200_filter* filter, uint32_t filter_size);
+
+/* backend::backproject (src/openmp/backprojection.cpp:156-199): accumulate one filtered projection
+ * into the slab d_vol (v_dim_x * v_dim_y * v_dim_z, x fastest).  vol_full is the FULL volume geometry;
+ * with enable_roi the voxel indices are shifted by (roi.x1, roi.y1, roi.z1); v_offset is the slab's z
+ * offset; sin/cos of the projection angle; delta_s/delta_t in millimetres (src/backprojection.cpp:49-50).
+ *
+ * DEFERRED: the projection is copied (transposed) into the context's filtered stack and the call
+ * returns; the volume is updated when the batch fills, on paris_b200_flush(), or when the volume is
+ * observed by paris_b200_vol_d2h().  d_proj may be freed (paris_b200_dev_free) right after the call.
+ * If flags has PARIS_B200_BP_FUSE_WEIGHT_FILTER, d_proj holds the RAW projection and weight + filter
+ * (with `filter`, using h_min/v_min/d_sd derived as src/weighting.cpp:37-42 does) are applied on the way
+ * into the stack by the fused kernel; d_proj itself is left untouched. */
+#define PARIS_B200_BP_FUSE_WEIGHT_FILTER 1u
+int paris_b200_backproject(paris_b200_ctx* ctx, const float* d_proj, uint32_t dim_x, uint32_t dim_y,
+                           float* d_vol, uint32_t v_dim_x, uint32_t v_dim_y, uint32_t v_dim_z, uint32_t v_offset,
+                           const paris_b200_detector_geometry* det, const paris_b200_volume_geometry* vol_full,
+                           int enable_roi, const paris_b200_roi* roi,
+                           float sin_phi, float cos_phi, float delta_s_mm, float delta_t_mm,
+                           uint32_t flags, const paris_b200_filter* filter);
+/* run every pending backprojection batch of the context (asynchronous on the compute stream) */
+int paris_b200_flush(paris_b200_ctx* ctx);
+
+/* ---- stack-level entry points (multi-GPU path: filter 1/N of the projections, all-gather the
+ *      stack, backproject all of them into the local slab) ---------------------------------- */
+
+/* Size in bytes of one stack slot (one filtered projection, TRANSPOSED: n_row lines of pitch floats,
+ * detector-row index fastest) and its pitch in floats. */
+int paris_b200_stack_slot_bytes(uint32_t n_row, uint32_t n_col, size_t* bytes, uint32_t* pitch);
+/* weight + filter a RAW device projection into slot `slot` of an external stack buffer */
+int paris_b200_filter_to_stack(paris_b200_ctx* ctx, const float* d_raw, const paris_b200_detector_geometry* det,
+                               const paris_b200_filter* filter, float* d_stack, uint32_t slot);
+/* backproject slots [first, first+count) of an external stack into d_vol; sin_phi/cos_phi are host
+ * arrays of `count` entries (slot first+i uses entry i). */
+int paris_b200_backproject_stack(paris_b200_ctx* ctx, const float* d_stack, uint32_t first, uint32_t count,
+                                 const float* sin_phi, const float* cos_phi,
+                                 float* d_vol, uint32_t v_dim_x, uint32_t v_dim_y, uint32_t v_dim_z,
+                                 uint32_t v_offset, const paris_b200_detector_geometry* det,
+                                 const paris_b200_volume_geometry* vol_full, int enable_roi,
+                                 const paris_b200_roi* roi);
+
+/* ---- synthetic input (bench / tests): analytic cone-beam line integrals of ellipsoids ------ */
+
+/* ellipsoids: n x 8 doubles {density, a, b, c, x0, y0, z0, theta_deg} in millimetres (host memory).
+ * Writes projections first_idx .. first_idx+n_proj-1 (angle = float(idx)*delta_phi) to d_stack_raw,
+ * n_proj x n_col x n_row floats, row-major. */
+int paris_b200_phantom_project(paris_b200_ctx* ctx, const double* ellipsoids, uint32_t n_ellipsoids,
+                               const paris_b200_detector_geometry* det, uint32_t first_idx, uint32_t n_proj,
+                               float* d_stack_raw);
+
+#ifdef __cplusplus
+}
+#endif
+
+#endif /* PARIS_B200_H_ */

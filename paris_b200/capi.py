@@ -1,0 +1,310 @@
+"""ctypes binding of the C ABI in include/paris_b200.h (libparis_b200.so).
+
+This is plumbing for tests/ and bench.py: every call below is a 1:1 forward to the C entry point of
+the same name.  There is no Python or CPU implementation behind it -- importing works without a GPU
+(so the symbol table can be checked), every compute call fails loudly without an sm_100a device.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import numpy as np
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libparis_b200.so")
+
+OK, EINVAL, ECUDA, ENOMEM, ESTATE = 0, 1, 2, 3, 4
+BP_FUSE_WEIGHT_FILTER = 1
+
+
+class DetectorGeometry(C.Structure):
+    _fields_ = [("n_row", C.c_uint32), ("n_col", C.c_uint32),
+                ("l_px_row", C.c_float), ("l_px_col", C.c_float),
+                ("delta_s", C.c_float), ("delta_t", C.c_float),
+                ("d_so", C.c_float), ("d_od", C.c_float), ("delta_phi", C.c_float)]
+
+
+class VolumeGeometry(C.Structure):
+    _fields_ = [("dim_x", C.c_uint32), ("dim_y", C.c_uint32), ("dim_z", C.c_uint32),
+                ("l_vx_x", C.c_float), ("l_vx_y", C.c_float), ("l_vx_z", C.c_float)]
+
+
+class Roi(C.Structure):
+    _fields_ = [("x1", C.c_uint32), ("x2", C.c_uint32), ("y1", C.c_uint32),
+                ("y2", C.c_uint32), ("z1", C.c_uint32), ("z2", C.c_uint32)]
+
+
+class SubvolumeInfo(C.Structure):
+    _fields_ = [("dim_x", C.c_uint32), ("dim_y", C.c_uint32), ("dim_z", C.c_uint32),
+                ("remainder", C.c_uint32), ("num", C.c_int32)]
+
+
+class Error(RuntimeError):
+    def __init__(self, code: int, text: str):
+        super().__init__(f"paris_b200 error {code}: {text}")
+        self.code = code
+
+
+_P = C.POINTER
+_vp = C.c_void_p
+_fp = C.c_void_p      # device / host float pointers travel as integers
+_u32 = C.c_uint32
+_f = C.c_float
+
+# name -> (restype, argtypes); must list EVERY symbol include/paris_b200.h declares (tests check that)
+SIGNATURES = {
+    "paris_b200_last_error": (C.c_char_p, []),
+    "paris_b200_version": (C.c_char_p, []),
+    "paris_b200_device_count": (C.c_int, [_P(C.c_int)]),
+    "paris_b200_ctx_create": (C.c_int, [C.c_int, _P(_vp)]),
+    "paris_b200_ctx_destroy": (C.c_int, [_vp]),
+    "paris_b200_ctx_device": (C.c_int, [_vp, _P(C.c_int)]),
+    "paris_b200_ctx_bind": (C.c_int, [_vp]),
+    "paris_b200_ctx_sync": (C.c_int, [_vp]),
+    "paris_b200_ctx_stream": (C.c_int, [_vp, _P(_vp)]),
+    "paris_b200_ctx_launch_count": (C.c_int, [_vp, _P(C.c_uint64)]),
+    "paris_b200_ctx_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
+    "paris_b200_calculate_volume_geometry": (C.c_int, [_P(DetectorGeometry), _P(VolumeGeometry)]),
+    "paris_b200_apply_roi": (C.c_int, [_P(VolumeGeometry), _P(Roi), _P(VolumeGeometry)]),
+    "paris_b200_filter_size": (_u32, [_u32]),
+    "paris_b200_make_subvolume_information": (C.c_int, [_vp, _P(VolumeGeometry), _P(DetectorGeometry), C.c_int,
+                                                        _P(SubvolumeInfo)]),
+    "paris_b200_host_alloc": (C.c_int, [C.c_size_t, C.c_int, _P(_vp)]),
+    "paris_b200_host_free": (C.c_int, [_vp]),
+    "paris_b200_dev_alloc": (C.c_int, [_vp, C.c_size_t, _P(_vp)]),
+    "paris_b200_dev_free": (C.c_int, [_vp, _vp]),
+    "paris_b200_volume_alloc": (C.c_int, [_vp, _u32, _u32, _u32, _P(_vp)]),
+    "paris_b200_volume_free": (C.c_int, [_vp, _fp]),
+    "paris_b200_proj_h2d": (C.c_int, [_vp, _fp, _fp, _u32, _u32]),
+    "paris_b200_h2d_done": (C.c_int, [_vp, _P(C.c_int)]),
+    "paris_b200_proj_d2h": (C.c_int, [_vp, _fp, _fp, _u32, _u32]),
+    "paris_b200_vol_h2d": (C.c_int, [_vp, _fp, _fp, C.c_size_t]),
+    "paris_b200_vol_d2h": (C.c_int, [_vp, _fp, _fp, C.c_size_t]),
+    "paris_b200_weight": (C.c_int, [_vp, _fp, _u32, _u32, _f, _f, _f, _f, _f]),
+    "paris_b200_filter_create": (C.c_int, [_vp, _u32, _f, _P(_vp)]),
+    "paris_b200_filter_destroy": (C.c_int, [_vp]),
+    "paris_b200_filter_read": (C.c_int, [_vp, _vp, _fp]),
+    "paris_b200_apply_filter": (C.c_int, [_vp, _fp, _u32, _u32, _vp, _u32, _u32]),
+    "paris_b200_weight_filter": (C.c_int, [_vp, _fp, _u32, _u32, _f, _f, _f, _f, _f, _vp, _u32]),
+    "paris_b200_backproject": (C.c_int, [_vp, _fp, _u32, _u32, _fp, _u32, _u32, _u32, _u32, _P(DetectorGeometry),
+                                         _P(VolumeGeometry), C.c_int, _P(Roi), _f, _f, _f, _f, _u32, _vp]),
+    "paris_b200_flush": (C.c_int, [_vp]),
+    "paris_b200_stack_slot_bytes": (C.c_int, [_u32, _u32, _P(C.c_size_t), _P(_u32)]),
+    "paris_b200_filter_to_stack": (C.c_int, [_vp, _fp, _P(DetectorGeometry), _vp, _fp, _u32]),
+    "paris_b200_backproject_stack": (C.c_int, [_vp, _fp, _u32, _u32, _P(_f), _P(_f), _fp, _u32, _u32, _u32, _u32,
+                                               _P(DetectorGeometry), _P(VolumeGeometry), C.c_int, _P(Roi)]),
+    "paris_b200_phantom_project": (C.c_int, [_vp, _P(C.c_double), _u32, _P(DetectorGeometry), _u32, _u32, _fp]),
+}
+
+_lib = None
+
+
+def lib() -> C.CDLL:
+    """Load libparis_b200.so (built by `make lib` / __graft_entry__.build()).  No fallback."""
+    global _lib
+    if _lib is None:
+        if not os.path.exists(LIB_PATH):
+            raise ImportError(f"{LIB_PATH} is missing: run `make lib` (or __graft_entry__.build()); "
+                              "paris_b200 has no CPU fallback")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int) -> None:
+    if rc != OK:
+        raise Error(rc, lib().paris_b200_last_error().decode())
+
+
+def _ptr(a) -> int:
+    """Address of a numpy array's data, or pass an integer device pointer through."""
+    if isinstance(a, np.ndarray):
+        assert a.flags["C_CONTIGUOUS"]
+        return a.ctypes.data
+    return int(a)
+
+
+def device_count() -> int:
+    n = C.c_int(0)
+    check(lib().paris_b200_device_count(C.byref(n)))
+    return n.value
+
+
+def filter_size(n_row: int) -> int:
+    return int(lib().paris_b200_filter_size(n_row))
+
+
+def calculate_volume_geometry(det: DetectorGeometry) -> VolumeGeometry:
+    out = VolumeGeometry()
+    check(lib().paris_b200_calculate_volume_geometry(C.byref(det), C.byref(out)))
+    return out
+
+
+def apply_roi(vol: VolumeGeometry, roi: Roi) -> VolumeGeometry:
+    out = VolumeGeometry()
+    check(lib().paris_b200_apply_roi(C.byref(vol), C.byref(roi), C.byref(out)))
+    return out
+
+
+def stack_slot_bytes(n_row: int, n_col: int):
+    b, p = C.c_size_t(0), _u32(0)
+    check(lib().paris_b200_stack_slot_bytes(n_row, n_col, C.byref(b), C.byref(p)))
+    return b.value, p.value
+
+
+class PinnedArray:
+    """A float32 numpy view over pinned host memory from paris_b200_host_alloc."""
+
+    def __init__(self, shape, zero=False):
+        n = int(np.prod(shape))
+        p = _vp()
+        check(lib().paris_b200_host_alloc(n * 4, int(zero), C.byref(p)))
+        self.ptr = p.value
+        self.array = np.ctypeslib.as_array((C.c_float * n).from_address(self.ptr)).reshape(shape)
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            check(lib().paris_b200_host_free(self.ptr))
+            self.ptr = 0
+
+
+class Context:
+    """One per device; thin object wrapper over the paris_b200_ctx_* / stage entry points."""
+
+    def __init__(self, device: int = 0):
+        self._L = lib()
+        h = _vp()
+        check(self._L.paris_b200_ctx_create(device, C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def close(self):
+        if self.h:
+            check(self._L.paris_b200_ctx_destroy(self.h))
+            self.h = None
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *exc):
+        self.close()
+
+    # -- plumbing
+    def sync(self):
+        check(self._L.paris_b200_ctx_sync(self.h))
+
+    def stream(self) -> int:
+        s = _vp()
+        check(self._L.paris_b200_ctx_stream(self.h, C.byref(s)))
+        return s.value or 0
+
+    def launch_count(self) -> int:
+        n = C.c_uint64(0)
+        check(self._L.paris_b200_ctx_launch_count(self.h, C.byref(n)))
+        return n.value
+
+    def set_option(self, name: str, value: int):
+        check(self._L.paris_b200_ctx_set_option(self.h, name.encode(), value))
+
+    def make_subvolume_information(self, vol: VolumeGeometry, det: DetectorGeometry, num_slabs: int) -> SubvolumeInfo:
+        out = SubvolumeInfo()
+        check(self._L.paris_b200_make_subvolume_information(self.h, C.byref(vol), C.byref(det), num_slabs,
+                                                            C.byref(out)))
+        return out
+
+    # -- memory
+    def dev_alloc(self, nbytes: int) -> int:
+        p = _vp()
+        check(self._L.paris_b200_dev_alloc(self.h, nbytes, C.byref(p)))
+        return p.value
+
+    def dev_free(self, d_ptr: int):
+        check(self._L.paris_b200_dev_free(self.h, d_ptr))
+
+    def volume_alloc(self, dim_x: int, dim_y: int, dim_z: int) -> int:
+        p = _vp()
+        check(self._L.paris_b200_volume_alloc(self.h, dim_x, dim_y, dim_z, C.byref(p)))
+        return p.value
+
+    def volume_free(self, d_vol: int):
+        check(self._L.paris_b200_volume_free(self.h, d_vol))
+
+    def proj_h2d(self, h_src, d_dst: int, dim_x: int, dim_y: int):
+        check(self._L.paris_b200_proj_h2d(self.h, _ptr(h_src), d_dst, dim_x, dim_y))
+
+    def h2d_done(self) -> bool:
+        d = C.c_int(0)
+        check(self._L.paris_b200_h2d_done(self.h, C.byref(d)))
+        return bool(d.value)
+
+    def proj_d2h(self, d_src: int, h_dst, dim_x: int, dim_y: int):
+        check(self._L.paris_b200_proj_d2h(self.h, d_src, _ptr(h_dst), dim_x, dim_y))
+
+    def vol_h2d(self, h_src, d_dst: int, n_voxels: int):
+        check(self._L.paris_b200_vol_h2d(self.h, _ptr(h_src), d_dst, n_voxels))
+
+    def vol_d2h(self, d_src: int, h_dst, n_voxels: int):
+        check(self._L.paris_b200_vol_d2h(self.h, d_src, _ptr(h_dst), n_voxels))
+
+    # -- stages
+    def weight(self, d_proj: int, dim_x: int, dim_y: int, h_min, v_min, d_sd, l_px_row, l_px_col):
+        check(self._L.paris_b200_weight(self.h, d_proj, dim_x, dim_y, h_min, v_min, d_sd, l_px_row, l_px_col))
+
+    def filter_create(self, size: int, tau: float) -> int:
+        f = _vp()
+        check(self._L.paris_b200_filter_create(self.h, size, tau, C.byref(f)))
+        return f.value
+
+    def filter_destroy(self, f: int):
+        check(self._L.paris_b200_filter_destroy(f))
+
+    def filter_read(self, f: int, size: int) -> np.ndarray:
+        k = np.zeros(size // 2 + 1, dtype=np.float32)
+        check(self._L.paris_b200_filter_read(self.h, f, _ptr(k)))
+        return k
+
+    def apply_filter(self, d_proj: int, dim_x: int, dim_y: int, f: int, size: int, n_col: int):
+        check(self._L.paris_b200_apply_filter(self.h, d_proj, dim_x, dim_y, f, size, n_col))
+
+    def weight_filter(self, d_proj: int, dim_x: int, dim_y: int, h_min, v_min, d_sd, l_px_row, l_px_col, f: int,
+                      size: int):
+        check(self._L.paris_b200_weight_filter(self.h, d_proj, dim_x, dim_y, h_min, v_min, d_sd, l_px_row, l_px_col,
+                                               f, size))
+
+    def backproject(self, d_proj: int, dim_x: int, dim_y: int, d_vol: int, v_dims, v_offset: int,
+                    det: DetectorGeometry, vol_full: VolumeGeometry, roi: Roi | None, sin_phi: float, cos_phi: float,
+                    delta_s_mm: float, delta_t_mm: float, flags: int = 0, filt: int | None = None):
+        check(self._L.paris_b200_backproject(self.h, d_proj, dim_x, dim_y, d_vol, v_dims[0], v_dims[1], v_dims[2],
+                                             v_offset, C.byref(det), C.byref(vol_full), int(roi is not None),
+                                             C.byref(roi) if roi is not None else None, sin_phi, cos_phi,
+                                             delta_s_mm, delta_t_mm, flags, filt))
+
+    def flush(self):
+        check(self._L.paris_b200_flush(self.h))
+
+    def filter_to_stack(self, d_raw: int, det: DetectorGeometry, filt: int, d_stack: int, slot: int):
+        check(self._L.paris_b200_filter_to_stack(self.h, d_raw, C.byref(det), filt, d_stack, slot))
+
+    def backproject_stack(self, d_stack: int, first: int, count: int, sin_phi: np.ndarray, cos_phi: np.ndarray,
+                          d_vol: int, v_dims, v_offset: int, det: DetectorGeometry, vol_full: VolumeGeometry,
+                          roi: Roi | None = None):
+        sn = np.ascontiguousarray(sin_phi, dtype=np.float32)
+        cs = np.ascontiguousarray(cos_phi, dtype=np.float32)
+        assert sn.size >= count and cs.size >= count
+        check(self._L.paris_b200_backproject_stack(self.h, d_stack, first, count,
+                                                   sn.ctypes.data_as(_P(_f)), cs.ctypes.data_as(_P(_f)),
+                                                   d_vol, v_dims[0], v_dims[1], v_dims[2], v_offset,
+                                                   C.byref(det), C.byref(vol_full), int(roi is not None),
+                                                   C.byref(roi) if roi is not None else None))
+
+    def phantom_project(self, ellipsoids_mm: np.ndarray, det: DetectorGeometry, first_idx: int, n_proj: int,
+                        d_stack_raw: int):
+        e = np.ascontiguousarray(ellipsoids_mm, dtype=np.float64)
+        check(self._L.paris_b200_phantom_project(self.h, e.ctypes.data_as(_P(C.c_double)), e.shape[0], C.byref(det),
+                                                 first_idx, n_proj, d_stack_raw))

@@ -1,0 +1,757 @@
+// api.cu -- the C ABI of include/paris_b200.h: contexts, memory, geometry, filter tables and the
+// deferred-backprojection bookkeeping.  The kernels live in weight.cu / filter.cu / backproject.cu.
+#include "common.cuh"
+
+#include <cmath>
+#include <cstdarg>
+#include <complex>
+
+namespace pb
+{
+    static thread_local char g_error[512] = "";
+
+    void set_error(const char* fmt, ...)
+    {
+        va_list ap;
+        va_start(ap, fmt);
+        vsnprintf(g_error, sizeof(g_error), fmt, ap);
+        va_end(ap);
+    }
+
+    static int bind(const paris_b200_ctx* ctx)
+    {
+        PB_CUDA(cudaSetDevice(ctx->device));
+        return PARIS_B200_OK;
+    }
+}
+
+using namespace pb;
+
+extern "C" const char* paris_b200_last_error(void) { return pb::g_error; }
+extern "C" const char* paris_b200_version(void) { return "paris_b200 0.1 (sm_100a)"; }
+
+// ---- devices / contexts -----------------------------------------------------------------------------------
+
+extern "C" int paris_b200_device_count(int* count)
+{
+    PB_CHECK_ARG(count != nullptr);
+    *count = 0;
+    PB_CUDA(cudaGetDeviceCount(count));
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_ctx_create(int device, paris_b200_ctx** out)
+{
+    PB_CHECK_ARG(out != nullptr);
+    *out = nullptr;
+    int n = 0;
+    PB_CUDA(cudaGetDeviceCount(&n));
+    PB_CHECK_ARG(device >= 0 && device < n);
+    PB_CUDA(cudaSetDevice(device));
+    cudaDeviceProp prop{};
+    PB_CUDA(cudaGetDeviceProperties(&prop, device));
+    if(prop.major != 10)
+    {
+        set_error("device %d is sm_%d%d; this library only carries sm_100a code (no fallback)", device, prop.major,
+                  prop.minor);
+        return PARIS_B200_ECUDA;
+    }
+    auto* ctx = new paris_b200_ctx{};
+    ctx->device = device;
+    ctx->sm_count = prop.multiProcessorCount;
+    PB_CUDA(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
+    PB_CUDA(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
+    PB_CUDA(cudaEventCreateWithFlags(&ctx->h2d_done, cudaEventDisableTiming));
+    PB_CUDA(cudaEventCreateWithFlags(&ctx->scratch_ev, cudaEventDisableTiming));
+    *out = ctx;
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_ctx_destroy(paris_b200_ctx* ctx)
+{
+    if(ctx == nullptr)
+        return PARIS_B200_OK;
+    PB_TRY(bind(ctx));
+    cudaStreamSynchronize(ctx->compute);
+    cudaStreamSynchronize(ctx->copy);
+    for(auto& b : ctx->pool)
+    {
+        if(b.ptr) cudaFree(b.ptr);
+        if(b.freed) cudaEventDestroy(b.freed);
+    }
+    if(ctx->stack) cudaFree(ctx->stack);
+    cudaEventDestroy(ctx->h2d_done);
+    cudaEventDestroy(ctx->scratch_ev);
+    cudaStreamDestroy(ctx->compute);
+    cudaStreamDestroy(ctx->copy);
+    delete ctx;
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_ctx_device(const paris_b200_ctx* ctx, int* device)
+{
+    PB_CHECK_ARG(ctx != nullptr && device != nullptr);
+    *device = ctx->device;
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_ctx_bind(paris_b200_ctx* ctx)
+{
+    PB_CHECK_ARG(ctx != nullptr);
+    return bind(ctx);
+}
+
+extern "C" int paris_b200_ctx_sync(paris_b200_ctx* ctx)
+{
+    PB_CHECK_ARG(ctx != nullptr);
+    PB_TRY(bind(ctx));
+    PB_CUDA(cudaStreamSynchronize(ctx->copy));
+    PB_CUDA(cudaStreamSynchronize(ctx->compute));
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_ctx_stream(paris_b200_ctx* ctx, void** stream)
+{
+    PB_CHECK_ARG(ctx != nullptr && stream != nullptr);
+    *stream = static_cast<void*>(ctx->compute);
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_ctx_launch_count(const paris_b200_ctx* ctx, uint64_t* launches)
+{
+    PB_CHECK_ARG(ctx != nullptr && launches != nullptr);
+    *launches = ctx->launches;
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_ctx_set_option(paris_b200_ctx* ctx, const char* name, int64_t value)
+{
+    PB_CHECK_ARG(ctx != nullptr && name != nullptr);
+    if(std::strcmp(name, "bp_batch") == 0)
+    {
+        PB_CHECK_ARG(value >= 1 && value <= kMaxBatch);
+        PB_TRY(paris_b200_flush(ctx));
+        if(ctx->stack != nullptr && static_cast<uint32_t>(value) > ctx->stack_slots)
+        {
+            PB_TRY(bind(ctx));
+            PB_CUDA(cudaStreamSynchronize(ctx->compute));
+            PB_CUDA(cudaFree(ctx->stack));
+            ctx->stack = nullptr;
+            ctx->stack_slots = 0;
+            ctx->tma.valid = false;
+        }
+        ctx->bp_batch = static_cast<int>(value);
+        return PARIS_B200_OK;
+    }
+    if(std::strcmp(name, "bp_kernel") == 0)
+    {
+        PB_CHECK_ARG(value >= 0 && value <= 2);
+        PB_TRY(paris_b200_flush(ctx));
+        ctx->bp_kernel = static_cast<int>(value);
+        return PARIS_B200_OK;
+    }
+    set_error("unknown option '%s'", name);
+    return PARIS_B200_EINVAL;
+}
+
+// ---- geometry (host arithmetic; same float expressions as the reference) -----------------------------------
+
+// src/geometry.cpp:36-67
+extern "C" int paris_b200_calculate_volume_geometry(const paris_b200_detector_geometry* det,
+                                                    paris_b200_volume_geometry* vol)
+{
+    PB_CHECK_ARG(det != nullptr && vol != nullptr);
+    const float n_row = static_cast<float>(det->n_row);
+    const float n_col = static_cast<float>(det->n_col);
+    const float off_s = std::fabs(det->delta_s * det->l_px_row);
+    const float off_t = std::fabs(det->delta_t * det->l_px_col);
+    const float d_so = std::fabs(det->d_so);
+    const float d_sd = std::fabs(det->d_od) + d_so;
+
+    const float half_width = ((n_row * det->l_px_row) / 2.f) + off_s;
+    const float alpha = std::atan(half_width / d_sd);
+    const float r = d_so * std::sin(alpha);
+
+    vol->l_vx_x = r / (half_width / det->l_px_row);
+    vol->l_vx_y = vol->l_vx_x;
+    vol->l_vx_z = vol->l_vx_x;
+    vol->dim_x = static_cast<uint32_t>((2.f * r) / vol->l_vx_x);
+    vol->dim_y = vol->dim_x;
+    vol->dim_z = static_cast<uint32_t>(((n_col * det->l_px_col / 2.f) + off_t) * (d_so / d_sd) * (2.f / vol->l_vx_z));
+    return PARIS_B200_OK;
+}
+
+// src/geometry.cpp:86-130
+extern "C" int paris_b200_apply_roi(const paris_b200_volume_geometry* vol, const paris_b200_roi* roi,
+                                    paris_b200_volume_geometry* out)
+{
+    PB_CHECK_ARG(vol != nullptr && roi != nullptr && out != nullptr);
+    *out = *vol;
+    if(!(roi->x1 < roi->x2 && roi->y1 < roi->y2 && roi->z1 < roi->z2))
+        return PARIS_B200_OK; // "Invalid ROI coordinates. ROI NOT applied."
+    const uint32_t dx = roi->x2 - roi->x1 + (roi->x1 == 0 ? 1u : 0u);
+    const uint32_t dy = roi->y2 - roi->y1 + (roi->y1 == 0 ? 1u : 0u);
+    const uint32_t dz = roi->z2 - roi->z1 + (roi->z1 == 0 ? 1u : 0u);
+    if(dx <= vol->dim_x && dy <= vol->dim_y && dz <= vol->dim_z)
+    {
+        out->dim_x = dx;
+        out->dim_y = dy;
+        out->dim_z = dz;
+    }
+    return PARIS_B200_OK;
+}
+
+// src/filtering.cpp:38
+extern "C" uint32_t paris_b200_filter_size(uint32_t n_row)
+{
+    return static_cast<uint32_t>(2 * std::pow(2.f, std::ceil(std::log2(n_row))));
+}
+
+// src/cuda/subvolume_information.cpp:63-118
+extern "C" int paris_b200_make_subvolume_information(paris_b200_ctx* ctx, const paris_b200_volume_geometry* vol,
+                                                     const paris_b200_detector_geometry* det, int num_slabs,
+                                                     paris_b200_subvolume_info* out)
+{
+    PB_CHECK_ARG(vol != nullptr && det != nullptr && out != nullptr && num_slabs >= 0);
+    uint32_t slabs = static_cast<uint32_t>(num_slabs);
+    if(slabs == 0)
+    {
+        PB_CHECK_ARG(ctx != nullptr);
+        PB_TRY(bind(ctx));
+        // 64-bit byte counts (the reference's 32-bit product overflows at >= 4 GiB)
+        const size_t vol_bytes = static_cast<size_t>(vol->dim_x) * vol->dim_y * vol->dim_z * sizeof(float);
+        const size_t proj_bytes = static_cast<size_t>(det->n_row) * det->n_col * sizeof(float);
+        size_t need = vol_bytes + 10u * proj_bytes;
+        size_t mem_free = 0, mem_total = 0;
+        PB_CUDA(cudaMemGetInfo(&mem_free, &mem_total));
+        slabs = 1;
+        while(need >= mem_free && slabs < vol->dim_z)
+        {
+            need /= 2;
+            slabs *= 2;
+        }
+    }
+    PB_CHECK_ARG(slabs >= 1 && slabs <= vol->dim_z);
+    out->dim_x = vol->dim_x;
+    out->dim_y = vol->dim_y;
+    out->dim_z = vol->dim_z / slabs;
+    out->remainder = vol->dim_z % slabs;
+    out->num = static_cast<int32_t>(slabs);
+    return PARIS_B200_OK;
+}
+
+// ---- memory ----------------------------------------------------------------------------------------------
+
+extern "C" int paris_b200_host_alloc(size_t bytes, int zero, void** h_ptr)
+{
+    PB_CHECK_ARG(h_ptr != nullptr && bytes > 0);
+    *h_ptr = nullptr;
+    PB_CUDA(cudaHostAlloc(h_ptr, bytes, cudaHostAllocPortable));
+    if(zero)
+        std::memset(*h_ptr, 0, bytes);
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_host_free(void* h_ptr)
+{
+    if(h_ptr != nullptr)
+        PB_CUDA(cudaFreeHost(h_ptr));
+    return PARIS_B200_OK;
+}
+
+static pb::raw_buffer* find_buffer(paris_b200_ctx* ctx, const void* p)
+{
+    for(auto& b : ctx->pool)
+        if(b.ptr == p)
+            return &b;
+    return nullptr;
+}
+
+extern "C" int paris_b200_dev_alloc(paris_b200_ctx* ctx, size_t bytes, void** d_ptr)
+{
+    PB_CHECK_ARG(ctx != nullptr && d_ptr != nullptr && bytes > 0);
+    PB_TRY(bind(ctx));
+    *d_ptr = nullptr;
+    // 1st choice: a free buffer of this size whose last reader has already finished
+    pb::raw_buffer* oldest = nullptr;
+    size_t same_size = 0;
+    for(auto& b : ctx->pool)
+    {
+        if(b.bytes != bytes)
+            continue;
+        ++same_size;
+        if(b.in_use)
+            continue;
+        if(!b.freed_valid || cudaEventQuery(b.freed) == cudaSuccess)
+        {
+            b.in_use = true;
+            b.freed_valid = false;
+            *d_ptr = b.ptr;
+            return PARIS_B200_OK;
+        }
+        if(oldest == nullptr)
+            oldest = &b;
+    }
+    (void)cudaGetLastError(); // cudaEventQuery's cudaErrorNotReady is not an error
+    // 2nd: grow the pool while it is small, so uploads can run ahead of a backprojection batch
+    const size_t cap = 2u * static_cast<size_t>(ctx->bp_batch) + 2u;
+    if(oldest == nullptr || same_size < cap)
+    {
+        pb::raw_buffer b{};
+        PB_CUDA(cudaMalloc(&b.ptr, bytes));
+        PB_CUDA(cudaEventCreateWithFlags(&b.freed, cudaEventDisableTiming));
+        b.bytes = bytes;
+        b.in_use = true;
+        ctx->pool.push_back(b);
+        *d_ptr = b.ptr;
+        return PARIS_B200_OK;
+    }
+    // 3rd: reuse a buffer still being read; the copy stream waits for its `freed` event in proj_h2d
+    oldest->in_use = true;
+    *d_ptr = oldest->ptr;
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_dev_free(paris_b200_ctx* ctx, void* d_ptr)
+{
+    PB_CHECK_ARG(ctx != nullptr);
+    if(d_ptr == nullptr)
+        return PARIS_B200_OK;
+    PB_TRY(bind(ctx));
+    auto* b = find_buffer(ctx, d_ptr);
+    if(b == nullptr || !b->in_use)
+    {
+        set_error("dev_free: %p was not allocated by this context", d_ptr);
+        return PARIS_B200_EINVAL;
+    }
+    PB_CUDA(cudaEventRecord(b->freed, ctx->compute));
+    b->freed_valid = true;
+    b->in_use = false;
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_volume_alloc(paris_b200_ctx* ctx, uint32_t dim_x, uint32_t dim_y, uint32_t dim_z,
+                                       float** d_vol)
+{
+    PB_CHECK_ARG(ctx != nullptr && d_vol != nullptr && dim_x > 0 && dim_y > 0 && dim_z > 0);
+    PB_TRY(bind(ctx));
+    const size_t bytes = static_cast<size_t>(dim_x) * dim_y * dim_z * sizeof(float);
+    *d_vol = nullptr;
+    PB_CUDA(cudaMalloc(reinterpret_cast<void**>(d_vol), bytes));
+    PB_CUDA(cudaMemsetAsync(*d_vol, 0, bytes, ctx->compute));
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_volume_free(paris_b200_ctx* ctx, float* d_vol)
+{
+    PB_CHECK_ARG(ctx != nullptr);
+    if(d_vol == nullptr)
+        return PARIS_B200_OK;
+    PB_TRY(bind(ctx));
+    if(ctx->pending > 0 && ctx->target.d_vol == d_vol)
+        ctx->pending = 0; // nobody can observe the result any more
+    PB_CUDA(cudaStreamSynchronize(ctx->compute));
+    PB_CUDA(cudaFree(d_vol));
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_proj_h2d(paris_b200_ctx* ctx, const float* h_src, float* d_dst, uint32_t dim_x,
+                                   uint32_t dim_y)
+{
+    PB_CHECK_ARG(ctx != nullptr && h_src != nullptr && d_dst != nullptr && dim_x > 0 && dim_y > 0);
+    PB_TRY(bind(ctx));
+    const size_t bytes = static_cast<size_t>(dim_x) * dim_y * sizeof(float);
+    auto* b = find_buffer(ctx, d_dst);
+    if(b != nullptr && b->freed_valid)
+    {
+        // pooled buffer recycled while its previous reader may still run
+        PB_CUDA(cudaStreamWaitEvent(ctx->copy, b->freed, 0));
+    }
+    else if(b == nullptr)
+    {
+        // foreign destination: order after everything queued on the compute stream
+        PB_CUDA(cudaEventRecord(ctx->scratch_ev, ctx->compute));
+        PB_CUDA(cudaStreamWaitEvent(ctx->copy, ctx->scratch_ev, 0));
+    }
+    PB_CUDA(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, ctx->copy));
+    PB_CUDA(cudaEventRecord(ctx->h2d_done, ctx->copy));
+    ctx->h2d_any = true;
+    PB_CUDA(cudaStreamWaitEvent(ctx->compute, ctx->h2d_done, 0));
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_h2d_done(paris_b200_ctx* ctx, int* done)
+{
+    PB_CHECK_ARG(ctx != nullptr && done != nullptr);
+    PB_TRY(bind(ctx));
+    *done = 1;
+    if(ctx->h2d_any)
+    {
+        const cudaError_t e = cudaEventQuery(ctx->h2d_done);
+        if(e == cudaErrorNotReady)
+        {
+            (void)cudaGetLastError();
+            *done = 0;
+        }
+        else
+            PB_CUDA(e);
+    }
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_proj_d2h(paris_b200_ctx* ctx, const float* d_src, float* h_dst, uint32_t dim_x,
+                                   uint32_t dim_y)
+{
+    PB_CHECK_ARG(ctx != nullptr && d_src != nullptr && h_dst != nullptr);
+    PB_TRY(bind(ctx));
+    const size_t bytes = static_cast<size_t>(dim_x) * dim_y * sizeof(float);
+    PB_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->compute));
+    PB_CUDA(cudaStreamSynchronize(ctx->compute));
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_vol_h2d(paris_b200_ctx* ctx, const float* h_src, float* d_dst, size_t n_voxels)
+{
+    PB_CHECK_ARG(ctx != nullptr && h_src != nullptr && d_dst != nullptr);
+    PB_TRY(bind(ctx));
+    PB_TRY(paris_b200_flush(ctx));
+    PB_CUDA(cudaMemcpyAsync(d_dst, h_src, n_voxels * sizeof(float), cudaMemcpyHostToDevice, ctx->compute));
+    PB_CUDA(cudaStreamSynchronize(ctx->compute));
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_vol_d2h(paris_b200_ctx* ctx, const float* d_src, float* h_dst, size_t n_voxels)
+{
+    PB_CHECK_ARG(ctx != nullptr && d_src != nullptr && h_dst != nullptr);
+    PB_TRY(bind(ctx));
+    PB_TRY(paris_b200_flush(ctx));
+    PB_CUDA(cudaMemcpyAsync(h_dst, d_src, n_voxels * sizeof(float), cudaMemcpyDeviceToHost, ctx->compute));
+    PB_CUDA(cudaStreamSynchronize(ctx->compute));
+    return PARIS_B200_OK;
+}
+
+// ---- filter table ------------------------------------------------------------------------------------------
+
+namespace
+{
+    // radix-2 decimation-in-time FFT in double, host side, used once per filter
+    void host_fft(std::vector<std::complex<double>>& a)
+    {
+        const size_t n = a.size();
+        for(size_t i = 1, j = 0; i < n; ++i)
+        {
+            size_t bit = n >> 1;
+            for(; j & bit; bit >>= 1)
+                j ^= bit;
+            j ^= bit;
+            if(i < j)
+                std::swap(a[i], a[j]);
+        }
+        for(size_t len = 2; len <= n; len <<= 1)
+        {
+            for(size_t i = 0; i < n; i += len)
+                for(size_t k = 0; k < len / 2; ++k)
+                {
+                    const double ang = -2.0 * M_PI * static_cast<double>(k) / static_cast<double>(len);
+                    const std::complex<double> w(std::cos(ang), std::sin(ang));
+                    const auto u = a[i + k];
+                    const auto v = a[i + k + len / 2] * w;
+                    a[i + k] = u + v;
+                    a[i + k + len / 2] = u - v;
+                }
+        }
+    }
+}
+
+extern "C" int paris_b200_filter_create(paris_b200_ctx* ctx, uint32_t size, float tau, paris_b200_filter** out)
+{
+    PB_CHECK_ARG(ctx != nullptr && out != nullptr);
+    PB_CHECK_ARG(size >= 32 && size <= 8192 && (size & (size - 1)) == 0);
+    PB_CHECK_ARG(tau > 0.f);
+    PB_TRY(bind(ctx));
+    *out = nullptr;
+
+    // spatial taps in float, exactly as src/openmp/filtering.cpp:52-73 writes them
+    std::vector<std::complex<double>> r(size);
+    const int32_t j0 = -(static_cast<int32_t>(size) - 2) / 2;
+    const float pi_f = static_cast<float>(M_PI);
+    for(uint32_t x = 0; x < size; ++x)
+    {
+        const int32_t j = j0 + static_cast<int32_t>(x);
+        float tap;
+        if(j == 0)
+            tap = (1.f / 8.f) * (1.f / std::pow(tau, 2.f));
+        else if(j % 2 == 0)
+            tap = 0.f;
+        else
+            tap = -(1.f / (2.f * static_cast<float>(j * j) * (pi_f * pi_f) * (tau * tau)));
+        r[x] = std::complex<double>(static_cast<double>(tap), 0.0);
+    }
+    host_fft(r);
+
+    // K[x] = tau * |R[x]| on the float-rounded transform (:155-162); K/N is exact (N = 2^k)
+    const uint32_t n_trans = size / 2 + 1;
+    std::vector<float> k(n_trans), kn(n_trans);
+    for(uint32_t x = 0; x < n_trans; ++x)
+    {
+        const float re = static_cast<float>(r[x].real());
+        const float im = static_cast<float>(r[x].imag());
+        k[x] = tau * std::abs(std::sqrt(std::pow(re, 2.f) + std::pow(im, 2.f)));
+        kn[x] = k[x] / static_cast<float>(size);
+    }
+    std::vector<float2> tw(size);
+    for(uint32_t i = 0; i < size; ++i)
+    {
+        const double ang = -2.0 * M_PI * static_cast<double>(i) / static_cast<double>(size);
+        tw[i] = make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang)));
+    }
+
+    auto* f = new paris_b200_filter{};
+    f->device = ctx->device;
+    f->size = size;
+    f->tau = tau;
+    PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&f->d_k), n_trans * sizeof(float)));
+    PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&f->d_kn), n_trans * sizeof(float)));
+    PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&f->d_tw), size * sizeof(float2)));
+    PB_CUDA(cudaMemcpy(f->d_k, k.data(), n_trans * sizeof(float), cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(f->d_kn, kn.data(), n_trans * sizeof(float), cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMemcpy(f->d_tw, tw.data(), size * sizeof(float2), cudaMemcpyHostToDevice));
+    *out = f;
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_filter_destroy(paris_b200_filter* f)
+{
+    if(f == nullptr)
+        return PARIS_B200_OK;
+    PB_CUDA(cudaSetDevice(f->device));
+    cudaFree(f->d_k);
+    cudaFree(f->d_kn);
+    cudaFree(f->d_tw);
+    delete f;
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_filter_read(paris_b200_ctx* ctx, const paris_b200_filter* f, float* h_k)
+{
+    PB_CHECK_ARG(ctx != nullptr && f != nullptr && h_k != nullptr);
+    PB_TRY(bind(ctx));
+    PB_CUDA(cudaMemcpy(h_k, f->d_k, (f->size / 2 + 1) * sizeof(float), cudaMemcpyDeviceToHost));
+    return PARIS_B200_OK;
+}
+
+// ---- stages ------------------------------------------------------------------------------------------------
+
+extern "C" int paris_b200_weight(paris_b200_ctx* ctx, float* d_proj, uint32_t dim_x, uint32_t dim_y, float h_min,
+                                 float v_min, float d_sd, float l_px_row, float l_px_col)
+{
+    PB_CHECK_ARG(ctx != nullptr && d_proj != nullptr && dim_x > 0 && dim_y > 0);
+    PB_TRY(bind(ctx));
+    return launch_weight(ctx, d_proj, dim_x, dim_y, h_min, v_min, d_sd, l_px_row, l_px_col);
+}
+
+extern "C" int paris_b200_apply_filter(paris_b200_ctx* ctx, float* d_proj, uint32_t dim_x, uint32_t dim_y,
+                                       const paris_b200_filter* filter, uint32_t filter_size, uint32_t n_col)
+{
+    PB_CHECK_ARG(ctx != nullptr && d_proj != nullptr && filter != nullptr);
+    PB_CHECK_ARG(filter_size == filter->size && n_col == dim_y && dim_x <= filter_size);
+    PB_TRY(bind(ctx));
+    return launch_filter(ctx, d_proj, d_proj, dim_x, dim_y, filter, weight_params{}, false, 0);
+}
+
+extern "C" int paris_b200_weight_filter(paris_b200_ctx* ctx, float* d_proj, uint32_t dim_x, uint32_t dim_y,
+                                        float h_min, float v_min, float d_sd, float l_px_row, float l_px_col,
+                                        const paris_b200_filter* filter, uint32_t filter_size)
+{
+    PB_CHECK_ARG(ctx != nullptr && d_proj != nullptr && filter != nullptr);
+    PB_CHECK_ARG(filter_size == filter->size && dim_x <= filter_size);
+    PB_TRY(bind(ctx));
+    weight_params w{1, h_min, v_min, d_sd, l_px_row, l_px_col};
+    return launch_filter(ctx, d_proj, d_proj, dim_x, dim_y, filter, w, false, 0);
+}
+
+// ---- deferred backprojection ------------------------------------------------------------------------------
+
+extern "C" int paris_b200_stack_slot_bytes(uint32_t n_row, uint32_t n_col, size_t* bytes, uint32_t* pitch)
+{
+    PB_CHECK_ARG(n_row > 0 && n_col > 0);
+    const uint32_t p = stack_pitch_for(n_col);
+    if(bytes) *bytes = static_cast<size_t>(p) * n_row * sizeof(float);
+    if(pitch) *pitch = p;
+    return PARIS_B200_OK;
+}
+
+static bool same_target(const bp_target& a, const bp_target& b)
+{
+    return a.d_vol == b.d_vol && a.v_dim_x == b.v_dim_x && a.v_dim_y == b.v_dim_y && a.v_dim_z == b.v_dim_z
+        && a.v_offset == b.v_offset && std::memcmp(&a.det, &b.det, sizeof(a.det)) == 0
+        && std::memcmp(&a.vol_full, &b.vol_full, sizeof(a.vol_full)) == 0 && a.enable_roi == b.enable_roi
+        && (!a.enable_roi || std::memcmp(&a.roi, &b.roi, sizeof(a.roi)) == 0) && a.delta_s_mm == b.delta_s_mm
+        && a.delta_t_mm == b.delta_t_mm;
+}
+
+static int ensure_stack(paris_b200_ctx* ctx, uint32_t n_row, uint32_t n_col)
+{
+    const uint32_t pitch = stack_pitch_for(n_col);
+    const uint32_t slots = static_cast<uint32_t>(ctx->bp_batch);
+    if(ctx->stack != nullptr && ctx->stack_n_row == n_row && ctx->stack_n_col == n_col && ctx->stack_slots >= slots)
+        return PARIS_B200_OK;
+    if(ctx->stack != nullptr)
+    {
+        PB_CUDA(cudaStreamSynchronize(ctx->compute));
+        PB_CUDA(cudaFree(ctx->stack));
+        ctx->stack = nullptr;
+    }
+    ctx->stack_slot_floats = static_cast<size_t>(pitch) * n_row;
+    PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&ctx->stack), ctx->stack_slot_floats * slots * sizeof(float)));
+    // pad columns (pitch > n_col) are never written by the filter kernel; keep them zero
+    PB_CUDA(cudaMemsetAsync(ctx->stack, 0, ctx->stack_slot_floats * slots * sizeof(float), ctx->compute));
+    ctx->stack_n_row = n_row;
+    ctx->stack_n_col = n_col;
+    ctx->stack_pitch = pitch;
+    ctx->stack_slots = slots;
+    ctx->tma.valid = false;
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_flush(paris_b200_ctx* ctx)
+{
+    PB_CHECK_ARG(ctx != nullptr);
+    if(ctx->pending == 0)
+        return PARIS_B200_OK;
+    PB_TRY(bind(ctx));
+    const int n = ctx->pending;
+    ctx->pending = 0;
+    return launch_backproject(ctx, ctx->stack, ctx->stack_slot_floats, ctx->stack_pitch, 0u, static_cast<uint32_t>(n),
+                              ctx->pend_sin, ctx->pend_cos, ctx->target);
+}
+
+extern "C" int paris_b200_backproject(paris_b200_ctx* ctx, const float* d_proj, uint32_t dim_x, uint32_t dim_y,
+                                      float* d_vol, uint32_t v_dim_x, uint32_t v_dim_y, uint32_t v_dim_z,
+                                      uint32_t v_offset, const paris_b200_detector_geometry* det,
+                                      const paris_b200_volume_geometry* vol_full, int enable_roi,
+                                      const paris_b200_roi* roi, float sin_phi, float cos_phi, float delta_s_mm,
+                                      float delta_t_mm, uint32_t flags, const paris_b200_filter* filter)
+{
+    PB_CHECK_ARG(ctx != nullptr && d_proj != nullptr && d_vol != nullptr && det != nullptr && vol_full != nullptr);
+    PB_CHECK_ARG(dim_x == det->n_row && dim_y == det->n_col);
+    PB_CHECK_ARG(v_dim_x > 0 && v_dim_y > 0 && v_dim_z > 0);
+    PB_CHECK_ARG(!enable_roi || roi != nullptr);
+    const bool fuse = (flags & PARIS_B200_BP_FUSE_WEIGHT_FILTER) != 0u;
+    PB_CHECK_ARG(!fuse || (filter != nullptr && dim_x <= filter->size));
+    PB_TRY(bind(ctx));
+
+    bp_target t{};
+    t.d_vol = d_vol;
+    t.v_dim_x = v_dim_x;
+    t.v_dim_y = v_dim_y;
+    t.v_dim_z = v_dim_z;
+    t.v_offset = v_offset;
+    t.det = *det;
+    t.vol_full = *vol_full;
+    t.enable_roi = enable_roi ? 1 : 0;
+    if(enable_roi)
+        t.roi = *roi;
+    t.delta_s_mm = delta_s_mm;
+    t.delta_t_mm = delta_t_mm;
+
+    if(ctx->pending > 0 && !same_target(ctx->target, t))
+        PB_TRY(paris_b200_flush(ctx));
+    PB_TRY(ensure_stack(ctx, dim_x, dim_y));
+    ctx->target = t;
+
+    float* slot = ctx->stack + ctx->stack_slot_floats * static_cast<size_t>(ctx->pending);
+    if(fuse)
+    {
+        // src/weighting.cpp:37-42
+        const float n_row_f = static_cast<float>(det->n_row);
+        const float n_col_f = static_cast<float>(det->n_col);
+        weight_params w{};
+        w.enable = 1;
+        w.h_min = (det->delta_s * det->l_px_row) - ((n_row_f * det->l_px_row) / 2);
+        w.v_min = (det->delta_t * det->l_px_col) - ((n_col_f * det->l_px_col) / 2);
+        w.d_sd = std::fabs(det->d_so) + std::fabs(det->d_od);
+        w.l_px_row = det->l_px_row;
+        w.l_px_col = det->l_px_col;
+        PB_TRY(launch_filter(ctx, d_proj, slot, dim_x, dim_y, filter, w, true, ctx->stack_pitch));
+    }
+    else
+        PB_TRY(launch_transpose_to_slot(ctx, d_proj, slot, dim_x, dim_y, ctx->stack_pitch));
+
+    ctx->pend_sin[ctx->pending] = sin_phi;
+    ctx->pend_cos[ctx->pending] = cos_phi;
+    ++ctx->pending;
+    if(ctx->pending >= ctx->bp_batch)
+        PB_TRY(paris_b200_flush(ctx));
+    return PARIS_B200_OK;
+}
+
+// ---- stack-level entry points -----------------------------------------------------------------------------
+
+extern "C" int paris_b200_filter_to_stack(paris_b200_ctx* ctx, const float* d_raw,
+                                          const paris_b200_detector_geometry* det, const paris_b200_filter* filter,
+                                          float* d_stack, uint32_t slot)
+{
+    PB_CHECK_ARG(ctx != nullptr && d_raw != nullptr && det != nullptr && filter != nullptr && d_stack != nullptr);
+    PB_CHECK_ARG(det->n_row <= filter->size);
+    PB_TRY(bind(ctx));
+    const uint32_t pitch = stack_pitch_for(det->n_col);
+    const size_t slot_floats = static_cast<size_t>(pitch) * det->n_row;
+    const float n_row_f = static_cast<float>(det->n_row);
+    const float n_col_f = static_cast<float>(det->n_col);
+    weight_params w{};
+    w.enable = 1;
+    w.h_min = (det->delta_s * det->l_px_row) - ((n_row_f * det->l_px_row) / 2);
+    w.v_min = (det->delta_t * det->l_px_col) - ((n_col_f * det->l_px_col) / 2);
+    w.d_sd = std::fabs(det->d_so) + std::fabs(det->d_od);
+    w.l_px_row = det->l_px_row;
+    w.l_px_col = det->l_px_col;
+    return launch_filter(ctx, d_raw, d_stack + slot_floats * slot, det->n_row, det->n_col, filter, w, true, pitch);
+}
+
+extern "C" int paris_b200_backproject_stack(paris_b200_ctx* ctx, const float* d_stack, uint32_t first, uint32_t count,
+                                            const float* sin_phi, const float* cos_phi, float* d_vol,
+                                            uint32_t v_dim_x, uint32_t v_dim_y, uint32_t v_dim_z, uint32_t v_offset,
+                                            const paris_b200_detector_geometry* det,
+                                            const paris_b200_volume_geometry* vol_full, int enable_roi,
+                                            const paris_b200_roi* roi)
+{
+    PB_CHECK_ARG(ctx != nullptr && d_stack != nullptr && d_vol != nullptr && det != nullptr && vol_full != nullptr);
+    PB_CHECK_ARG(sin_phi != nullptr && cos_phi != nullptr);
+    PB_CHECK_ARG(!enable_roi || roi != nullptr);
+    PB_TRY(bind(ctx));
+    PB_TRY(paris_b200_flush(ctx));
+    bp_target t{};
+    t.d_vol = d_vol;
+    t.v_dim_x = v_dim_x;
+    t.v_dim_y = v_dim_y;
+    t.v_dim_z = v_dim_z;
+    t.v_offset = v_offset;
+    t.det = *det;
+    t.vol_full = *vol_full;
+    t.enable_roi = enable_roi ? 1 : 0;
+    if(enable_roi)
+        t.roi = *roi;
+    // src/backprojection.cpp:49-50
+    t.delta_s_mm = det->delta_s * det->l_px_row;
+    t.delta_t_mm = det->delta_t * det->l_px_col;
+    const uint32_t pitch = stack_pitch_for(det->n_col);
+    const size_t slot_floats = static_cast<size_t>(pitch) * det->n_row;
+    for(uint32_t done = 0; done < count;)
+    {
+        const uint32_t n = std::min<uint32_t>(count - done, static_cast<uint32_t>(ctx->bp_batch));
+        PB_TRY(launch_backproject(ctx, d_stack, slot_floats, pitch, first + done, n, sin_phi + done, cos_phi + done, t));
+        done += n;
+    }
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_phantom_project(paris_b200_ctx* ctx, const double* ellipsoids, uint32_t n_ellipsoids,
+                                          const paris_b200_detector_geometry* det, uint32_t first_idx,
+                                          uint32_t n_proj, float* d_stack_raw)
+{
+    PB_CHECK_ARG(ctx != nullptr && ellipsoids != nullptr && det != nullptr && d_stack_raw != nullptr);
+    PB_CHECK_ARG(n_ellipsoids >= 1 && n_ellipsoids <= 64);
+    PB_TRY(bind(ctx));
+    return launch_phantom(ctx, ellipsoids, n_ellipsoids, det, first_idx, n_proj, d_stack_raw);
+}

@@ -1,0 +1,151 @@
+// common.cuh -- context, error plumbing and launch helpers shared by the sm_100a kernels.
+#pragma once
+
+#include <cuda.h>
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/paris_b200.h"
+
+namespace pb
+{
+    void set_error(const char* fmt, ...);
+
+    // Maximum projections accumulated by one backprojection launch (sin/cos travel as kernel parameters).
+    constexpr int kMaxBatch = 64;
+
+    struct raw_buffer
+    {
+        void* ptr = nullptr;
+        size_t bytes = 0;
+        bool in_use = false;
+        cudaEvent_t freed = nullptr;   // recorded on the compute stream at dev_free
+        bool freed_valid = false;
+    };
+
+    // Geometry of one pending backprojection batch: everything but the angles must match for
+    // projections to share a launch.
+    struct bp_target
+    {
+        float* d_vol = nullptr;
+        uint32_t v_dim_x = 0, v_dim_y = 0, v_dim_z = 0, v_offset = 0;
+        paris_b200_detector_geometry det{};
+        paris_b200_volume_geometry vol_full{};
+        int enable_roi = 0;
+        paris_b200_roi roi{};
+        float delta_s_mm = 0.f, delta_t_mm = 0.f;
+    };
+
+    struct tma_desc_cache
+    {
+        const float* base = nullptr;
+        uint32_t n_row = 0, pitch = 0, slots = 0, box_v = 0, box_h = 0;
+        CUtensorMap map{};
+        bool valid = false;
+    };
+}
+
+struct paris_b200_filter
+{
+    int device = 0;
+    uint32_t size = 0;       // N
+    float tau = 0.f;
+    float* d_k = nullptr;    // K[x], x = 0..N/2 (as the reference defines it)
+    float* d_kn = nullptr;   // K[x] / N  (exact: N is a power of two)
+    float2* d_tw = nullptr;  // exp(-2 pi i k / N), k = 0..N-1
+};
+
+struct paris_b200_ctx
+{
+    int device = 0;
+    int sm_count = 0;
+    cudaStream_t compute = nullptr;
+    cudaStream_t copy = nullptr;
+    cudaEvent_t h2d_done = nullptr;  // last H2D on the copy stream
+    bool h2d_any = false;
+    cudaEvent_t scratch_ev = nullptr;
+    uint64_t launches = 0;
+
+    // options
+    int bp_batch = 32;
+    int bp_kernel = 0;
+
+    // pooled raw projection buffers (dev_alloc / dev_free)
+    std::vector<pb::raw_buffer> pool;
+
+    // filtered stack owned by the context (deferred backprojection)
+    float* stack = nullptr;
+    uint32_t stack_n_row = 0, stack_n_col = 0, stack_pitch = 0, stack_slots = 0;
+    size_t stack_slot_floats = 0;
+
+    // pending batch
+    pb::bp_target target{};
+    int pending = 0;
+    float pend_sin[pb::kMaxBatch];
+    float pend_cos[pb::kMaxBatch];
+
+    pb::tma_desc_cache tma;
+};
+
+#define PB_CUDA(expr)                                                                                   \
+    do                                                                                                  \
+    {                                                                                                   \
+        cudaError_t e_ = (expr);                                                                        \
+        if(e_ != cudaSuccess)                                                                           \
+        {                                                                                               \
+            pb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__);  \
+            return e_ == cudaErrorMemoryAllocation ? PARIS_B200_ENOMEM : PARIS_B200_ECUDA;              \
+        }                                                                                               \
+    } while(0)
+
+#define PB_CHECK_ARG(cond)                                                                              \
+    do                                                                                                  \
+    {                                                                                                   \
+        if(!(cond))                                                                                     \
+        {                                                                                               \
+            pb::set_error("invalid argument: %s (%s:%d)", #cond, __FILE__, __LINE__);                   \
+            return PARIS_B200_EINVAL;                                                                   \
+        }                                                                                               \
+    } while(0)
+
+#define PB_TRY(expr)                 \
+    do                               \
+    {                                \
+        int rc_ = (expr);            \
+        if(rc_ != PARIS_B200_OK)     \
+            return rc_;              \
+    } while(0)
+
+// kernel launchers implemented in the individual .cu files ------------------------------------------------
+namespace pb
+{
+    int launch_weight(paris_b200_ctx* ctx, float* d_proj, uint32_t dim_x, uint32_t dim_y, float h_min, float v_min,
+                      float d_sd, float l_px_row, float l_px_col);
+
+    struct weight_params
+    {
+        int enable = 0;
+        float h_min = 0.f, v_min = 0.f, d_sd = 0.f, l_px_row = 0.f, l_px_col = 0.f;
+    };
+
+    // src rows -> (optional weight) -> ramp filter -> dst.  dst_transposed: write dst[s*dst_pitch + t]
+    // (stack slot layout) instead of dst[t*dim_x + s].
+    int launch_filter(paris_b200_ctx* ctx, const float* d_src, float* d_dst, uint32_t dim_x, uint32_t dim_y,
+                      const paris_b200_filter* f, const weight_params& w, bool dst_transposed, uint32_t dst_pitch);
+
+    int launch_transpose_to_slot(paris_b200_ctx* ctx, const float* d_src, float* d_slot, uint32_t dim_x,
+                                 uint32_t dim_y, uint32_t pitch);
+
+    int launch_backproject(paris_b200_ctx* ctx, const float* d_stack, size_t slot_floats, uint32_t pitch,
+                           uint32_t first, uint32_t count, const float* sn, const float* cs, const bp_target& t);
+
+    int launch_phantom(paris_b200_ctx* ctx, const double* h_ellipsoids, uint32_t n, const paris_b200_detector_geometry* det,
+                       uint32_t first_idx, uint32_t n_proj, float* d_out);
+
+    inline uint32_t stack_pitch_for(uint32_t n_col) { return (n_col + 31u) & ~31u; }
+}

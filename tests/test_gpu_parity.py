@@ -1,0 +1,121 @@
+"""GPU parity: the sm_100a kernels, called through the C ABI, against the CPU oracle on the same inputs."""
+import numpy as np
+import pytest
+
+import oracle
+from paris_b200 import capi
+from paris_b200.pipeline import Pipeline, weight_constants
+
+from cases import MAX_ABS_TOL, RMSE_TOL, both_det, coarse_volume, contrast, errors, shepp_logan, to_capi_vol
+
+pytestmark = pytest.mark.gpu
+
+
+@pytest.mark.parametrize("n_row,n_col,delta_s,delta_t", [(64, 48, 0.0, 0.0), (100, 37, 3.0, -2.0), (256, 256, 0.0, 0.0)])
+def test_weight_bit_exact(ctx, port, n_row, n_col, delta_s, delta_t):
+    odet, det = both_det(n_row, n_col, delta_s=delta_s, delta_t=delta_t)
+    rng = np.random.default_rng(1)
+    p = rng.standard_normal((n_col, n_row)).astype(np.float32)
+    pl = Pipeline(ctx, det)
+    d = pl.load(p)
+    pl.weight(d)
+    got = pl.download(d)
+    pl.release(d)
+    assert np.array_equal(got, port.weight(p, odet))
+
+
+@pytest.mark.parametrize("size,tau", [(32, 0.4), (128, 0.4), (512, 0.4), (2048, 0.2), (4096, 0.1), (8192, 0.05)])
+def test_filter_table(ctx, port, size, tau):
+    f = ctx.filter_create(size, tau)
+    k = ctx.filter_read(f, size)
+    ctx.filter_destroy(f)
+    ref = port.make_filter(size, tau)
+    # same float taps, transform in double on both sides, rounded to float: at most an ulp apart
+    np.testing.assert_allclose(k, ref, rtol=3e-7, atol=0)
+
+
+@pytest.mark.parametrize("n_row,n_col", [(16, 8), (64, 48), (100, 37), (256, 256), (1024, 33), (2048, 16), (3000, 9)])
+def test_apply_filter(ctx, port, n_row, n_col):
+    odet, det = both_det(n_row, n_col, l_px=0.2)
+    rng = np.random.default_rng(2)
+    p = rng.standard_normal((n_col, n_row)).astype(np.float32)
+    pl = Pipeline(ctx, det)
+    d = pl.load(p)
+    pl.filter(d)
+    got = pl.download(d)
+    pl.release(d)
+    pl.close()
+    ref = port.filter(p, odet)
+    scale = np.abs(ref).max()
+    # float32 FFT against the oracle's float64 FFT
+    assert np.abs(got - ref).max() <= 2e-6 * scale
+
+
+def test_weight_filter_fused_equals_stages(ctx, port):
+    odet, det = both_det(200, 50, l_px=0.3, delta_s=2.0)
+    rng = np.random.default_rng(3)
+    p = rng.standard_normal((50, 200)).astype(np.float32)
+    pl = Pipeline(ctx, det)
+    a = pl.load(p)
+    pl.weight(a)
+    pl.filter(a)
+    b = pl.load(p)
+    pl.weight_filter(b)
+    ga, gb = pl.download(a), pl.download(b)
+    pl.release(a)
+    pl.release(b)
+    pl.close()
+    assert np.array_equal(ga, gb)
+    ref = port.filter(port.weight(p, odet), odet)
+    assert np.abs(ga - ref).max() <= 2e-6 * np.abs(ref).max()
+
+
+def _recon_case(n, n_proj, coarse=None, delta_s=0.0):
+    odet, det = both_det(n, n, n_proj=n_proj, delta_s=delta_s)
+    P = oracle.Port()
+    ovol = P.calculate_volume_geometry(odet) if coarse is None else coarse_volume(odet, coarse)
+    stack = shepp_logan(odet, n_proj)
+    return odet, det, ovol, to_capi_vol(ovol), stack
+
+
+@pytest.mark.parametrize("batch", [1, 5, 32])
+def test_backproject_exact_kernel_bit_exact(ctx, port, batch):
+    """bp_kernel=1: the reference's arithmetic operation for operation -> identical bits for any batch."""
+    n, n_proj = 48, 12
+    odet, det, ovol, vol, stack = _recon_case(n, n_proj)
+    filtered = np.stack([port.filter(port.weight(s, odet), odet) for s in stack])
+    ref = np.zeros((ovol.dim_z, ovol.dim_y, ovol.dim_x), np.float32)
+    for i in range(n_proj):
+        port.backproject(filtered[i], i, ref, odet, ovol)
+
+    ctx.set_option("bp_kernel", 1)
+    ctx.set_option("bp_batch", batch)
+    pl = Pipeline(ctx, det)
+    v = pl.make_volume(vol.dim_x, vol.dim_y, vol.dim_z)
+    for i in range(n_proj):
+        d = pl.load(filtered[i], idx=i)
+        pl.backproject(d, v, 0, vol)
+        pl.release(d)
+    got = pl.save(v)
+    pl.free_volume(v)
+    pl.close()
+    ctx.set_option("bp_kernel", 0)
+    ctx.set_option("bp_batch", 32)
+    assert np.array_equal(got, ref)
+
+
+@pytest.mark.parametrize("fused", [False, True])
+@pytest.mark.parametrize("kernel", [1, 0])
+def test_reconstruction_within_tolerance(ctx, port, kernel, fused):
+    """config-1-like: K^3 volume from a (2K)^2 detector, full pipeline, north_star tolerance."""
+    n, n_proj, k = 96, 64, 48
+    odet, det, ovol, vol, stack = _recon_case(n, n_proj, coarse=k)
+    ref, _ = port.reconstruct(stack, (k, k, k), odet, ovol)
+    ctx.set_option("bp_kernel", kernel)
+    pl = Pipeline(ctx, det)
+    got = pl.reconstruct(stack, (k, k, k), vol, fused=fused)
+    pl.close()
+    ctx.set_option("bp_kernel", 0)
+    mx, rms = errors(got, ref, contrast(n_proj))
+    print(f"kernel={kernel} fused={fused}: max {mx:.3e} rmse {rms:.3e}")
+    assert mx <= MAX_ABS_TOL and rms <= RMSE_TOL
