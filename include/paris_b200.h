@@ -95,6 +95,14 @@ int paris_b200_ctx_stream(paris_b200_ctx* ctx, void** stream);
 /* counters since ctx_create: kernels launched by this library on this context */
 int paris_b200_ctx_launch_count(const paris_b200_ctx* ctx, uint64_t* launches);
 
+/* CUDA-event timing on the context's compute stream (bench / profiling plumbing) */
+typedef struct paris_b200_event paris_b200_event;
+int paris_b200_event_create(paris_b200_ctx* ctx, paris_b200_event** ev);
+int paris_b200_event_record(paris_b200_ctx* ctx, paris_b200_event* ev);
+/* waits for `stop`, then returns the milliseconds between the two records */
+int paris_b200_event_elapsed_ms(paris_b200_event* start, paris_b200_event* stop, float* ms);
+int paris_b200_event_destroy(paris_b200_event* ev);
+
 /* Tunables.  "bp_batch": projections accumulated per backprojection launch (default 32);
  * "bp_kernel": 0 = auto, 1 = generic L1-gather kernel, 2 = TMA-staged kernel. */
 int paris_b200_ctx_set_option(paris_b200_ctx* ctx, const char* name, int64_t value);

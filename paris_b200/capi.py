@@ -64,6 +64,10 @@ SIGNATURES = {
     "paris_b200_ctx_sync": (C.c_int, [_vp]),
     "paris_b200_ctx_stream": (C.c_int, [_vp, _P(_vp)]),
     "paris_b200_ctx_launch_count": (C.c_int, [_vp, _P(C.c_uint64)]),
+    "paris_b200_event_create": (C.c_int, [_vp, _P(_vp)]),
+    "paris_b200_event_record": (C.c_int, [_vp, _vp]),
+    "paris_b200_event_elapsed_ms": (C.c_int, [_vp, _vp, _P(_f)]),
+    "paris_b200_event_destroy": (C.c_int, [_vp]),
     "paris_b200_ctx_set_option": (C.c_int, [_vp, C.c_char_p, C.c_int64]),
     "paris_b200_calculate_volume_geometry": (C.c_int, [_P(DetectorGeometry), _P(VolumeGeometry)]),
     "paris_b200_apply_roi": (C.c_int, [_P(VolumeGeometry), _P(Roi), _P(VolumeGeometry)]),
@@ -208,6 +212,21 @@ class Context:
         n = C.c_uint64(0)
         check(self._L.paris_b200_ctx_launch_count(self.h, C.byref(n)))
         return n.value
+
+    def event(self) -> int:
+        """Create a CUDA event and record it on the compute stream."""
+        e = _vp()
+        check(self._L.paris_b200_event_create(self.h, C.byref(e)))
+        check(self._L.paris_b200_event_record(self.h, e))
+        return e.value
+
+    def elapsed_ms(self, start: int, stop: int, destroy: bool = True) -> float:
+        ms = _f(0)
+        check(self._L.paris_b200_event_elapsed_ms(start, stop, C.byref(ms)))
+        if destroy:
+            check(self._L.paris_b200_event_destroy(start))
+            check(self._L.paris_b200_event_destroy(stop))
+        return float(ms.value)
 
     def set_option(self, name: str, value: int):
         check(self._L.paris_b200_ctx_set_option(self.h, name.encode(), value))

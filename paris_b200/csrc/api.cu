@@ -124,6 +124,49 @@ extern "C" int paris_b200_ctx_launch_count(const paris_b200_ctx* ctx, uint64_t* 
     return PARIS_B200_OK;
 }
 
+struct paris_b200_event
+{
+    int device;
+    cudaEvent_t ev;
+};
+
+extern "C" int paris_b200_event_create(paris_b200_ctx* ctx, paris_b200_event** ev)
+{
+    PB_CHECK_ARG(ctx != nullptr && ev != nullptr);
+    PB_TRY(bind(ctx));
+    auto* e = new paris_b200_event{ctx->device, nullptr};
+    PB_CUDA(cudaEventCreate(&e->ev));
+    *ev = e;
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_event_record(paris_b200_ctx* ctx, paris_b200_event* ev)
+{
+    PB_CHECK_ARG(ctx != nullptr && ev != nullptr);
+    PB_TRY(bind(ctx));
+    PB_CUDA(cudaEventRecord(ev->ev, ctx->compute));
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_event_elapsed_ms(paris_b200_event* start, paris_b200_event* stop, float* ms)
+{
+    PB_CHECK_ARG(start != nullptr && stop != nullptr && ms != nullptr);
+    PB_CUDA(cudaSetDevice(stop->device));
+    PB_CUDA(cudaEventSynchronize(stop->ev));
+    PB_CUDA(cudaEventElapsedTime(ms, start->ev, stop->ev));
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_event_destroy(paris_b200_event* ev)
+{
+    if(ev == nullptr)
+        return PARIS_B200_OK;
+    cudaSetDevice(ev->device);
+    cudaEventDestroy(ev->ev);
+    delete ev;
+    return PARIS_B200_OK;
+}
+
 extern "C" int paris_b200_ctx_set_option(paris_b200_ctx* ctx, const char* name, int64_t value)
 {
     PB_CHECK_ARG(ctx != nullptr && name != nullptr);

@@ -1,16 +1,508 @@
-// backproject_tma.cu -- placeholder until the TMA-staged kernel lands: reports "not handled".
+// backproject_tma.cu -- K2, production kernel: TMA-staged, register-accumulating backprojection.
+//
+// Work decomposition (one CTA = one voxel tile, all projections of the batch):
+//   * tile = TX x TY voxel columns x TZ = 32*WZ slices.  A warp's 32 LANES RUN ALONG z for one column
+//     group: for a fixed column (x, y) and projection, the detector column position h, the bilinear
+//     x-weights and the magnification are the same for every z, and the detector row position is
+//     affine in z:  v(z) = v_base + z * dv.  All per-(column, projection) terms -- the reference's
+//     rotate / perspective-divide arithmetic of /root/reference/src/openmp/backprojection.cpp:120-133,
+//     including the one IEEE division -- are therefore computed ONCE per column and projection by one
+//     thread, put in a shared-memory table and read back as a warp-wide broadcast.
+//   * the filtered stack is stored transposed (detector-row index v fastest), so the 32 lanes of an
+//     update read 32 nearly consecutive floats of one stack line; the tile's footprint on projection p,
+//     a BH x BV box, is fetched by ONE 3-D TMA load (cp.async.bulk.tensor) into a ring of shared-memory
+//     stages, out-of-detector parts zero-filled by the TMA unit.  mbarrier transaction counts signal
+//     arrival; loads run S-1 projections ahead of the math.
+//   * each thread keeps CPW accumulators (its columns at its z) in registers for the whole batch, seeded
+//     from the volume and stored once: the volume is read and written once per batch, and the per-voxel
+//     summation order is the reference's (projection order), so no re-association error is introduced.
+//   * exact FP32 bilinear interpolation on the four point-fetched samples with the reference's
+//     "all four neighbours inside, else 0" rule (:65-71) -- no hardware texture filtering (8-bit weights
+//     break the tolerance).
+//
+// Tensor cores are not used: this is a gather plus interpolation, not a contraction.
 #include "common.cuh"
 #include "backproject.cuh"
 
+#include <cuda.h>
+#include <cudaTypedefs.h>
+
 namespace pb
 {
-    int launch_bp_tma(paris_b200_ctx*, const float*, size_t, uint32_t, const bp_geometry&, const bp_angles&, float*,
-                      bool required, bool* handled)
+    // ---- tile configuration ---------------------------------------------------------------------------
+    template <int TX_, int TY_, int WZ_, int CPW_, int BH_, int BV_, int STAGES_>
+    struct tile_cfg
+    {
+        static constexpr int TX = TX_, TY = TY_, WZ = WZ_, CPW = CPW_, BH = BH_, BV = BV_, STAGES = STAGES_;
+        static constexpr int TZ = 32 * WZ;
+        static constexpr int COLS = TX * TY;
+        static constexpr int WC = COLS / CPW;             // warps across column groups
+        static constexpr int THREADS = 32 * WZ * WC;
+        static constexpr int STAGE_BYTES = BH * BV * 4;
+        static constexpr int TAB_BYTES = COLS * (16 + 8);  // float4 + float2 per column
+        static constexpr size_t SMEM = size_t(STAGES) * STAGE_BYTES + 2 * TAB_BYTES + kMaxBatch * 16 + STAGES * 8 + 128;
+        static_assert(COLS % CPW == 0, "columns per warp must divide the tile");
+        static_assert(CPW % TX == 0 || TX % CPW == 0, "a warp's columns must be whole or partial x-runs");
+        static_assert(BV % 4 == 0, "TMA inner box extent must be a multiple of 16 bytes");
+        static_assert(BH <= 256 && BV <= 256, "TMA box extents are limited to 256");
+    };
+
+    struct box_origin
+    {
+        int h0, v0;      // detector coordinates of the box's first element
+        int all_valid;   // every bilinear cell any voxel of the tile touches lies inside the detector and the box
+        int pad;
+    };
+
+    // ---- small PTX wrappers -----------------------------------------------------------------------------
+    __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
+
+    __device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
+    {
+        asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count));
+    }
+
+    __device__ __forceinline__ void mbar_expect_tx(uint32_t bar, uint32_t bytes)
+    {
+        asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(bar), "r"(bytes) : "memory");
+    }
+
+    __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
+    {
+        asm volatile(
+            "{\n"
+            ".reg .pred p;\n"
+            "WAIT_LOOP:\n"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n"
+            "@p bra WAIT_DONE;\n"
+            "bra WAIT_LOOP;\n"
+            "WAIT_DONE:\n"
+            "}\n" ::"r"(bar), "r"(parity) : "memory");
+    }
+
+    __device__ __forceinline__ void tma_load_3d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2)
+    {
+        asm volatile(
+            "cp.async.bulk.tensor.3d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5}], [%2];"
+            ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
+    }
+
+    __device__ __forceinline__ float lds_f32(uint32_t addr)
+    {
+        float v;
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+        return v;
+    }
+
+    // ---- per-projection geometry helpers ------------------------------------------------------------------
+
+    __device__ __forceinline__ float centered(uint32_t coord, uint32_t dim, float size)
+    {
+        // src/openmp/backprojection.cpp:39-43, same float operations
+        const float size2 = size / 2.f;
+        return __fadd_rn(__fadd_rn(-__fmul_rn(static_cast<float>(dim), size2), size2),
+                         __fmul_rn(static_cast<float>(coord), size));
+    }
+
+    struct column_terms
+    {
+        float h;        // fractional detector column, exactly the reference's float arithmetic (:121-129)
+        float factor;   // d_sd / (s + d_so), IEEE
+        float u;        // d_so / (s + d_so)
+    };
+
+    __device__ __forceinline__ column_terms project_column(float x_k, float y_l, float sn, float cs, const bp_geometry& g)
+    {
+        column_terms c;
+        const float s = __fadd_rn(__fmul_rn(x_k, cs), __fmul_rn(y_l, sn));
+        const float t = __fadd_rn(__fmul_rn(-x_k, sn), __fmul_rn(y_l, cs));
+        const float denom = __fadd_rn(s, g.d_so);
+        c.factor = __fdiv_rn(g.d_sd, denom);
+        const float size2 = g.l_px_x / 2.f;
+        const float min_h = __fsub_rn(-__fmul_rn(static_cast<float>(g.p_dim_x), size2), g.delta_s);
+        c.h = __fsub_rn(__fdiv_rn(__fsub_rn(__fmul_rn(t, c.factor), min_h), g.l_px_x), 0.5f);
+        c.u = __fdiv_rn(g.d_so, denom);
+        return c;
+    }
+
+    // fractional detector row of slice coordinate z_m (double): (z_m*factor - min_v)/l_px_y - 0.5 (:130-133)
+    __device__ __forceinline__ double row_of(double z_m, double factor, const bp_geometry& g)
+    {
+        const double min_v = -(static_cast<double>(g.p_dim_y) * (static_cast<double>(g.l_px_y) / 2.0))
+                           - static_cast<double>(g.delta_t);
+        return (z_m * factor - min_v) / static_cast<double>(g.l_px_y) - 0.5;
+    }
+
+    __device__ __forceinline__ double centered_d(uint32_t coord, uint32_t dim, float size)
+    {
+        const double sz = static_cast<double>(size);
+        return -(static_cast<double>(dim) * (sz / 2.0)) + sz / 2.0 + static_cast<double>(coord) * sz;
+    }
+
+    // ---- the kernel ------------------------------------------------------------------------------------------
+
+    template <class CFG, bool CHECKED>
+    __device__ __forceinline__ void consume(float (&acc)[CFG::CPW], const float4* __restrict__ tab_a,
+                                            const float2* __restrict__ tab_b, int col0, float m_f,
+                                            int v_lo, uint32_t v_span)
+    {
+        #pragma unroll
+        for(int i = 0; i < CFG::CPW; ++i)
+        {
+            const float4 ea = tab_a[col0 + i];   // {stage base + 4*BV*x1 (bits), v_base, dv, w*(1-fx)}
+            const float wb = tab_b[col0 + i].x;  // w*fx
+            const float v = fmaf(m_f, ea.y, ea.z) ;
+            const float fl = floorf(v);
+            const float fy = v - fl;
+            int iy = static_cast<int>(fl);
+            bool ok = true;
+            if(CHECKED)
+            {
+                // all four neighbours inside the detector (rows iy+v0 and iy+v0+1), else the term is 0
+                ok = static_cast<uint32_t>(iy - v_lo) < v_span;
+                iy = min(max(iy, 0), CFG::BV - 2);
+            }
+            const uint32_t addr = __float_as_uint(ea.x) + 4u * static_cast<uint32_t>(iy);
+            const float q11 = lds_f32(addr);
+            const float q12 = lds_f32(addr + 4);
+            const float q21 = lds_f32(addr + 4 * CFG::BV);
+            const float q22 = lds_f32(addr + 4 * CFG::BV + 4);
+            const float g0 = fmaf(wb, q21, ea.w * q11);
+            const float g1 = fmaf(wb, q22, ea.w * q12);
+            float d = fmaf(fy, g1 - g0, g0);
+            if(CHECKED)
+                d = ok ? d : 0.f;
+            acc[i] += d;
+        }
+    }
+
+    template <class CFG>
+    __global__ void __launch_bounds__(CFG::THREADS, 1)
+    bp_tma_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ vol, const bp_geometry g,
+                  const bp_angles ang, const uint32_t first_slot)
+    {
+        extern __shared__ __align__(128) unsigned char smem[];
+        unsigned char* stage_mem = smem;                                                   // STAGES x BH x BV floats
+        float4* tab_a = reinterpret_cast<float4*>(smem + size_t(CFG::STAGES) * CFG::STAGE_BYTES);
+        float2* tab_b = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(tab_a) + 2 * CFG::COLS * 16);
+        box_origin* origin = reinterpret_cast<box_origin*>(reinterpret_cast<unsigned char*>(tab_b) + 2 * CFG::COLS * 8);
+        uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(origin) + kMaxBatch * 16);
+
+        const int tid = threadIdx.x;
+        const int lane = tid & 31;
+        const int warp = tid >> 5;
+        const int wz = warp % CFG::WZ;      // which 32-slice group
+        const int wc = warp / CFG::WZ;      // which column group
+        const int count = ang.count;
+
+        const uint32_t x0 = blockIdx.x * CFG::TX;
+        const uint32_t y0 = blockIdx.y * CFG::TY;
+        const uint32_t z0 = blockIdx.z * CFG::TZ;
+        const bool full_tile = x0 + CFG::TX <= g.v_dim_x && y0 + CFG::TY <= g.v_dim_y && z0 + CFG::TZ <= g.v_dim_z;
+
+        // ---- prologue 1: barriers, box origins for every projection of the batch ---------------------------
+        if(tid == 0)
+        {
+            #pragma unroll
+            for(int s = 0; s < CFG::STAGES; ++s)
+                mbar_init(smem_u32(&bars[s]), 1);
+            asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+        }
+        if(tid < count)
+        {
+            const float sn = ang.sn[tid], cs = ang.cs[tid];
+            // extremes over the tile's corners (h and factor are projective/monotone over the convex tile)
+            const uint32_t xe = min(x0 + CFG::TX, g.v_dim_x) - 1u, ye = min(y0 + CFG::TY, g.v_dim_y) - 1u;
+            const uint32_t ze = min(z0 + CFG::TZ, g.v_dim_z) - 1u;
+            const double zlo = centered_d(z0 + g.off_z, g.full_z, g.l_vx_z);
+            const double zhi = centered_d(ze + g.off_z, g.full_z, g.l_vx_z);
+            float hmin = 3.0e38f, hmax = -3.0e38f;
+            double vmin = 1.0e300, vmax = -1.0e300;
+            #pragma unroll
+            for(int c = 0; c < 4; ++c)
+            {
+                const uint32_t k = (c & 1) ? xe : x0, l = (c & 2) ? ye : y0;
+                const column_terms ct = project_column(centered(k + g.off_x, g.full_x, g.l_vx_x),
+                                                       centered(l + g.off_y, g.full_y, g.l_vx_y), sn, cs, g);
+                hmin = fminf(hmin, ct.h);
+                hmax = fmaxf(hmax, ct.h);
+                const double va = row_of(zlo, static_cast<double>(ct.factor), g);
+                const double vb = row_of(zhi, static_cast<double>(ct.factor), g);
+                vmin = fmin(vmin, fmin(va, vb));
+                vmax = fmax(vmax, fmax(va, vb));
+            }
+            // clamp so the integer conversions are safe for columns far off the detector
+            const float lim_h = static_cast<float>(g.p_dim_x) + 8.f, lim_v = static_cast<float>(g.p_dim_y) + 8.f;
+            const float hlo_f = fminf(fmaxf(floorf(hmin), -8.f), lim_h), hhi_f = fminf(fmaxf(floorf(hmax), -8.f), lim_h);
+            const float vlo_f = fminf(fmaxf(floorf(static_cast<float>(vmin)), -8.f), lim_v);
+            const float vhi_f = fminf(fmaxf(floorf(static_cast<float>(vmax)), -8.f), lim_v);
+            const int hlo = static_cast<int>(hlo_f), hhi = static_cast<int>(hhi_f);
+            const int vlo = static_cast<int>(vlo_f), vhi = static_cast<int>(vhi_f);
+            box_origin o;
+            o.h0 = hlo - 1;
+            // the TMA unit wants the innermost start coordinate on a 16-byte boundary (measured on B200:
+            // anything else raises an illegal-instruction fault), so round down to a multiple of 4 floats
+            o.v0 = ((vlo - 1) >> 2) << 2;
+            // cells used: columns hlo-1 .. hhi+2, rows vlo-1 .. vhi+2 (one cell of slack for float rounding)
+            const bool fits = (hhi + 2 - o.h0) < CFG::BH && (vhi + 2 - o.v0) < CFG::BV;
+            const bool inside = hlo - 1 >= 0 && hhi + 2 <= static_cast<int>(g.p_dim_x) - 1
+                             && vlo - 1 >= 0 && vhi + 2 <= static_cast<int>(g.p_dim_y) - 1
+                             && hmin == hmin && hmax == hmax && vmin == vmin && vmax == vmax;
+            o.all_valid = (fits && inside && full_tile) ? 1 : 0;
+            o.pad = 0;
+            origin[tid] = o;
+        }
+        __syncthreads();
+
+        // ---- prologue 2: start the TMA pipeline, seed the accumulators, build the first table -------------------
+        if(tid == 0)
+        {
+            const int pre = count < CFG::STAGES ? count : CFG::STAGES;
+            for(int p = 0; p < pre; ++p)
+            {
+                const uint32_t bar = smem_u32(&bars[p]);
+                mbar_expect_tx(bar, CFG::STAGE_BYTES);
+                tma_load_3d(smem_u32(stage_mem + size_t(p) * CFG::STAGE_BYTES), &tmap, bar, origin[p].v0, origin[p].h0,
+                            static_cast<int>(first_slot) + p);
+            }
+        }
+
+        // this thread's voxels: columns col0 .. col0+CPW-1 of the tile at slice z
+        const int col0 = wc * CFG::CPW;
+        const uint32_t z = z0 + wz * 32 + lane;
+        const bool z_ok = z < g.v_dim_z;
+        const size_t slice = static_cast<size_t>(g.v_dim_x) * g.v_dim_y;
+        float acc[CFG::CPW];
+        #pragma unroll
+        for(int i = 0; i < CFG::CPW; ++i)
+        {
+            const uint32_t x = x0 + (col0 + i) % CFG::TX, y = y0 + (col0 + i) / CFG::TX;
+            const bool ok = z_ok && x < g.v_dim_x && y < g.v_dim_y;
+            acc[i] = ok ? vol[static_cast<size_t>(z) * slice + static_cast<size_t>(y) * g.v_dim_x + x] : 0.f;
+        }
+
+        // table builder state: thread c < COLS owns tile column c
+        const bool builder = tid < CFG::COLS;
+        float bx_k = 0.f, by_l = 0.f;
+        double z_m0 = 0.0;
+        if(builder)
+        {
+            bx_k = centered(x0 + tid % CFG::TX + g.off_x, g.full_x, g.l_vx_x);
+            by_l = centered(y0 + tid / CFG::TX + g.off_y, g.full_y, g.l_vx_y);
+            z_m0 = centered_d(z0 + g.off_z, g.full_z, g.l_vx_z);
+        }
+        const uint32_t stage_base0 = smem_u32(stage_mem);
+
+        auto build = [&](int p) {
+            const box_origin o = origin[p];
+            const column_terms ct = project_column(bx_k, by_l, ang.sn[p], ang.cs[p], g);
+            const float x1 = floorf(ct.h);
+            const bool valid_x = x1 >= 0.f && x1 + 1.f < static_cast<float>(g.p_dim_x);
+            float4 ea = make_float4(0.f, 0.f, 0.f, 0.f);
+            float2 eb = make_float2(0.f, 0.f);
+            int x1rel = 0;
+            if(valid_x)
+            {
+                const float fx = ct.h - x1;
+                const float w = 0.5f * ct.u * ct.u;
+                x1rel = min(max(static_cast<int>(x1) - o.h0, 0), CFG::BH - 2);
+                const double fd = static_cast<double>(ct.factor);
+                const double dv = static_cast<double>(g.l_vx_z) * fd / static_cast<double>(g.l_px_y);
+                const double vb = row_of(z_m0, fd, g) - static_cast<double>(o.v0);
+                ea.y = static_cast<float>(dv);
+                ea.z = static_cast<float>(vb);
+                ea.w = w * (1.f - fx);
+                eb.x = w * fx;
+            }
+            const uint32_t base = stage_base0 + static_cast<uint32_t>(p % CFG::STAGES) * CFG::STAGE_BYTES
+                                + 4u * static_cast<uint32_t>(x1rel * CFG::BV);
+            ea.x = __uint_as_float(base);
+            tab_a[(p & 1) * CFG::COLS + tid] = ea;
+            tab_b[(p & 1) * CFG::COLS + tid] = eb;
+        };
+
+        if(builder && count > 0)
+            build(0);
+        __syncthreads();
+
+        // ---- main loop over the projections of the batch -----------------------------------------------------------
+        const float m_f = static_cast<float>(wz * 32 + lane);
+        #pragma unroll 1
+        for(int p = 0; p < count; ++p)
+        {
+            if(builder && p + 1 < count)
+                build(p + 1);
+
+            const int stage = p % CFG::STAGES;
+            mbar_wait(smem_u32(&bars[stage]), static_cast<uint32_t>((p / CFG::STAGES) & 1));
+
+            const box_origin o = origin[p];
+            const float4* ta = tab_a + (p & 1) * CFG::COLS;
+            const float2* tb = tab_b + (p & 1) * CFG::COLS;
+            if(o.all_valid)
+                consume<CFG, false>(acc, ta, tb, col0, m_f, 0, 0u);
+            else
+                consume<CFG, true>(acc, ta, tb, col0, m_f, -o.v0, static_cast<uint32_t>(g.p_dim_y - 1u));
+
+            __syncthreads(); // stage and table[p&1] are free again; table[(p+1)&1] is complete
+            if(tid == 0 && p + CFG::STAGES < count)
+            {
+                const int q = p + CFG::STAGES;
+                const uint32_t bar = smem_u32(&bars[stage]);
+                mbar_expect_tx(bar, CFG::STAGE_BYTES);
+                tma_load_3d(smem_u32(stage_mem + size_t(stage) * CFG::STAGE_BYTES), &tmap, bar, origin[q].v0,
+                            origin[q].h0, static_cast<int>(first_slot) + q);
+            }
+        }
+
+        // ---- epilogue: one store per voxel ---------------------------------------------------------------------------
+        #pragma unroll
+        for(int i = 0; i < CFG::CPW; ++i)
+        {
+            const uint32_t x = x0 + (col0 + i) % CFG::TX, y = y0 + (col0 + i) / CFG::TX;
+            if(z_ok && x < g.v_dim_x && y < g.v_dim_y)
+                vol[static_cast<size_t>(z) * slice + static_cast<size_t>(y) * g.v_dim_x + x] = acc[i];
+        }
+    }
+
+    // ---- host side -------------------------------------------------------------------------------------------------
+
+    static PFN_cuTensorMapEncodeTiled_v12000 get_encode()
+    {
+        static PFN_cuTensorMapEncodeTiled_v12000 fn = nullptr;
+        if(fn == nullptr)
+        {
+            void* p = nullptr;
+            cudaDriverEntryPointQueryResult q{};
+            if(cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess
+               && q == cudaDriverEntryPointSuccess)
+                fn = reinterpret_cast<PFN_cuTensorMapEncodeTiled_v12000>(p);
+        }
+        return fn;
+    }
+
+    static int make_tensor_map(paris_b200_ctx* ctx, const float* d_stack, uint32_t n_row, uint32_t pitch, uint32_t slots,
+                               size_t slot_floats, uint32_t box_v, uint32_t box_h)
+    {
+        auto& c = ctx->tma;
+        if(c.valid && c.base == d_stack && c.n_row == n_row && c.pitch == pitch && c.slots == slots && c.box_v == box_v
+           && c.box_h == box_h)
+            return PARIS_B200_OK;
+        auto encode = get_encode();
+        if(encode == nullptr)
+        {
+            set_error("cuTensorMapEncodeTiled is not available from the driver");
+            return PARIS_B200_ECUDA;
+        }
+        const cuuint64_t dims[3] = {pitch, n_row, slots};
+        const cuuint64_t strides[2] = {static_cast<cuuint64_t>(pitch) * 4u, static_cast<cuuint64_t>(slot_floats) * 4u};
+        const cuuint32_t box[3] = {box_v, box_h, 1u};
+        const cuuint32_t elem[3] = {1u, 1u, 1u};
+        const CUresult r = encode(&c.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(d_stack), dims, strides,
+                                  box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
+                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if(r != CUDA_SUCCESS)
+        {
+            set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
+            return PARIS_B200_ECUDA;
+        }
+        c.base = d_stack;
+        c.n_row = n_row;
+        c.pitch = pitch;
+        c.slots = slots;
+        c.box_v = box_v;
+        c.box_h = box_h;
+        c.valid = true;
+        return PARIS_B200_OK;
+    }
+
+    // Conservative extent of a tile's footprint on the detector, over every angle and every tile of the slab.
+    struct footprint
+    {
+        bool ok;
+        int need_h, need_v;
+    };
+
+    static footprint tile_footprint(const bp_geometry& g, int tx, int ty, int tz)
+    {
+        footprint f{false, 0, 0};
+        // farthest voxel column from the rotation axis, and farthest slice from the mid-plane, in millimetres
+        auto extent = [](uint32_t off, uint32_t n, uint32_t full, float size) {
+            const double lo = (static_cast<double>(off) + 0.5 - full / 2.0) * size;
+            const double hi = (static_cast<double>(off) + n - 0.5 - full / 2.0) * size;
+            return std::max(std::fabs(lo), std::fabs(hi));
+        };
+        const double rx = extent(g.off_x, g.v_dim_x, g.full_x, g.l_vx_x);
+        const double ry = extent(g.off_y, g.v_dim_y, g.full_y, g.l_vx_y);
+        const double rz = extent(g.off_z, g.v_dim_z, g.full_z, g.l_vx_z);
+        const double r = std::sqrt(rx * rx + ry * ry);
+        const double d_so = g.d_so;
+        if(!(d_so > 0.0) || !(d_so - r > 0.05 * d_so))
+            return f; // source (nearly) inside the slab: magnification unbounded
+        const double fmax = g.d_sd / (d_so - r);
+        const double diag = std::sqrt(std::pow((tx - 1) * static_cast<double>(g.l_vx_x), 2)
+                                    + std::pow((ty - 1) * static_cast<double>(g.l_vx_y), 2));
+        const double dfac = fmax * fmax / g.d_sd * diag;                 // change of the magnification across a tile
+        const double span_h = (diag * fmax + r * dfac) / g.l_px_x;       // |d(t*factor)| <= |dt|*f + |t|*|df|
+        const double span_v = ((tz - 1) * static_cast<double>(g.l_vx_z) * fmax + rz * dfac) / g.l_px_y;
+        // kernel needs (floor(max) + 2) - (floor(min) - 1) < B  <=  span + 1 + 3 < B
+        f.need_h = static_cast<int>(std::ceil(span_h)) + 5;
+        f.need_v = static_cast<int>(std::ceil(span_v)) + 5 + 3; // + alignment of the box start to 4 floats
+        f.ok = true;
+        return f;
+    }
+
+    template <class CFG>
+    static int launch_cfg(paris_b200_ctx* ctx, const float* d_stack, size_t slot_floats, uint32_t first,
+                          const bp_geometry& g, const bp_angles& a, float* d_vol)
+    {
+        // the tensor map spans the slots this launch can touch: [0, first + count)
+        const uint32_t slots = first + static_cast<uint32_t>(a.count);
+        PB_TRY(make_tensor_map(ctx, d_stack, g.p_dim_x, g.pitch, slots, slot_floats, CFG::BV, CFG::BH));
+        auto kern = bp_tma_kernel<CFG>;
+        PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(CFG::SMEM)));
+        const dim3 grid((g.v_dim_x + CFG::TX - 1) / CFG::TX, (g.v_dim_y + CFG::TY - 1) / CFG::TY,
+                        (g.v_dim_z + CFG::TZ - 1) / CFG::TZ);
+        if(grid.y > 65535u || grid.z > 65535u)
+        {
+            set_error("slab too large for the backprojection grid");
+            return PARIS_B200_EINVAL;
+        }
+        kern<<<grid, CFG::THREADS, CFG::SMEM, ctx->compute>>>(ctx->tma.map, d_vol, g, a, first);
+        PB_CUDA(cudaGetLastError());
+        ++ctx->launches;
+        return PARIS_B200_OK;
+    }
+
+    //                      TX  TY  WZ CPW  BH   BV  STAGES
+    using cfg_fine   = tile_cfg<16, 16, 2, 32, 40, 96, 6>;    // ~1 detector pixel per voxel (PARIS-derived volumes)
+    using cfg_coarse = tile_cfg<16, 16, 2, 32, 64, 164, 4>;   // ~2 detector pixels per voxel (K^3 from a (2K)^2 detector)
+
+    int launch_bp_tma(paris_b200_ctx* ctx, const float* d_stack, size_t slot_floats, uint32_t first,
+                      const bp_geometry& g, const bp_angles& a, float* d_vol, bool required, bool* handled)
     {
         *handled = false;
+        const footprint f = tile_footprint(g, 16, 16, 64);
+        const bool aligned = (reinterpret_cast<uintptr_t>(d_stack) % 16u) == 0u && (g.pitch % 4u) == 0u;
+        if(f.ok && aligned)
+        {
+            if(f.need_h <= cfg_fine::BH && f.need_v <= cfg_fine::BV)
+            {
+                PB_TRY(launch_cfg<cfg_fine>(ctx, d_stack, slot_floats, first, g, a, d_vol));
+                *handled = true;
+                return PARIS_B200_OK;
+            }
+            if(f.need_h <= cfg_coarse::BH && f.need_v <= cfg_coarse::BV)
+            {
+                PB_TRY(launch_cfg<cfg_coarse>(ctx, d_stack, slot_floats, first, g, a, d_vol));
+                *handled = true;
+                return PARIS_B200_OK;
+            }
+        }
         if(required)
         {
-            set_error("TMA backprojection kernel not available");
+            set_error("geometry does not fit the TMA kernel's tiles (footprint %d x %d detector cells per tile)",
+                      f.need_h, f.need_v);
             return PARIS_B200_ESTATE;
         }
         return PARIS_B200_OK;
