@@ -182,15 +182,23 @@ int paris_b200_weight_filter(paris_b200_ctx* ctx, float* d_proj, uint32_t dim_x,
  * returns; the volume is updated when the batch fills, on paris_b200_flush(), or when the volume is
  * observed by paris_b200_vol_d2h().  d_proj may be freed (paris_b200_dev_free) right after the call.
  * If flags has PARIS_B200_BP_FUSE_WEIGHT_FILTER, d_proj holds the RAW projection and weight + filter
- * (with `filter`, using h_min/v_min/d_sd derived as src/weighting.cpp:37-42 does) are applied on the way
- * into the stack by the fused kernel; d_proj itself is left untouched. */
+ * (with `filter`; the weighting scalars from `weighting`, or derived from det as src/weighting.cpp:37-42
+ * does when that is NULL) are applied on the way into the stack by the fused kernel; d_proj itself is
+ * left untouched. */
 #define PARIS_B200_BP_FUSE_WEIGHT_FILTER 1u
+/* the five scalars backend::weight receives (src/weighting.cpp:37-44) */
+typedef struct paris_b200_weighting
+{
+    float h_min, v_min, d_sd, l_px_row, l_px_col;
+} paris_b200_weighting;
 int paris_b200_backproject(paris_b200_ctx* ctx, const float* d_proj, uint32_t dim_x, uint32_t dim_y,
                            float* d_vol, uint32_t v_dim_x, uint32_t v_dim_y, uint32_t v_dim_z, uint32_t v_offset,
                            const paris_b200_detector_geometry* det, const paris_b200_volume_geometry* vol_full,
                            int enable_roi, const paris_b200_roi* roi,
                            float sin_phi, float cos_phi, float delta_s_mm, float delta_t_mm,
-                           uint32_t flags, const paris_b200_filter* filter);
+                           uint32_t flags, const paris_b200_filter* filter, const paris_b200_weighting* weighting);
+/* block the calling thread until every H2D copy issued so far has left its host buffer */
+int paris_b200_h2d_wait(paris_b200_ctx* ctx);
 /* run every pending backprojection batch of the context (asynchronous on the compute stream) */
 int paris_b200_flush(paris_b200_ctx* ctx);
 

@@ -92,7 +92,8 @@ SIGNATURES = {
     "paris_b200_apply_filter": (C.c_int, [_vp, _fp, _u32, _u32, _vp, _u32, _u32]),
     "paris_b200_weight_filter": (C.c_int, [_vp, _fp, _u32, _u32, _f, _f, _f, _f, _f, _vp, _u32]),
     "paris_b200_backproject": (C.c_int, [_vp, _fp, _u32, _u32, _fp, _u32, _u32, _u32, _u32, _P(DetectorGeometry),
-                                         _P(VolumeGeometry), C.c_int, _P(Roi), _f, _f, _f, _f, _u32, _vp]),
+                                         _P(VolumeGeometry), C.c_int, _P(Roi), _f, _f, _f, _f, _u32, _vp, _vp]),
+    "paris_b200_h2d_wait": (C.c_int, [_vp]),
     "paris_b200_flush": (C.c_int, [_vp]),
     "paris_b200_stack_slot_bytes": (C.c_int, [_u32, _u32, _P(C.c_size_t), _P(_u32)]),
     "paris_b200_filter_to_stack": (C.c_int, [_vp, _fp, _P(DetectorGeometry), _vp, _fp, _u32]),
@@ -302,7 +303,7 @@ class Context:
         check(self._L.paris_b200_backproject(self.h, d_proj, dim_x, dim_y, d_vol, v_dims[0], v_dims[1], v_dims[2],
                                              v_offset, C.byref(det), C.byref(vol_full), int(roi is not None),
                                              C.byref(roi) if roi is not None else None, sin_phi, cos_phi,
-                                             delta_s_mm, delta_t_mm, flags, filt))
+                                             delta_s_mm, delta_t_mm, flags, filt, None))
 
     def flush(self):
         check(self._L.paris_b200_flush(self.h))

@@ -442,6 +442,14 @@ extern "C" int paris_b200_h2d_done(paris_b200_ctx* ctx, int* done)
     return PARIS_B200_OK;
 }
 
+extern "C" int paris_b200_h2d_wait(paris_b200_ctx* ctx)
+{
+    PB_CHECK_ARG(ctx != nullptr);
+    PB_TRY(bind(ctx));
+    PB_CUDA(cudaStreamSynchronize(ctx->copy));
+    return PARIS_B200_OK;
+}
+
 extern "C" int paris_b200_proj_d2h(paris_b200_ctx* ctx, const float* d_src, float* h_dst, uint32_t dim_x,
                                    uint32_t dim_y)
 {
@@ -674,7 +682,8 @@ extern "C" int paris_b200_backproject(paris_b200_ctx* ctx, const float* d_proj, 
                                       uint32_t v_offset, const paris_b200_detector_geometry* det,
                                       const paris_b200_volume_geometry* vol_full, int enable_roi,
                                       const paris_b200_roi* roi, float sin_phi, float cos_phi, float delta_s_mm,
-                                      float delta_t_mm, uint32_t flags, const paris_b200_filter* filter)
+                                      float delta_t_mm, uint32_t flags, const paris_b200_filter* filter,
+                                      const paris_b200_weighting* weighting)
 {
     PB_CHECK_ARG(ctx != nullptr && d_proj != nullptr && d_vol != nullptr && det != nullptr && vol_full != nullptr);
     PB_CHECK_ARG(dim_x == det->n_row && dim_y == det->n_col);
@@ -711,11 +720,22 @@ extern "C" int paris_b200_backproject(paris_b200_ctx* ctx, const float* d_proj, 
         const float n_col_f = static_cast<float>(det->n_col);
         weight_params w{};
         w.enable = 1;
-        w.h_min = (det->delta_s * det->l_px_row) - ((n_row_f * det->l_px_row) / 2);
-        w.v_min = (det->delta_t * det->l_px_col) - ((n_col_f * det->l_px_col) / 2);
-        w.d_sd = std::fabs(det->d_so) + std::fabs(det->d_od);
-        w.l_px_row = det->l_px_row;
-        w.l_px_col = det->l_px_col;
+        if(weighting != nullptr)
+        {
+            w.h_min = weighting->h_min;
+            w.v_min = weighting->v_min;
+            w.d_sd = weighting->d_sd;
+            w.l_px_row = weighting->l_px_row;
+            w.l_px_col = weighting->l_px_col;
+        }
+        else
+        {
+            w.h_min = (det->delta_s * det->l_px_row) - ((n_row_f * det->l_px_row) / 2);
+            w.v_min = (det->delta_t * det->l_px_col) - ((n_col_f * det->l_px_col) / 2);
+            w.d_sd = std::fabs(det->d_so) + std::fabs(det->d_od);
+            w.l_px_row = det->l_px_row;
+            w.l_px_col = det->l_px_col;
+        }
         PB_TRY(launch_filter(ctx, d_proj, slot, dim_x, dim_y, filter, w, true, ctx->stack_pitch));
     }
     else

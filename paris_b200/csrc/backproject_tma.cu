@@ -195,10 +195,16 @@ namespace pb
         const int wc = warp / CFG::WZ;      // which column group
         const int count = ang.count;
 
-        const uint32_t x0 = blockIdx.x * CFG::TX;
-        const uint32_t y0 = blockIdx.y * CFG::TY;
-        const uint32_t z0 = blockIdx.z * CFG::TZ;
-        const bool full_tile = x0 + CFG::TX <= g.v_dim_x && y0 + CFG::TY <= g.v_dim_y && z0 + CFG::TZ <= g.v_dim_z;
+        // Tiles are anchored at multiples of the tile size in GLOBAL voxel indices (ROI and slab offsets
+        // included), and every per-tile quantity below is derived from the full, unclipped tile.  A voxel
+        // therefore sees the same arithmetic whichever ROI / z-slab decomposition it is reconstructed in:
+        // slabs and ROI blocks are bit-identical to the corresponding crop of the one-piece reconstruction.
+        const uint32_t x0 = (g.off_x / CFG::TX + blockIdx.x) * CFG::TX;   // global index of the tile's first voxel
+        const uint32_t y0 = (g.off_y / CFG::TY + blockIdx.y) * CFG::TY;
+        const uint32_t z0 = (g.off_z / CFG::TZ + blockIdx.z) * CFG::TZ;
+        const bool full_tile = x0 >= g.off_x && x0 + CFG::TX <= g.off_x + g.v_dim_x
+                            && y0 >= g.off_y && y0 + CFG::TY <= g.off_y + g.v_dim_y
+                            && z0 >= g.off_z && z0 + CFG::TZ <= g.off_z + g.v_dim_z;
 
         // ---- prologue 1: barriers, box origins for every projection of the batch ---------------------------
         if(tid == 0)
@@ -212,18 +218,17 @@ namespace pb
         {
             const float sn = ang.sn[tid], cs = ang.cs[tid];
             // extremes over the tile's corners (h and factor are projective/monotone over the convex tile)
-            const uint32_t xe = min(x0 + CFG::TX, g.v_dim_x) - 1u, ye = min(y0 + CFG::TY, g.v_dim_y) - 1u;
-            const uint32_t ze = min(z0 + CFG::TZ, g.v_dim_z) - 1u;
-            const double zlo = centered_d(z0 + g.off_z, g.full_z, g.l_vx_z);
-            const double zhi = centered_d(ze + g.off_z, g.full_z, g.l_vx_z);
+            const uint32_t xe = x0 + CFG::TX - 1u, ye = y0 + CFG::TY - 1u, ze = z0 + CFG::TZ - 1u;
+            const double zlo = centered_d(z0, g.full_z, g.l_vx_z);
+            const double zhi = centered_d(ze, g.full_z, g.l_vx_z);
             float hmin = 3.0e38f, hmax = -3.0e38f;
             double vmin = 1.0e300, vmax = -1.0e300;
             #pragma unroll
             for(int c = 0; c < 4; ++c)
             {
                 const uint32_t k = (c & 1) ? xe : x0, l = (c & 2) ? ye : y0;
-                const column_terms ct = project_column(centered(k + g.off_x, g.full_x, g.l_vx_x),
-                                                       centered(l + g.off_y, g.full_y, g.l_vx_y), sn, cs, g);
+                const column_terms ct = project_column(centered(k, g.full_x, g.l_vx_x),
+                                                       centered(l, g.full_y, g.l_vx_y), sn, cs, g);
                 hmin = fminf(hmin, ct.h);
                 hmax = fmaxf(hmax, ct.h);
                 const double va = row_of(zlo, static_cast<double>(ct.factor), g);
@@ -269,14 +274,15 @@ namespace pb
 
         // this thread's voxels: columns col0 .. col0+CPW-1 of the tile at slice z
         const int col0 = wc * CFG::CPW;
-        const uint32_t z = z0 + wz * 32 + lane;
+        // (local indices wrap to huge values for voxels before the region's origin and fail the range test)
+        const uint32_t z = z0 + wz * 32 + lane - g.off_z;
         const bool z_ok = z < g.v_dim_z;
         const size_t slice = static_cast<size_t>(g.v_dim_x) * g.v_dim_y;
         float acc[CFG::CPW];
         #pragma unroll
         for(int i = 0; i < CFG::CPW; ++i)
         {
-            const uint32_t x = x0 + (col0 + i) % CFG::TX, y = y0 + (col0 + i) / CFG::TX;
+            const uint32_t x = x0 + (col0 + i) % CFG::TX - g.off_x, y = y0 + (col0 + i) / CFG::TX - g.off_y;
             const bool ok = z_ok && x < g.v_dim_x && y < g.v_dim_y;
             acc[i] = ok ? vol[static_cast<size_t>(z) * slice + static_cast<size_t>(y) * g.v_dim_x + x] : 0.f;
         }
@@ -287,9 +293,9 @@ namespace pb
         double z_m0 = 0.0;
         if(builder)
         {
-            bx_k = centered(x0 + tid % CFG::TX + g.off_x, g.full_x, g.l_vx_x);
-            by_l = centered(y0 + tid / CFG::TX + g.off_y, g.full_y, g.l_vx_y);
-            z_m0 = centered_d(z0 + g.off_z, g.full_z, g.l_vx_z);
+            bx_k = centered(x0 + tid % CFG::TX, g.full_x, g.l_vx_x);
+            by_l = centered(y0 + tid / CFG::TX, g.full_y, g.l_vx_y);
+            z_m0 = centered_d(z0, g.full_z, g.l_vx_z);
         }
         const uint32_t stage_base0 = smem_u32(stage_mem);
 
@@ -359,7 +365,7 @@ namespace pb
         #pragma unroll
         for(int i = 0; i < CFG::CPW; ++i)
         {
-            const uint32_t x = x0 + (col0 + i) % CFG::TX, y = y0 + (col0 + i) / CFG::TX;
+            const uint32_t x = x0 + (col0 + i) % CFG::TX - g.off_x, y = y0 + (col0 + i) / CFG::TX - g.off_y;
             if(z_ok && x < g.v_dim_x && y < g.v_dim_y)
                 vol[static_cast<size_t>(z) * slice + static_cast<size_t>(y) * g.v_dim_x + x] = acc[i];
         }
@@ -427,14 +433,16 @@ namespace pb
     {
         footprint f{false, 0, 0};
         // farthest voxel column from the rotation axis, and farthest slice from the mid-plane, in millimetres
-        auto extent = [](uint32_t off, uint32_t n, uint32_t full, float size) {
-            const double lo = (static_cast<double>(off) + 0.5 - full / 2.0) * size;
-            const double hi = (static_cast<double>(off) + n - 0.5 - full / 2.0) * size;
+        // (tiles are anchored at global multiples of the tile size and may stick out of the region)
+        auto extent = [](uint32_t off, uint32_t n, uint32_t full, float size, int tile) {
+            const uint32_t first = off / tile * tile, last = (off + n - 1u) / tile * tile + tile - 1u;
+            const double lo = (static_cast<double>(first) + 0.5 - full / 2.0) * size;
+            const double hi = (static_cast<double>(last) + 0.5 - full / 2.0) * size;
             return std::max(std::fabs(lo), std::fabs(hi));
         };
-        const double rx = extent(g.off_x, g.v_dim_x, g.full_x, g.l_vx_x);
-        const double ry = extent(g.off_y, g.v_dim_y, g.full_y, g.l_vx_y);
-        const double rz = extent(g.off_z, g.v_dim_z, g.full_z, g.l_vx_z);
+        const double rx = extent(g.off_x, g.v_dim_x, g.full_x, g.l_vx_x, tx);
+        const double ry = extent(g.off_y, g.v_dim_y, g.full_y, g.l_vx_y, ty);
+        const double rz = extent(g.off_z, g.v_dim_z, g.full_z, g.l_vx_z, tz);
         const double r = std::sqrt(rx * rx + ry * ry);
         const double d_so = g.d_so;
         if(!(d_so > 0.0) || !(d_so - r > 0.05 * d_so))
@@ -461,8 +469,10 @@ namespace pb
         PB_TRY(make_tensor_map(ctx, d_stack, g.p_dim_x, g.pitch, slots, slot_floats, CFG::BV, CFG::BH));
         auto kern = bp_tma_kernel<CFG>;
         PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(CFG::SMEM)));
-        const dim3 grid((g.v_dim_x + CFG::TX - 1) / CFG::TX, (g.v_dim_y + CFG::TY - 1) / CFG::TY,
-                        (g.v_dim_z + CFG::TZ - 1) / CFG::TZ);
+        // tiles anchored at global multiples of the tile size: first tile holds off, last holds off + dim - 1
+        auto tiles = [](uint32_t off, uint32_t dim, uint32_t t) { return (off + dim - 1u) / t - off / t + 1u; };
+        const dim3 grid(tiles(g.off_x, g.v_dim_x, CFG::TX), tiles(g.off_y, g.v_dim_y, CFG::TY),
+                        tiles(g.off_z, g.v_dim_z, CFG::TZ));
         if(grid.y > 65535u || grid.z > 65535u)
         {
             set_error("slab too large for the backprojection grid");
