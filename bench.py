@@ -1,0 +1,352 @@
+#!/usr/bin/env python
+"""bench.py -- FDK hot path (weight -> ramp filter -> backprojection) on N B200s, one JSON line.
+
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c1|c2|c3]
+
+A "step" is one full reconstruction of the workload from its raw projections:
+  value   device-resident: raw stack already in HBM; per step the fused weight+filter kernel fills the
+          filtered stack and the batched backprojection kernel builds the volume (CUDA events on the
+          library's compute stream).  GUPS = voxels x projections / seconds / 1e9.
+  e2e     the same reconstruction through the reference-shaped per-projection loop of the C++ host layer
+          (load -> weight -> filter -> backproject per projection, then copy_d2h): raw projections start
+          in pinned HOST memory and the volume ends in pinned HOST memory, copies inside the timed region.
+N > 1 (torchrun): the region is cut into N z-slabs (one per rank); every rank filters 1/N of the
+projections, an NCCL all-gather distributes the filtered stack, every rank backprojects all projections
+into its own slab (no reduction).  Strong scaling: the workload is the same for every N.
+
+--impl reference times the reference's own OpenMP backend (oracle/_ref, built from /root/reference; the
+plain-C port if that is absent) on the host cores, on a bounded sample of the same workload.
+"""
+from __future__ import annotations
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import tempfile
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+CONFIGS = {
+    # name: (detector n, projections, volume k, description)
+    "c1": (256, 256, 128, "128^3 volume from 256 projections of 256^2 detector"),
+    "c2": (1024, 720, 512, "512^3 volume from 720 projections of 1024^2 detector, full-scan FDK, float32"),
+    "c3": (2048, 1440, 1024, "1024^3 volume from 1440 projections of 2048^2 detector"),
+}
+
+
+def geometry(cfg: str):
+    from paris_b200 import capi
+    n, n_proj, k, _ = CONFIGS[cfg]
+    l_px = 0.2 * 1024 / n  # 204.8 mm detector
+    det = capi.DetectorGeometry(n, n, l_px, l_px, 0.0, 0.0, 500.0, 500.0, 360.0 / n_proj)
+    nat = capi.calculate_volume_geometry(det)
+    # "K^3 from a (2K)^2 detector": the natural full-FOV volume sampled with K^3 larger voxels
+    f32 = np.float32
+    vol = capi.VolumeGeometry(k, k, k, f32(nat.l_vx_x * nat.dim_x / k), f32(nat.l_vx_y * nat.dim_y / k),
+                              f32(nat.l_vx_z * nat.dim_z / k))
+    return det, vol, n_proj
+
+
+def ellipsoids(det):
+    from paris_b200 import phantom
+    r = 0.9 * phantom.fov_radius(det.n_row, det.l_px_row, det.delta_s, det.d_so, det.d_od)
+    return phantom.scaled_ellipsoids(phantom.SHEPP_LOGAN_3D, r)
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, device: int):
+        self.device = device
+        self.proc = None
+        self.path = None
+
+    def start(self):
+        try:
+            f = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False)
+            self.path = f.name
+            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.FIELDS}",
+                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f,
+                                         stderr=subprocess.DEVNULL)
+        except OSError:
+            self.proc = None
+
+    def stop(self) -> dict:
+        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
+        if self.proc is None:
+            return out
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=5)
+        except subprocess.TimeoutExpired:
+            self.proc.kill()
+        sm, mx, power, reasons = [], [], [], set()
+        try:
+            for line in open(self.path):
+                p = [x.strip() for x in line.split(",")]
+                if len(p) < 9:
+                    continue
+                try:
+                    sm.append(float(p[1]))
+                    mx.append(float(p[2]))
+                    power.append(float(p[3]))
+                except ValueError:
+                    continue
+                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
+                                   p[5:9]):
+                    if v.lower().startswith("active"):
+                        reasons.add(name)
+            os.unlink(self.path)
+        except OSError:
+            pass
+        if sm:
+            # "under load": the upper half of the samples (the sampler also sees the gaps between steps)
+            busy = sorted(sm)[len(sm) // 2:]
+            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
+                       samples=len(sm), power_w_max=float(max(power)))
+        return out
+
+
+def measured_peaks() -> dict:
+    try:
+        return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    except (OSError, ValueError):
+        return {}
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# CPU arm: the reference's OpenMP backend (or the plain-C port) on a bounded sample of the workload
+# ------------------------------------------------------------------------------------------------------------------
+
+def cpu_reconstruct_sample(cfg: str, budget_s: float, fetch=None):
+    """Times weight+filter+backproject of the reference on `p` projections of the workload (full region).
+    Returns (gups_total, gups_backprojection, cores, kind, description, seconds)."""
+    import oracle
+    from paris_b200 import phantom
+    det, vol, n_proj = geometry(cfg)
+    odet = oracle.DetectorGeometry(det.n_row, det.n_col, det.l_px_row, det.l_px_col, det.delta_s, det.delta_t,
+                                   det.d_so, det.d_od, det.delta_phi)
+    ovol = oracle.VolumeGeometry(vol.dim_x, vol.dim_y, vol.dim_z, vol.l_vx_x, vol.l_vx_y, vol.l_vx_z)
+    if oracle.have_ref():
+        impl, kind = oracle.Reference(), "reference"
+    else:
+        impl, kind = oracle.Port(), "port"
+    cores = impl.num_threads()
+    shape = (vol.dim_z, vol.dim_y, vol.dim_x)
+    voxels = vol.dim_x * vol.dim_y * vol.dim_z
+
+    def raw(count, stride):
+        if fetch is not None:
+            return fetch(count, stride)
+        ang = np.float32(det.delta_phi) * (np.arange(count, dtype=np.float32) * np.float32(stride))
+        return phantom.project(ellipsoids(det), det.n_row, det.n_col, det.l_px_row, det.l_px_col, det.delta_s,
+                               det.delta_t, det.d_so, det.d_od, ang.astype(np.float64))
+
+    # calibrate on 2 projections (the first builds FFT plans / statics and is excluded by the callee)
+    stride = max(1, n_proj // 16)
+    _, t = impl.reconstruct(raw(2, stride), shape, odet, ovol, idx_stride=stride)
+    per_proj = max(sum(t), 1e-4)
+    count = int(max(2, min(64, budget_s / per_proj))) + 1
+    stride = max(1, n_proj // count)
+    t0 = time.perf_counter()
+    _, t = impl.reconstruct(raw(count, stride), shape, odet, ovol, idx_stride=stride)
+    wall = time.perf_counter() - t0
+    timed = count - 1
+    gups_total = voxels * timed / sum(t) / 1e9
+    gups_bp = voxels * timed / t[2] / 1e9
+    desc = (f"{timed} of {n_proj} projections (every {stride}th) of {CONFIGS[cfg][3]}, full region, "
+            f"weight {t[0]:.2f}s + filter {t[1]:.2f}s + backproject {t[2]:.2f}s")
+    return gups_total, gups_bp, cores, kind, desc, wall
+
+
+def run_reference(args, rank: int):
+    if rank != 0:
+        return
+    det, vol, n_proj = geometry(args.config)
+    vals, info = [], None
+    for i in range(args.warmup + args.steps):
+        g_total, g_bp, cores, kind, desc, wall = cpu_reconstruct_sample(args.config, budget_s=args.cpu_budget)
+        if i >= args.warmup:
+            vals.append(g_total)
+        info = (g_bp, cores, kind, desc, wall)
+    value = float(np.mean(vals))
+    updates = vol.dim_x * vol.dim_y * vol.dim_z * n_proj
+    line = {
+        "impl": "reference", "metric": "fdk_reconstruction_gups", "value": value, "unit": "GUPS",
+        "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
+        "ms_per_step": updates / value / 1e6, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
+        "dtype": "f32", "data": "synthetic",
+        "config": {"workload": CONFIGS[args.config][3], "note": "ms_per_step extrapolated from the sample"},
+        "cpu_baseline": {"value": value, "unit": "GUPS", "cores": info[1], "kind": info[2], "sample": info[3],
+                         "backprojection_only_gups": info[0]},
+        "e2e": {"value": value, "unit": "GUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0,
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ------------------------------------------------------------------------------------------------------------------
+# B200 arm
+# ------------------------------------------------------------------------------------------------------------------
+
+def run_b200(args, rank: int, world: int, local_rank: int):
+    from paris_b200 import capi, dropin
+    from paris_b200.pipeline import angle_sin_cos
+
+    dist = None
+    if world > 1:
+        import torch
+        import torch.distributed as dist_mod
+        torch.cuda.set_device(local_rank)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+        dist = dist_mod
+
+    det, vol, n_proj = geometry(args.config)
+    n = det.n_row
+    px = n * n
+    dims = (vol.dim_x, vol.dim_y, vol.dim_z)
+    voxels = dims[0] * dims[1] * dims[2]
+    updates = voxels * n_proj
+
+    # one context per process, shared by the C++ loop (e2e) and the stack-level calls (value)
+    from paris_b200.multi import SlabPlan, MultiGpuReconstructor
+    plan = SlabPlan(dims[2], world, rank)
+    rec = MultiGpuReconstructor(local_rank, det, vol, n_proj, plan, dist)
+    ctx = rec.ctx
+
+    # synthetic raw stack: this rank's share of the projections, generated on the device, mirrored on the host
+    rec.generate_inputs(ellipsoids(det))
+
+    sampler = ClockSampler(local_rank)
+    barrier = (lambda: dist.barrier()) if dist is not None else (lambda: None)
+
+    # ---- device-resident steps -------------------------------------------------------------------------------
+    for _ in range(args.warmup):
+        rec.step_resident()
+    ctx.sync()
+    barrier()
+    sampler.start()
+    launches0 = ctx.launch_count()
+    t_filter = t_gather = t_bp = 0.0
+    t0 = time.perf_counter()
+    e_start = ctx.event()
+    for _ in range(args.steps):
+        tf, tg, tb = rec.step_resident(timed=True)
+        t_filter += tf
+        t_gather += tg
+        t_bp += tb
+    e_stop = ctx.event()
+    ms_total = ctx.elapsed_ms(e_start, e_stop)
+    ctx.sync()
+    barrier()
+    wall_resident = time.perf_counter() - t0
+    launches = ctx.launch_count() - launches0
+
+    # ---- end-to-end steps (host -> host through the reference-shaped loop) ---------------------------------------
+    for _ in range(max(1, args.warmup // 2)):
+        rec.step_e2e()
+    barrier()
+    e2e_ms = []
+    for _ in range(args.steps):
+        barrier()
+        t1 = time.perf_counter()
+        rec.step_e2e()
+        ctx.sync()
+        e2e_ms.append((time.perf_counter() - t1) * 1e3)
+    clocks = sampler.stop()
+
+    ms_step = ms_total / args.steps
+    e2e_step = float(np.mean(e2e_ms))
+    if dist is not None:
+        import torch
+        t = torch.tensor([ms_step, e2e_step, t_filter, t_gather, t_bp], dtype=torch.float64, device="cuda")
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms_step, e2e_step, t_filter, t_gather, t_bp = [float(x) for x in t.tolist()]
+
+    if rank == 0:
+        peaks = measured_peaks()
+        hbm_peak = float(peaks.get("hbm_gbs", 6650.0))
+        peak_src = "measured" if "hbm_gbs" in peaks else "fallback"
+        sm_mhz = clocks.get("sm_mhz") or float(peaks.get("sm_max_mhz", 1965.0))
+        # backprojection: 4 point-fetched float samples per voxel update from shared memory
+        bp_s = t_bp / args.steps / 1e3
+        filt_s = t_filter / args.steps / 1e3
+        my_updates = plan.slab_dz * dims[0] * dims[1] * n_proj
+        bp_gbs = 16.0 * my_updates / bp_s / 1e9
+        smem_peak = 148 * 128 * sm_mhz * 1e6 / 1e9
+        filt_gbs = 8.0 * px * rec.my_count / filt_s / 1e9
+        line = {
+            "metric": "fdk_reconstruction_gups", "value": updates / (ms_step / 1e3) / 1e9, "unit": "GUPS",
+            "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
+            "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+            "config": {"workload": CONFIGS[args.config][3], "parallelism": f"z-slab x{world}",
+                       "l2": "inputs larger than L2 (raw + filtered stack >= 6 GB at c2)",
+                       "bp_batch": rec.batch, "stack_layout": "transposed, v fastest"},
+            "backprojection_gups": my_updates * world / bp_s / 1e9,
+            "stage_ms": {"filter": filt_s * 1e3, "allgather": t_gather / args.steps, "backproject": bp_s * 1e3},
+            "roofline": {"kernel": "bp_tma_kernel", "bound": "smem", "achieved": bp_gbs, "peak": smem_peak,
+                         "unit": "GB/s", "frac": bp_gbs / smem_peak, "traffic": None,
+                         "note": "16 B of shared-memory sample fetches per voxel update; peak = 148 SMs x 128 B/clk x "
+                                 f"{sm_mhz:.0f} MHz (SM clock sampled during the run); not an HBM- or tensor-bound kernel"},
+            "roofline_filter": {"kernel": "filter_kernel", "bound": "hbm", "achieved": filt_gbs, "peak": hbm_peak,
+                                "unit": "GB/s", "frac": filt_gbs / hbm_peak, "traffic": None,
+                                "note": f"8 B per detector pixel; peak {peak_src} (MEASURED_PEAKS.json hbm_gbs)"},
+            "e2e": {"value": updates / (e2e_step / 1e3) / 1e9, "unit": "GUPS", "seconds": e2e_step / 1e3,
+                    "h2d_bytes_per_step": 4 * px * n_proj, "d2h_bytes_per_step": 4 * voxels,
+                    "path": "paris_b200_dropin_reconstruct: per-projection load/weight/filter/backproject + copy_d2h"},
+            "gpu_launches": int(launches), "clocks": clocks,
+            "wall_s_resident": wall_resident,
+        }
+        if world == 1 and not args.no_cpu_baseline:
+            try:
+                g_total, g_bp, cores, kind, desc, _ = cpu_reconstruct_sample(args.config, budget_s=args.cpu_budget,
+                                                                           fetch=rec.host_sample)
+                line["cpu_baseline"] = {"value": g_total, "unit": "GUPS", "cores": cores, "kind": kind, "sample": desc,
+                                        "backprojection_only_gups": g_bp}
+            except Exception as e:  # the CPU checker must never take the GPU number down with it
+                line["cpu_baseline"] = {"value": None, "unit": "GUPS", "cores": None, "kind": "unavailable",
+                                        "sample": repr(e)}
+        print(json.dumps(line), flush=True)
+
+    rec.close()
+    if dist is not None:
+        dist.barrier()
+        dist.destroy_process_group()
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work per reference sample")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    if args.impl == "reference":
+        run_reference(args, rank)
+        return
+    if world != args.gpus:
+        if world == 1 and args.gpus > 1:
+            sys.exit("bench.py --gpus N with N > 1 must be launched with torchrun (one rank per GPU)")
+    run_b200(args, rank, world, local_rank)
+
+
+if __name__ == "__main__":
+    main()

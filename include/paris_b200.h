@@ -135,6 +135,8 @@ int paris_b200_dev_free(paris_b200_ctx* ctx, void* d_ptr);
 /* make_volume_device: zero-initialised dim_x*dim_y*dim_z floats */
 int paris_b200_volume_alloc(paris_b200_ctx* ctx, uint32_t dim_x, uint32_t dim_y, uint32_t dim_z, float** d_vol);
 int paris_b200_volume_free(paris_b200_ctx* ctx, float* d_vol);
+/* zero a device volume again (asynchronous on the compute stream); pending batches targeting it are dropped */
+int paris_b200_volume_clear(paris_b200_ctx* ctx, float* d_vol, uint32_t dim_x, uint32_t dim_y, uint32_t dim_z);
 
 /* copy_h2d(projection): asynchronous when h_src is pinned; later work of the context waits for it.
  * The host buffer must stay valid until paris_b200_h2d_done() reports completion (or ctx_sync). */

@@ -80,6 +80,7 @@ SIGNATURES = {
     "paris_b200_dev_free": (C.c_int, [_vp, _vp]),
     "paris_b200_volume_alloc": (C.c_int, [_vp, _u32, _u32, _u32, _P(_vp)]),
     "paris_b200_volume_free": (C.c_int, [_vp, _fp]),
+    "paris_b200_volume_clear": (C.c_int, [_vp, _fp, _u32, _u32, _u32]),
     "paris_b200_proj_h2d": (C.c_int, [_vp, _fp, _fp, _u32, _u32]),
     "paris_b200_h2d_done": (C.c_int, [_vp, _P(C.c_int)]),
     "paris_b200_proj_d2h": (C.c_int, [_vp, _fp, _fp, _u32, _u32]),
@@ -182,17 +183,22 @@ class PinnedArray:
 class Context:
     """One per device; thin object wrapper over the paris_b200_ctx_* / stage entry points."""
 
-    def __init__(self, device: int = 0):
+    def __init__(self, device: int = 0, handle: int | None = None):
+        """handle: wrap an existing paris_b200_ctx* (not owned, e.g. the C++ layer's thread context)."""
         self._L = lib()
-        h = _vp()
-        check(self._L.paris_b200_ctx_create(device, C.byref(h)))
-        self.h = h
+        self._owned = handle is None
+        if handle is None:
+            h = _vp()
+            check(self._L.paris_b200_ctx_create(device, C.byref(h)))
+            self.h = h
+        else:
+            self.h = _vp(handle)
         self.device = device
 
     def close(self):
-        if self.h:
+        if self.h and self._owned:
             check(self._L.paris_b200_ctx_destroy(self.h))
-            self.h = None
+        self.h = None
 
     def __enter__(self):
         return self
@@ -251,6 +257,9 @@ class Context:
         p = _vp()
         check(self._L.paris_b200_volume_alloc(self.h, dim_x, dim_y, dim_z, C.byref(p)))
         return p.value
+
+    def volume_clear(self, d_vol: int, dim_x: int, dim_y: int, dim_z: int):
+        check(self._L.paris_b200_volume_clear(self.h, d_vol, dim_x, dim_y, dim_z))
 
     def volume_free(self, d_vol: int):
         check(self._L.paris_b200_volume_free(self.h, d_vol))

@@ -57,6 +57,21 @@ extern "C"
         }
     }
 
+    // paris::b200::set_device for the calling thread.
+    int paris_b200_dropin_set_device(int device)
+    {
+        try
+        {
+            auto dev = paris::b200::device_handle{device};
+            paris::b200::set_device(dev);
+            return 0;
+        }
+        catch(const std::exception&)
+        {
+            return -1;
+        }
+    }
+
     // The calling thread's context, so callers can time / count launches on the same streams.
     paris_b200_ctx* paris_b200_dropin_context(void)
     {

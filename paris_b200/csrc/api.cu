@@ -315,43 +315,41 @@ extern "C" int paris_b200_dev_alloc(paris_b200_ctx* ctx, size_t bytes, void** d_
     PB_CHECK_ARG(ctx != nullptr && d_ptr != nullptr && bytes > 0);
     PB_TRY(bind(ctx));
     *d_ptr = nullptr;
-    // 1st choice: a free buffer of this size whose last reader has already finished
-    pb::raw_buffer* oldest = nullptr;
+    // Free buffers are recycled in the order they were released (FIFO): the front of the queue is the
+    // buffer whose last reader finished -- or will finish -- first, so an upload into it can run as far
+    // ahead of the compute stream as the pool is deep.
     size_t same_size = 0;
-    for(auto& b : ctx->pool)
+    for(const auto& b : ctx->pool)
+        same_size += b.bytes == bytes ? 1u : 0u;
+    const size_t cap = 2u * static_cast<size_t>(ctx->bp_batch) + 2u;
+    for(auto it = ctx->free_fifo.begin(); it != ctx->free_fifo.end(); ++it)
     {
+        pb::raw_buffer& b = ctx->pool[*it];
         if(b.bytes != bytes)
             continue;
-        ++same_size;
-        if(b.in_use)
-            continue;
-        if(!b.freed_valid || cudaEventQuery(b.freed) == cudaSuccess)
+        bool ready = !b.freed_valid;
+        if(!ready)
         {
-            b.in_use = true;
-            b.freed_valid = false;
-            *d_ptr = b.ptr;
-            return PARIS_B200_OK;
+            ready = cudaEventQuery(b.freed) == cudaSuccess;
+            (void)cudaGetLastError(); // cudaErrorNotReady is not an error
         }
-        if(oldest == nullptr)
-            oldest = &b;
-    }
-    (void)cudaGetLastError(); // cudaEventQuery's cudaErrorNotReady is not an error
-    // 2nd: grow the pool while it is small, so uploads can run ahead of a backprojection batch
-    const size_t cap = 2u * static_cast<size_t>(ctx->bp_batch) + 2u;
-    if(oldest == nullptr || same_size < cap)
-    {
-        pb::raw_buffer b{};
-        PB_CUDA(cudaMalloc(&b.ptr, bytes));
-        PB_CUDA(cudaEventCreateWithFlags(&b.freed, cudaEventDisableTiming));
-        b.bytes = bytes;
+        if(!ready && same_size < cap)
+            break; // oldest candidate still busy and the pool may grow: allocate a fresh buffer instead
+        // either idle, or busy with the pool at its cap: proj_h2d makes the copy stream wait for `freed`
+        if(ready)
+            b.freed_valid = false;
         b.in_use = true;
-        ctx->pool.push_back(b);
         *d_ptr = b.ptr;
+        ctx->free_fifo.erase(it);
         return PARIS_B200_OK;
     }
-    // 3rd: reuse a buffer still being read; the copy stream waits for its `freed` event in proj_h2d
-    oldest->in_use = true;
-    *d_ptr = oldest->ptr;
+    pb::raw_buffer nb{};
+    PB_CUDA(cudaMalloc(&nb.ptr, bytes));
+    PB_CUDA(cudaEventCreateWithFlags(&nb.freed, cudaEventDisableTiming));
+    nb.bytes = bytes;
+    nb.in_use = true;
+    ctx->pool.push_back(nb);
+    *d_ptr = nb.ptr;
     return PARIS_B200_OK;
 }
 
@@ -370,6 +368,7 @@ extern "C" int paris_b200_dev_free(paris_b200_ctx* ctx, void* d_ptr)
     PB_CUDA(cudaEventRecord(b->freed, ctx->compute));
     b->freed_valid = true;
     b->in_use = false;
+    ctx->free_fifo.push_back(static_cast<size_t>(b - ctx->pool.data()));
     return PARIS_B200_OK;
 }
 
@@ -382,6 +381,17 @@ extern "C" int paris_b200_volume_alloc(paris_b200_ctx* ctx, uint32_t dim_x, uint
     *d_vol = nullptr;
     PB_CUDA(cudaMalloc(reinterpret_cast<void**>(d_vol), bytes));
     PB_CUDA(cudaMemsetAsync(*d_vol, 0, bytes, ctx->compute));
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_volume_clear(paris_b200_ctx* ctx, float* d_vol, uint32_t dim_x, uint32_t dim_y,
+                                       uint32_t dim_z)
+{
+    PB_CHECK_ARG(ctx != nullptr && d_vol != nullptr);
+    PB_TRY(bind(ctx));
+    if(ctx->pending > 0 && ctx->target.d_vol == d_vol)
+        ctx->pending = 0;
+    PB_CUDA(cudaMemsetAsync(d_vol, 0, static_cast<size_t>(dim_x) * dim_y * dim_z * sizeof(float), ctx->compute));
     return PARIS_B200_OK;
 }
 

@@ -7,6 +7,7 @@
 #include <cstdint>
 #include <cstdio>
 #include <cstring>
+#include <deque>
 #include <string>
 #include <vector>
 
@@ -77,6 +78,7 @@ struct paris_b200_ctx
 
     // pooled raw projection buffers (dev_alloc / dev_free)
     std::vector<pb::raw_buffer> pool;
+    std::deque<size_t> free_fifo;   // indices into pool, in release order
 
     // filtered stack owned by the context (deferred backprojection)
     float* stack = nullptr;

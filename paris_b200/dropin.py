@@ -25,10 +25,18 @@ def lib() -> C.CDLL:
             C.c_void_p, C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(capi.DetectorGeometry),
             C.POINTER(capi.VolumeGeometry), C.c_int, C.POINTER(capi.Roi), C.c_uint32, C.c_uint32, C.c_uint32,
             C.c_uint32, C.c_uint32, C.c_int, C.c_void_p, C.c_char_p, C.c_size_t]
+        L.paris_b200_dropin_set_device.restype = C.c_int
+        L.paris_b200_dropin_set_device.argtypes = [C.c_int]
         L.paris_b200_dropin_context.restype = C.c_void_p
         L.paris_b200_dropin_context.argtypes = []
         _lib = L
     return _lib
+
+
+def set_device(device: int) -> None:
+    """paris::b200::set_device for the calling thread (creates / rebinds its context)."""
+    if lib().paris_b200_dropin_set_device(device) != 0:
+        raise capi.Error(capi.ECUDA, capi.lib().paris_b200_last_error().decode())
 
 
 def context_handle() -> int:
