@@ -1,13 +1,18 @@
 // backproject_tma.cu -- K2, production kernel: TMA-staged, register-accumulating backprojection.
 //
 // Work decomposition (one CTA = one voxel tile, all projections of the batch):
-//   * tile = TX x TY voxel columns x TZ = 32*WZ slices.  A warp's 32 LANES RUN ALONG z for one column
-//     group: for a fixed column (x, y) and projection, the detector column position h, the bilinear
-//     x-weights and the magnification are the same for every z, and the detector row position is
-//     affine in z:  v(z) = v_base + z * dv.  All per-(column, projection) terms -- the reference's
-//     rotate / perspective-divide arithmetic of /root/reference/src/openmp/backprojection.cpp:120-133,
-//     including the one IEEE division -- are therefore computed ONCE per column and projection by one
-//     thread, put in a shared-memory table and read back as a warp-wide broadcast.
+//   * tile = TX x TY voxel columns x TZ = 32*NZ slices.  A warp's 32 LANES RUN ALONG z for one column
+//     group (lane l owns slices l, l+32, ...): for a fixed column (x, y) and projection, the detector
+//     column position h, the bilinear x-weights and the magnification are the same for every z, and the
+//     detector row position is affine in z:  v(z) = v_base + z * dv.  All per-(column, projection)
+//     terms -- the reference's rotate / perspective-divide arithmetic of
+//     /root/reference/src/openmp/backprojection.cpp:120-133, including the one IEEE division -- are
+//     therefore computed ONCE per column and projection by one thread, put in a shared-memory table and
+//     read back as a warp-wide broadcast, once for the NZ slices of a lane.
+//   * v(z) is evaluated in 9.23 unsigned fixed point relative to the staged box (one IMAD); its integer
+//     part is the shared-memory row, its fraction the bilinear y-weight (bit-assembled into a float, no
+//     conversion instructions).  Resolution 2^-23 detector rows -- finer than the reference's own float
+//     rounding of v at |v| ~ 1000 (ulp 6e-5).
 //   * the filtered stack is stored transposed (detector-row index v fastest), so the 32 lanes of an
 //     update read 32 nearly consecutive floats of one stack line; the tile's footprint on projection p,
 //     a BH x BV box, is fetched by ONE 3-D TMA load (cp.async.bulk.tensor) into a ring of shared-memory
@@ -30,27 +35,33 @@
 namespace pb
 {
     // ---- tile configuration ---------------------------------------------------------------------------
-    template <int TX_, int TY_, int WZ_, int CPW_, int BH_, int BV_, int STAGES_>
+    template <int TX_, int TY_, int NZ_, int CPW_, int BH_, int BV_, int STAGES_>
     struct tile_cfg
     {
-        static constexpr int TX = TX_, TY = TY_, WZ = WZ_, CPW = CPW_, BH = BH_, BV = BV_, STAGES = STAGES_;
-        static constexpr int TZ = 32 * WZ;
+        static constexpr int TX = TX_, TY = TY_, NZ = NZ_, CPW = CPW_, BH = BH_, BV = BV_, STAGES = STAGES_;
+        static constexpr int TZ = 32 * NZ;                // slices per tile; lane l owns l, l+32, ...
         static constexpr int COLS = TX * TY;
-        static constexpr int WC = COLS / CPW;             // warps across column groups
-        static constexpr int THREADS = 32 * WZ * WC;
+        static constexpr int WARPS = COLS / CPW;          // one warp per group of CPW columns
+        static constexpr int THREADS = 32 * WARPS;
         static constexpr int STAGE_BYTES = BH * BV * 4;
-        static constexpr int TAB_BYTES = COLS * (16 + 8);  // float4 + float2 per column
+        static constexpr int TAB_BYTES = COLS * (16 + 4);  // float4 + float per column
         static constexpr size_t SMEM = size_t(STAGES) * STAGE_BYTES + 2 * TAB_BYTES + kMaxBatch * 16 + STAGES * 8 + 128;
+        // fixed point: rows are carried with a bias of BV so that they stay non-negative on boundary tiles
+        static constexpr int FRAC = 23;
+        static constexpr int BIAS = BV;
         static_assert(COLS % CPW == 0, "columns per warp must divide the tile");
         static_assert(CPW % TX == 0 || TX % CPW == 0, "a warp's columns must be whole or partial x-runs");
         static_assert(BV % 4 == 0, "TMA inner box extent must be a multiple of 16 bytes");
         static_assert(BH <= 256 && BV <= 256, "TMA box extents are limited to 256");
+        static_assert(2 * BV + 32 < (1 << (32 - FRAC)), "biased rows must fit the 9 integer bits");
+        static_assert(STAGE_BYTES % 128 == 0, "stages must keep the 128-byte TMA destination alignment");
     };
 
     struct box_origin
     {
         int h0, v0;      // detector coordinates of the box's first element
-        int all_valid;   // every bilinear cell any voxel of the tile touches lies inside the detector and the box
+        int all_valid;   // 1: every bilinear cell the tile touches lies inside the detector and the box;
+                         // 2: the tile's shadow misses the detector altogether (nothing to add); 0: mixed
         int pad;
     };
 
@@ -142,37 +153,44 @@ namespace pb
     // ---- the kernel ------------------------------------------------------------------------------------------
 
     template <class CFG, bool CHECKED>
-    __device__ __forceinline__ void consume(float (&acc)[CFG::CPW], const float4* __restrict__ tab_a,
-                                            const float2* __restrict__ tab_b, int col0, float m_f,
-                                            int v_lo, uint32_t v_span)
+    __device__ __forceinline__ void consume(float (&acc)[CFG::NZ][CFG::CPW], const float4* __restrict__ tab_a,
+                                            const float* __restrict__ tab_b, int col0, uint32_t lane,
+                                            int row_shift, uint32_t row_span)
     {
         #pragma unroll
         for(int i = 0; i < CFG::CPW; ++i)
         {
-            const float4 ea = tab_a[col0 + i];   // {stage base + 4*BV*x1 (bits), v_base, dv, w*(1-fx)}
-            const float wb = tab_b[col0 + i].x;  // w*fx
-            const float v = fmaf(m_f, ea.y, ea.z) ;
-            const float fl = floorf(v);
-            const float fy = v - fl;
-            int iy = static_cast<int>(fl);
-            bool ok = true;
-            if(CHECKED)
+            // {stage address of (column x1, row -BIAS), v_base (9.23, biased), dv (9.23), w*(1-fx)} and w*fx
+            const float4 ea = tab_a[col0 + i];
+            const float wb = tab_b[col0 + i];
+            const uint32_t base = __float_as_uint(ea.x);
+            const uint32_t dv = __float_as_uint(ea.z);
+            uint32_t vfix = dv * lane + __float_as_uint(ea.y);
+            #pragma unroll
+            for(int j = 0; j < CFG::NZ; ++j)
             {
-                // all four neighbours inside the detector (rows iy+v0 and iy+v0+1), else the term is 0
-                ok = static_cast<uint32_t>(iy - v_lo) < v_span;
-                iy = min(max(iy, 0), CFG::BV - 2);
+                uint32_t row = vfix >> CFG::FRAC;                                 // biased row inside the box
+                const float fy = __uint_as_float((vfix & ((1u << CFG::FRAC) - 1u)) | 0x3f800000u) - 1.0f;
+                bool ok = true;
+                if(CHECKED)
+                {
+                    // all four neighbours inside the detector (rows r and r+1), else the term is 0
+                    ok = (row + static_cast<uint32_t>(row_shift)) < row_span;
+                    row = min(max(row, static_cast<uint32_t>(CFG::BIAS)), static_cast<uint32_t>(CFG::BIAS + CFG::BV - 2));
+                }
+                const uint32_t addr = base + 4u * row;
+                const float q11 = lds_f32(addr);
+                const float q12 = lds_f32(addr + 4);
+                const float q21 = lds_f32(addr + 4 * CFG::BV);
+                const float q22 = lds_f32(addr + 4 * CFG::BV + 4);
+                const float g0 = fmaf(wb, q21, ea.w * q11);
+                const float g1 = fmaf(wb, q22, ea.w * q12);
+                float d = fmaf(fy, g1 - g0, g0);
+                if(CHECKED)
+                    d = ok ? d : 0.f;
+                acc[j][i] += d;
+                vfix += dv << 5;   // next slice of this lane: 32 rows of dv further
             }
-            const uint32_t addr = __float_as_uint(ea.x) + 4u * static_cast<uint32_t>(iy);
-            const float q11 = lds_f32(addr);
-            const float q12 = lds_f32(addr + 4);
-            const float q21 = lds_f32(addr + 4 * CFG::BV);
-            const float q22 = lds_f32(addr + 4 * CFG::BV + 4);
-            const float g0 = fmaf(wb, q21, ea.w * q11);
-            const float g1 = fmaf(wb, q22, ea.w * q12);
-            float d = fmaf(fy, g1 - g0, g0);
-            if(CHECKED)
-                d = ok ? d : 0.f;
-            acc[i] += d;
         }
     }
 
@@ -184,15 +202,13 @@ namespace pb
         extern __shared__ __align__(128) unsigned char smem[];
         unsigned char* stage_mem = smem;                                                   // STAGES x BH x BV floats
         float4* tab_a = reinterpret_cast<float4*>(smem + size_t(CFG::STAGES) * CFG::STAGE_BYTES);
-        float2* tab_b = reinterpret_cast<float2*>(reinterpret_cast<unsigned char*>(tab_a) + 2 * CFG::COLS * 16);
-        box_origin* origin = reinterpret_cast<box_origin*>(reinterpret_cast<unsigned char*>(tab_b) + 2 * CFG::COLS * 8);
+        float* tab_b = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tab_a) + 2 * CFG::COLS * 16);
+        box_origin* origin = reinterpret_cast<box_origin*>(reinterpret_cast<unsigned char*>(tab_b) + 2 * CFG::COLS * 4);
         uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(origin) + kMaxBatch * 16);
 
         const int tid = threadIdx.x;
-        const int lane = tid & 31;
-        const int warp = tid >> 5;
-        const int wz = warp % CFG::WZ;      // which 32-slice group
-        const int wc = warp / CFG::WZ;      // which column group
+        const uint32_t lane = tid & 31;
+        const int warp = tid >> 5;          // which group of CPW columns
         const int count = ang.count;
 
         // Tiles are anchored at multiples of the tile size in GLOBAL voxel indices (ROI and slab offsets
@@ -236,6 +252,7 @@ namespace pb
                 vmin = fmin(vmin, fmin(va, vb));
                 vmax = fmax(vmax, fmax(va, vb));
             }
+            const bool finite = hmin == hmin && hmax == hmax && vmin == vmin && vmax == vmax;
             // clamp so the integer conversions are safe for columns far off the detector
             const float lim_h = static_cast<float>(g.p_dim_x) + 8.f, lim_v = static_cast<float>(g.p_dim_y) + 8.f;
             const float hlo_f = fminf(fmaxf(floorf(hmin), -8.f), lim_h), hhi_f = fminf(fmaxf(floorf(hmax), -8.f), lim_h);
@@ -251,9 +268,12 @@ namespace pb
             // cells used: columns hlo-1 .. hhi+2, rows vlo-1 .. vhi+2 (one cell of slack for float rounding)
             const bool fits = (hhi + 2 - o.h0) < CFG::BH && (vhi + 2 - o.v0) < CFG::BV;
             const bool inside = hlo - 1 >= 0 && hhi + 2 <= static_cast<int>(g.p_dim_x) - 1
-                             && vlo - 1 >= 0 && vhi + 2 <= static_cast<int>(g.p_dim_y) - 1
-                             && hmin == hmin && hmax == hmax && vmin == vmin && vmax == vmax;
-            o.all_valid = (fits && inside && full_tile) ? 1 : 0;
+                             && vlo - 1 >= 0 && vhi + 2 <= static_cast<int>(g.p_dim_y) - 1;
+            // no voxel of the tile has all four neighbours on the detector: x1 = floor(h) < 0 or x1+1 >= dim_x
+            // for every column, or the same for the rows (two cells of slack on the safe side)
+            const bool outside = hmax < -2.f || hmin > static_cast<float>(g.p_dim_x) + 1.f
+                              || vmax < -2.0 || vmin > static_cast<double>(g.p_dim_y) + 1.0;
+            o.all_valid = !finite ? 0 : outside ? 2 : (fits && inside && full_tile) ? 1 : 0;
             o.pad = 0;
             origin[tid] = o;
         }
@@ -272,19 +292,23 @@ namespace pb
             }
         }
 
-        // this thread's voxels: columns col0 .. col0+CPW-1 of the tile at slice z
-        const int col0 = wc * CFG::CPW;
+        // this thread's voxels: columns col0 .. col0+CPW-1 of the tile at slices lane, lane+32, ...
         // (local indices wrap to huge values for voxels before the region's origin and fail the range test)
-        const uint32_t z = z0 + wz * 32 + lane - g.off_z;
-        const bool z_ok = z < g.v_dim_z;
+        const int col0 = warp * CFG::CPW;
+        const uint32_t zl = z0 + lane - g.off_z;
         const size_t slice = static_cast<size_t>(g.v_dim_x) * g.v_dim_y;
-        float acc[CFG::CPW];
+        float acc[CFG::NZ][CFG::CPW];
         #pragma unroll
-        for(int i = 0; i < CFG::CPW; ++i)
+        for(int j = 0; j < CFG::NZ; ++j)
         {
-            const uint32_t x = x0 + (col0 + i) % CFG::TX - g.off_x, y = y0 + (col0 + i) / CFG::TX - g.off_y;
-            const bool ok = z_ok && x < g.v_dim_x && y < g.v_dim_y;
-            acc[i] = ok ? vol[static_cast<size_t>(z) * slice + static_cast<size_t>(y) * g.v_dim_x + x] : 0.f;
+            #pragma unroll
+            for(int i = 0; i < CFG::CPW; ++i)
+            {
+                const uint32_t x = x0 + (col0 + i) % CFG::TX - g.off_x, y = y0 + (col0 + i) / CFG::TX - g.off_y;
+                const uint32_t z = zl + 32u * j;
+                const bool ok = z < g.v_dim_z && x < g.v_dim_x && y < g.v_dim_y;
+                acc[j][i] = ok ? vol[static_cast<size_t>(z) * slice + static_cast<size_t>(y) * g.v_dim_x + x] : 0.f;
+            }
         }
 
         // table builder state: thread c < COLS owns tile column c
@@ -298,30 +322,43 @@ namespace pb
             z_m0 = centered_d(z0, g.full_z, g.l_vx_z);
         }
         const uint32_t stage_base0 = smem_u32(stage_mem);
+        constexpr double kOne = static_cast<double>(1u << CFG::FRAC);
 
         auto build = [&](int p) {
             const box_origin o = origin[p];
+            if(o.all_valid == 2)
+                return; // the projection is skipped for this tile
             const column_terms ct = project_column(bx_k, by_l, ang.sn[p], ang.cs[p], g);
             const float x1 = floorf(ct.h);
             const bool valid_x = x1 >= 0.f && x1 + 1.f < static_cast<float>(g.p_dim_x);
-            float4 ea = make_float4(0.f, 0.f, 0.f, 0.f);
-            float2 eb = make_float2(0.f, 0.f);
+            // a dead entry reads row 0 of column 0 of the box with zero weights
+            float4 ea = make_float4(0.f, __uint_as_float(static_cast<uint32_t>(CFG::BIAS) << CFG::FRAC),
+                                    __uint_as_float(0u), 0.f);
+            float eb = 0.f;
             int x1rel = 0;
             if(valid_x)
             {
-                const float fx = ct.h - x1;
-                const float w = 0.5f * ct.u * ct.u;
-                x1rel = min(max(static_cast<int>(x1) - o.h0, 0), CFG::BH - 2);
                 const double fd = static_cast<double>(ct.factor);
                 const double dv = static_cast<double>(g.l_vx_z) * fd / static_cast<double>(g.l_px_y);
-                const double vb = row_of(z_m0, fd, g) - static_cast<double>(o.v0);
-                ea.y = static_cast<float>(dv);
-                ea.z = static_cast<float>(vb);
-                ea.w = w * (1.f - fx);
-                eb.x = w * fx;
+                // biased, box-relative row of the tile's first slice
+                const double vb = row_of(z_m0, fd, g) - static_cast<double>(o.v0) + static_cast<double>(CFG::BIAS);
+                const double vend = vb + dv * static_cast<double>(CFG::TZ - 1);
+                // representable in 9.23 unsigned for every slice of the tile?  (always true when the host-side
+                // footprint check holds; columns of a far-off tile that fail it cannot touch the detector)
+                if(dv >= 0.0 && vb >= 0.0 && vend < static_cast<double>(2 * CFG::BV + 16))
+                {
+                    const float fx = ct.h - x1;
+                    const float w = 0.5f * ct.u * ct.u;
+                    x1rel = min(max(static_cast<int>(x1) - o.h0, 0), CFG::BH - 2);
+                    ea.y = __uint_as_float(static_cast<uint32_t>(__double2ll_rn(vb * kOne)));
+                    ea.z = __uint_as_float(static_cast<uint32_t>(__double2ll_rn(dv * kOne)));
+                    ea.w = w * (1.f - fx);
+                    eb = w * fx;
+                }
             }
+            // address of (column x1, row -BIAS): the biased row index is added as is
             const uint32_t base = stage_base0 + static_cast<uint32_t>(p % CFG::STAGES) * CFG::STAGE_BYTES
-                                + 4u * static_cast<uint32_t>(x1rel * CFG::BV);
+                                + 4u * static_cast<uint32_t>(x1rel * CFG::BV) - 4u * static_cast<uint32_t>(CFG::BIAS);
             ea.x = __uint_as_float(base);
             tab_a[(p & 1) * CFG::COLS + tid] = ea;
             tab_b[(p & 1) * CFG::COLS + tid] = eb;
@@ -332,7 +369,6 @@ namespace pb
         __syncthreads();
 
         // ---- main loop over the projections of the batch -----------------------------------------------------------
-        const float m_f = static_cast<float>(wz * 32 + lane);
         #pragma unroll 1
         for(int p = 0; p < count; ++p)
         {
@@ -344,11 +380,12 @@ namespace pb
 
             const box_origin o = origin[p];
             const float4* ta = tab_a + (p & 1) * CFG::COLS;
-            const float2* tb = tab_b + (p & 1) * CFG::COLS;
-            if(o.all_valid)
-                consume<CFG, false>(acc, ta, tb, col0, m_f, 0, 0u);
-            else
-                consume<CFG, true>(acc, ta, tb, col0, m_f, -o.v0, static_cast<uint32_t>(g.p_dim_y - 1u));
+            const float* tb = tab_b + (p & 1) * CFG::COLS;
+            if(o.all_valid == 1)
+                consume<CFG, false>(acc, ta, tb, col0, lane, 0, 0u);
+            else if(o.all_valid == 0)
+                // detector row of biased box row r is r - BIAS + v0; valid iff 0 <= row < dim_y - 1
+                consume<CFG, true>(acc, ta, tb, col0, lane, o.v0 - CFG::BIAS, static_cast<uint32_t>(g.p_dim_y - 1u));
 
             __syncthreads(); // stage and table[p&1] are free again; table[(p+1)&1] is complete
             if(tid == 0 && p + CFG::STAGES < count)
@@ -363,11 +400,16 @@ namespace pb
 
         // ---- epilogue: one store per voxel ---------------------------------------------------------------------------
         #pragma unroll
-        for(int i = 0; i < CFG::CPW; ++i)
+        for(int j = 0; j < CFG::NZ; ++j)
         {
-            const uint32_t x = x0 + (col0 + i) % CFG::TX - g.off_x, y = y0 + (col0 + i) / CFG::TX - g.off_y;
-            if(z_ok && x < g.v_dim_x && y < g.v_dim_y)
-                vol[static_cast<size_t>(z) * slice + static_cast<size_t>(y) * g.v_dim_x + x] = acc[i];
+            #pragma unroll
+            for(int i = 0; i < CFG::CPW; ++i)
+            {
+                const uint32_t x = x0 + (col0 + i) % CFG::TX - g.off_x, y = y0 + (col0 + i) / CFG::TX - g.off_y;
+                const uint32_t z = zl + 32u * j;
+                if(z < g.v_dim_z && x < g.v_dim_x && y < g.v_dim_y)
+                    vol[static_cast<size_t>(z) * slice + static_cast<size_t>(y) * g.v_dim_x + x] = acc[j][i];
+            }
         }
     }
 
@@ -484,9 +526,9 @@ namespace pb
         return PARIS_B200_OK;
     }
 
-    //                      TX  TY  WZ CPW  BH   BV  STAGES
-    using cfg_fine   = tile_cfg<16, 16, 2, 32, 40, 96, 6>;    // ~1 detector pixel per voxel (PARIS-derived volumes)
-    using cfg_coarse = tile_cfg<16, 16, 2, 32, 64, 164, 4>;   // ~2 detector pixels per voxel (K^3 from a (2K)^2 detector)
+    //                      TX  TY  NZ CPW  BH   BV  STAGES
+    using cfg_fine   = tile_cfg<16, 16, 2, 16, 40, 96, 6>;    // ~1 detector pixel per voxel (PARIS-derived volumes)
+    using cfg_coarse = tile_cfg<16, 16, 2, 16, 64, 164, 4>;   // ~2 detector pixels per voxel (K^3 from a (2K)^2 detector)
 
     int launch_bp_tma(paris_b200_ctx* ctx, const float* d_stack, size_t slot_floats, uint32_t first,
                       const bp_geometry& g, const bp_angles& a, float* d_vol, bool required, bool* handled)
