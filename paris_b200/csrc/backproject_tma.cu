@@ -98,6 +98,14 @@ namespace pb
             ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2) : "memory");
     }
 
+    // (a & b) | c in one LOP3
+    __device__ __forceinline__ uint32_t and_or(uint32_t a, uint32_t b, uint32_t c)
+    {
+        uint32_t d;
+        asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
+        return d;
+    }
+
     __device__ __forceinline__ float lds_f32(uint32_t addr)
     {
         float v;
@@ -157,6 +165,9 @@ namespace pb
                                             const float* __restrict__ tab_b, int col0, uint32_t lane,
                                             int row_shift, uint32_t row_span)
     {
+        // kept in registers so the fraction -> float assembly is a single three-input LOP3
+        uint32_t frac_mask = (1u << CFG::FRAC) - 1u, one_bits = 0x3f800000u;
+        asm volatile("" : "+r"(frac_mask), "+r"(one_bits));
         #pragma unroll
         for(int i = 0; i < CFG::CPW; ++i)
         {
@@ -170,7 +181,7 @@ namespace pb
             for(int j = 0; j < CFG::NZ; ++j)
             {
                 uint32_t row = vfix >> CFG::FRAC;                                 // biased row inside the box
-                const float fy = __uint_as_float((vfix & ((1u << CFG::FRAC) - 1u)) | 0x3f800000u) - 1.0f;
+                const float fy = __uint_as_float(and_or(vfix, frac_mask, one_bits)) - 1.0f;
                 bool ok = true;
                 if(CHECKED)
                 {
@@ -279,7 +290,33 @@ namespace pb
         }
         __syncthreads();
 
-        // ---- prologue 2: start the TMA pipeline, seed the accumulators, build the first table -------------------
+        // ---- prologue 2: seed the accumulators, start the TMA pipeline, build the first table -------------------
+        // The tile of the volume travels through shared memory (the still unused stage buffers) so that global
+        // memory sees runs of TX consecutive voxels; a lane's own voxels are 32 slices apart.
+        // (local indices wrap to huge values for voxels before the region's origin and fail the range test)
+        const int col0 = warp * CFG::CPW;
+        const size_t slice = static_cast<size_t>(g.v_dim_x) * g.v_dim_y;
+        float* scratch = reinterpret_cast<float*>(stage_mem);          // [TZ][COLS + 1]
+        constexpr int kPitch = CFG::COLS + 1;
+        static_assert(size_t(CFG::TZ) * kPitch * 4 <= size_t(CFG::STAGES) * CFG::STAGE_BYTES, "scratch must fit the stages");
+        for(int e = tid; e < CFG::TZ * CFG::COLS; e += CFG::THREADS)
+        {
+            const int c = e % CFG::COLS, zl = e / CFG::COLS;
+            const uint32_t x = x0 + c % CFG::TX - g.off_x, y = y0 + c / CFG::TX - g.off_y, z = z0 + zl - g.off_z;
+            const bool ok = z < g.v_dim_z && x < g.v_dim_x && y < g.v_dim_y;
+            scratch[zl * kPitch + c] = ok ? vol[static_cast<size_t>(z) * slice + static_cast<size_t>(y) * g.v_dim_x + x] : 0.f;
+        }
+        __syncthreads();
+        float acc[CFG::NZ][CFG::CPW];
+        #pragma unroll
+        for(int j = 0; j < CFG::NZ; ++j)
+        {
+            #pragma unroll
+            for(int i = 0; i < CFG::CPW; ++i)
+                acc[j][i] = scratch[(lane + 32u * j) * kPitch + col0 + i];
+        }
+        __syncthreads(); // scratch is dead: the stages may be filled
+
         if(tid == 0)
         {
             const int pre = count < CFG::STAGES ? count : CFG::STAGES;
@@ -289,25 +326,6 @@ namespace pb
                 mbar_expect_tx(bar, CFG::STAGE_BYTES);
                 tma_load_3d(smem_u32(stage_mem + size_t(p) * CFG::STAGE_BYTES), &tmap, bar, origin[p].v0, origin[p].h0,
                             static_cast<int>(first_slot) + p);
-            }
-        }
-
-        // this thread's voxels: columns col0 .. col0+CPW-1 of the tile at slices lane, lane+32, ...
-        // (local indices wrap to huge values for voxels before the region's origin and fail the range test)
-        const int col0 = warp * CFG::CPW;
-        const uint32_t zl = z0 + lane - g.off_z;
-        const size_t slice = static_cast<size_t>(g.v_dim_x) * g.v_dim_y;
-        float acc[CFG::NZ][CFG::CPW];
-        #pragma unroll
-        for(int j = 0; j < CFG::NZ; ++j)
-        {
-            #pragma unroll
-            for(int i = 0; i < CFG::CPW; ++i)
-            {
-                const uint32_t x = x0 + (col0 + i) % CFG::TX - g.off_x, y = y0 + (col0 + i) / CFG::TX - g.off_y;
-                const uint32_t z = zl + 32u * j;
-                const bool ok = z < g.v_dim_z && x < g.v_dim_x && y < g.v_dim_y;
-                acc[j][i] = ok ? vol[static_cast<size_t>(z) * slice + static_cast<size_t>(y) * g.v_dim_x + x] : 0.f;
             }
         }
 
@@ -398,18 +416,22 @@ namespace pb
             }
         }
 
-        // ---- epilogue: one store per voxel ---------------------------------------------------------------------------
+        // ---- epilogue: back through shared memory, one coalesced store per voxel -------------------------------------
+        // (the loop's last __syncthreads guarantees nobody reads the stages any more and no TMA load is in flight)
         #pragma unroll
         for(int j = 0; j < CFG::NZ; ++j)
         {
             #pragma unroll
             for(int i = 0; i < CFG::CPW; ++i)
-            {
-                const uint32_t x = x0 + (col0 + i) % CFG::TX - g.off_x, y = y0 + (col0 + i) / CFG::TX - g.off_y;
-                const uint32_t z = zl + 32u * j;
-                if(z < g.v_dim_z && x < g.v_dim_x && y < g.v_dim_y)
-                    vol[static_cast<size_t>(z) * slice + static_cast<size_t>(y) * g.v_dim_x + x] = acc[j][i];
-            }
+                scratch[(lane + 32u * j) * kPitch + col0 + i] = acc[j][i];
+        }
+        __syncthreads();
+        for(int e = tid; e < CFG::TZ * CFG::COLS; e += CFG::THREADS)
+        {
+            const int c = e % CFG::COLS, zl = e / CFG::COLS;
+            const uint32_t x = x0 + c % CFG::TX - g.off_x, y = y0 + c / CFG::TX - g.off_y, z = z0 + zl - g.off_z;
+            if(z < g.v_dim_z && x < g.v_dim_x && y < g.v_dim_y)
+                vol[static_cast<size_t>(z) * slice + static_cast<size_t>(y) * g.v_dim_x + x] = scratch[zl * kPitch + c];
         }
     }
 
