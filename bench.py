@@ -61,60 +61,64 @@ def ellipsoids(det):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons DURING the timed region (B200_PROFILING.md recipe)."""
+    """SM clock / throttle reasons DURING the timed region (B200_PROFILING.md recipe), read through NVML
+    from a background thread.  (An `nvidia-smi -lms 100` child process was measured to stall this process's
+    CUDA calls for hundreds of milliseconds per step; three light NVML queries do not.)"""
 
-    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
-              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
-              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+    # NB: NVML queries contend with CUDA submissions inside the driver.  Sampling every 100 ms is harmless for
+    # the device-resident steps (a few dozen launches per step) but was measured to stretch the end-to-end
+    # steps (thousands of API calls each) from 139 ms to as much as 1 s -- so that phase is sampled at 500 ms.
+    REASONS = {"hw_slowdown": 0x8, "hw_thermal_slowdown": 0x40, "sw_thermal_slowdown": 0x20, "sw_power_cap": 0x4}
 
-    def __init__(self, device: int):
-        self.device = device
-        self.proc = None
-        self.path = None
+    def __init__(self, device: int, interval_ms: int = 100):
+        self.device, self.interval = device, interval_ms / 1e3
+        self.samples, self.power, self.reasons = [], [], set()
+        self.max_mhz = None
+        self._stop = threading.Event()
+        self._thread = None
+
+    def _run(self):
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            index = self.device
+            if visible:
+                try:
+                    index = int(visible.split(",")[self.device])
+                except (ValueError, IndexError):
+                    pass
+            h = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
+            while not self._stop.is_set():
+                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+                self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1e3)
+                mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+                for name, bit in self.REASONS.items():
+                    if mask & bit:
+                        self.reasons.add(name)
+                self._stop.wait(self.interval)
+            pynvml.nvmlShutdown()
+        except Exception as e:  # no NVML: report that instead of clocks
+            self.error = repr(e)
 
     def start(self):
-        try:
-            f = tempfile.NamedTemporaryFile(prefix="clocks_", suffix=".csv", delete=False)
-            self.path = f.name
-            self.proc = subprocess.Popen(["nvidia-smi", f"--id={self.device}", f"--query-gpu={self.FIELDS}",
-                                          "--format=csv,noheader,nounits", "-lms", "100"], stdout=f,
-                                         stderr=subprocess.DEVNULL)
-        except OSError:
-            self.proc = None
+        self._thread = threading.Thread(target=self._run, daemon=True)
+        self._thread.start()
 
     def stop(self) -> dict:
-        out = {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
-        if self.proc is None:
+        out = {"sm_mhz": None, "sm_max_mhz": self.max_mhz, "reasons": [], "samples": 0}
+        if self._thread is None:
             return out
-        self.proc.terminate()
-        try:
-            self.proc.wait(timeout=5)
-        except subprocess.TimeoutExpired:
-            self.proc.kill()
-        sm, mx, power, reasons = [], [], [], set()
-        try:
-            for line in open(self.path):
-                p = [x.strip() for x in line.split(",")]
-                if len(p) < 9:
-                    continue
-                try:
-                    sm.append(float(p[1]))
-                    mx.append(float(p[2]))
-                    power.append(float(p[3]))
-                except ValueError:
-                    continue
-                for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"),
-                                   p[5:9]):
-                    if v.lower().startswith("active"):
-                        reasons.add(name)
-            os.unlink(self.path)
-        except OSError:
-            pass
-        if sm:
+        self._stop.set()
+        self._thread.join(timeout=5)
+        if self.samples:
             # "under load": the upper half of the samples (the sampler also sees the gaps between steps)
-            busy = sorted(sm)[len(sm) // 2:]
-            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=float(max(mx)), reasons=sorted(reasons),
-                       samples=len(sm), power_w_max=float(max(power)))
+            busy = sorted(self.samples)[len(self.samples) // 2:]
+            out.update(sm_mhz=float(np.median(busy)), sm_max_mhz=self.max_mhz, reasons=sorted(self.reasons),
+                       samples=len(self.samples), power_w_max=float(max(self.power)))
+        if hasattr(self, "error"):
+            out["error"] = self.error
         return out
 
 
@@ -228,7 +232,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     # synthetic raw stack: this rank's share of the projections, generated on the device, mirrored on the host
     rec.generate_inputs(ellipsoids(det))
 
-    sampler = ClockSampler(local_rank)
+    sampler = ClockSampler(local_rank, args.clock_interval_ms)
     barrier = (lambda: dist.barrier()) if dist is not None else (lambda: None)
 
     # ---- device-resident steps -------------------------------------------------------------------------------
@@ -252,11 +256,14 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     barrier()
     wall_resident = time.perf_counter() - t0
     launches = ctx.launch_count() - launches0
+    clocks = sampler.stop()
 
     # ---- end-to-end steps (host -> host through the reference-shaped loop) ---------------------------------------
     for _ in range(max(1, args.warmup // 2)):
         rec.step_e2e()
     barrier()
+    sampler_e2e = ClockSampler(local_rank, 500)
+    sampler_e2e.start()
     e2e_ms = []
     for _ in range(args.steps):
         barrier()
@@ -264,7 +271,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         rec.step_e2e()
         ctx.sync()
         e2e_ms.append((time.perf_counter() - t1) * 1e3)
-    clocks = sampler.stop()
+    clocks_e2e = sampler_e2e.stop()
+    clocks["reasons"] = sorted(set(clocks["reasons"]) | set(clocks_e2e["reasons"]))
+    clocks["e2e_phase"] = {k: clocks_e2e.get(k) for k in ("sm_mhz", "samples", "power_w_max")}
 
     ms_step = ms_total / args.steps
     e2e_step = float(np.mean(e2e_ms))
@@ -304,6 +313,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                                 "note": f"8 B per detector pixel; peak {peak_src} (MEASURED_PEAKS.json hbm_gbs)"},
             "e2e": {"value": updates / (e2e_step / 1e3) / 1e9, "unit": "GUPS", "seconds": e2e_step / 1e3,
                     "h2d_bytes_per_step": 4 * px * n_proj, "d2h_bytes_per_step": 4 * voxels,
+                    "ms_steps": [round(x, 2) for x in e2e_ms],
                     "path": "paris_b200_dropin_reconstruct: per-projection load/weight/filter/backproject + copy_d2h"},
             "gpu_launches": int(launches), "clocks": clocks,
             "wall_s_resident": wall_resident,
@@ -334,6 +344,7 @@ def main():
     ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work per reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--clock-interval-ms", type=int, default=100, help="NVML sampling period")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

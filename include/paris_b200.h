@@ -95,6 +95,10 @@ int paris_b200_ctx_stream(paris_b200_ctx* ctx, void** stream);
 /* counters since ctx_create: kernels launched by this library on this context */
 int paris_b200_ctx_launch_count(const paris_b200_ctx* ctx, uint64_t* launches);
 
+/* diagnostics: stats[0..5] = kernel launches, pool cudaMallocs, pool reuses of an idle buffer, pool reuses of a
+ * buffer still being read (the upload waits), backprojection flushes, pool size; n >= 6 */
+int paris_b200_ctx_stats(const paris_b200_ctx* ctx, uint64_t* stats, int n);
+
 /* CUDA-event timing on the context's compute stream (bench / profiling plumbing) */
 typedef struct paris_b200_event paris_b200_event;
 int paris_b200_event_create(paris_b200_ctx* ctx, paris_b200_event** ev);
@@ -103,7 +107,7 @@ int paris_b200_event_record(paris_b200_ctx* ctx, paris_b200_event* ev);
 int paris_b200_event_elapsed_ms(paris_b200_event* start, paris_b200_event* stop, float* ms);
 int paris_b200_event_destroy(paris_b200_event* ev);
 
-/* Tunables.  "bp_batch": projections accumulated per backprojection launch (default 32);
+/* Tunables.  "bp_batch": projections accumulated per backprojection launch (default 64, max 64);
  * "bp_kernel": 0 = auto, 1 = generic L1-gather kernel, 2 = TMA-staged kernel. */
 int paris_b200_ctx_set_option(paris_b200_ctx* ctx, const char* name, int64_t value);
 
@@ -213,6 +217,11 @@ int paris_b200_stack_slot_bytes(uint32_t n_row, uint32_t n_col, size_t* bytes, u
 /* weight + filter a RAW device projection into slot `slot` of an external stack buffer */
 int paris_b200_filter_to_stack(paris_b200_ctx* ctx, const float* d_raw, const paris_b200_detector_geometry* det,
                                const paris_b200_filter* filter, float* d_stack, uint32_t slot);
+/* the same for `count` raw projections laid out raw_stride floats apart, into slots first_slot.. ; one
+ * launch per 64 projections */
+int paris_b200_filter_to_stack_batch(paris_b200_ctx* ctx, const float* d_raw, size_t raw_stride, uint32_t count,
+                                     const paris_b200_detector_geometry* det, const paris_b200_filter* filter,
+                                     float* d_stack, uint32_t first_slot);
 /* backproject slots [first, first+count) of an external stack into d_vol; sin_phi/cos_phi are host
  * arrays of `count` entries (slot first+i uses entry i). */
 int paris_b200_backproject_stack(paris_b200_ctx* ctx, const float* d_stack, uint32_t first, uint32_t count,

@@ -64,6 +64,7 @@ SIGNATURES = {
     "paris_b200_ctx_sync": (C.c_int, [_vp]),
     "paris_b200_ctx_stream": (C.c_int, [_vp, _P(_vp)]),
     "paris_b200_ctx_launch_count": (C.c_int, [_vp, _P(C.c_uint64)]),
+    "paris_b200_ctx_stats": (C.c_int, [_vp, _P(C.c_uint64), C.c_int]),
     "paris_b200_event_create": (C.c_int, [_vp, _P(_vp)]),
     "paris_b200_event_record": (C.c_int, [_vp, _vp]),
     "paris_b200_event_elapsed_ms": (C.c_int, [_vp, _vp, _P(_f)]),
@@ -98,6 +99,7 @@ SIGNATURES = {
     "paris_b200_flush": (C.c_int, [_vp]),
     "paris_b200_stack_slot_bytes": (C.c_int, [_u32, _u32, _P(C.c_size_t), _P(_u32)]),
     "paris_b200_filter_to_stack": (C.c_int, [_vp, _fp, _P(DetectorGeometry), _vp, _fp, _u32]),
+    "paris_b200_filter_to_stack_batch": (C.c_int, [_vp, _fp, C.c_size_t, _u32, _P(DetectorGeometry), _vp, _fp, _u32]),
     "paris_b200_backproject_stack": (C.c_int, [_vp, _fp, _u32, _u32, _P(_f), _P(_f), _fp, _u32, _u32, _u32, _u32,
                                                _P(DetectorGeometry), _P(VolumeGeometry), C.c_int, _P(Roi)]),
     "paris_b200_phantom_project": (C.c_int, [_vp, _P(C.c_double), _u32, _P(DetectorGeometry), _u32, _u32, _fp]),
@@ -220,6 +222,11 @@ class Context:
         check(self._L.paris_b200_ctx_launch_count(self.h, C.byref(n)))
         return n.value
 
+    def stats(self) -> dict:
+        a = (C.c_uint64 * 6)()
+        check(self._L.paris_b200_ctx_stats(self.h, a, 6))
+        return dict(zip(("launches", "pool_malloc", "pool_ready", "pool_busy", "flushes", "pool_size"), list(a)))
+
     def event(self) -> int:
         """Create a CUDA event and record it on the compute stream."""
         e = _vp()
@@ -319,6 +326,11 @@ class Context:
 
     def filter_to_stack(self, d_raw: int, det: DetectorGeometry, filt: int, d_stack: int, slot: int):
         check(self._L.paris_b200_filter_to_stack(self.h, d_raw, C.byref(det), filt, d_stack, slot))
+
+    def filter_to_stack_batch(self, d_raw: int, raw_stride: int, count: int, det: DetectorGeometry, filt: int,
+                              d_stack: int, first_slot: int):
+        check(self._L.paris_b200_filter_to_stack_batch(self.h, d_raw, raw_stride, count, C.byref(det), filt, d_stack,
+                                                       first_slot))
 
     def backproject_stack(self, d_stack: int, first: int, count: int, sin_phi: np.ndarray, cos_phi: np.ndarray,
                           d_vol: int, v_dims, v_offset: int, det: DetectorGeometry, vol_full: VolumeGeometry,

@@ -27,6 +27,8 @@ namespace pb
 
 using namespace pb;
 
+static int flush_if_held(paris_b200_ctx* ctx, const void* d_ptr);
+
 extern "C" const char* paris_b200_last_error(void) { return pb::g_error; }
 extern "C" const char* paris_b200_version(void) { return "paris_b200 0.1 (sm_100a)"; }
 
@@ -121,6 +123,18 @@ extern "C" int paris_b200_ctx_launch_count(const paris_b200_ctx* ctx, uint64_t* 
 {
     PB_CHECK_ARG(ctx != nullptr && launches != nullptr);
     *launches = ctx->launches;
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_ctx_stats(const paris_b200_ctx* ctx, uint64_t* stats, int n)
+{
+    PB_CHECK_ARG(ctx != nullptr && stats != nullptr && n >= 6);
+    stats[0] = ctx->launches;
+    stats[1] = ctx->stat_pool_malloc;
+    stats[2] = ctx->stat_pool_ready;
+    stats[3] = ctx->stat_pool_busy;
+    stats[4] = ctx->stat_flush;
+    stats[5] = ctx->pool.size();
     return PARIS_B200_OK;
 }
 
@@ -337,13 +351,19 @@ extern "C" int paris_b200_dev_alloc(paris_b200_ctx* ctx, size_t bytes, void** d_
             break; // oldest candidate still busy and the pool may grow: allocate a fresh buffer instead
         // either idle, or busy with the pool at its cap: proj_h2d makes the copy stream wait for `freed`
         if(ready)
+        {
             b.freed_valid = false;
+            ++ctx->stat_pool_ready;
+        }
+        else
+            ++ctx->stat_pool_busy;
         b.in_use = true;
         *d_ptr = b.ptr;
         ctx->free_fifo.erase(it);
         return PARIS_B200_OK;
     }
     pb::raw_buffer nb{};
+    ++ctx->stat_pool_malloc;
     PB_CUDA(cudaMalloc(&nb.ptr, bytes));
     PB_CUDA(cudaEventCreateWithFlags(&nb.freed, cudaEventDisableTiming));
     nb.bytes = bytes;
@@ -364,6 +384,11 @@ extern "C" int paris_b200_dev_free(paris_b200_ctx* ctx, void* d_ptr)
     {
         set_error("dev_free: %p was not allocated by this context", d_ptr);
         return PARIS_B200_EINVAL;
+    }
+    if(b->held)
+    {
+        b->free_pending = true; // released for real once the deferred filter launch that reads it is enqueued
+        return PARIS_B200_OK;
     }
     PB_CUDA(cudaEventRecord(b->freed, ctx->compute));
     b->freed_valid = true;
@@ -390,7 +415,7 @@ extern "C" int paris_b200_volume_clear(paris_b200_ctx* ctx, float* d_vol, uint32
     PB_CHECK_ARG(ctx != nullptr && d_vol != nullptr);
     PB_TRY(bind(ctx));
     if(ctx->pending > 0 && ctx->target.d_vol == d_vol)
-        ctx->pending = 0;
+        PB_TRY(paris_b200_flush(ctx));
     PB_CUDA(cudaMemsetAsync(d_vol, 0, static_cast<size_t>(dim_x) * dim_y * dim_z * sizeof(float), ctx->compute));
     return PARIS_B200_OK;
 }
@@ -402,7 +427,7 @@ extern "C" int paris_b200_volume_free(paris_b200_ctx* ctx, float* d_vol)
         return PARIS_B200_OK;
     PB_TRY(bind(ctx));
     if(ctx->pending > 0 && ctx->target.d_vol == d_vol)
-        ctx->pending = 0; // nobody can observe the result any more
+        PB_TRY(paris_b200_flush(ctx)); // (simplest way to let go of the batch's raw buffers)
     PB_CUDA(cudaStreamSynchronize(ctx->compute));
     PB_CUDA(cudaFree(d_vol));
     return PARIS_B200_OK;
@@ -413,6 +438,7 @@ extern "C" int paris_b200_proj_h2d(paris_b200_ctx* ctx, const float* h_src, floa
 {
     PB_CHECK_ARG(ctx != nullptr && h_src != nullptr && d_dst != nullptr && dim_x > 0 && dim_y > 0);
     PB_TRY(bind(ctx));
+    PB_TRY(flush_if_held(ctx, d_dst));
     const size_t bytes = static_cast<size_t>(dim_x) * dim_y * sizeof(float);
     auto* b = find_buffer(ctx, d_dst);
     if(b != nullptr && b->freed_valid)
@@ -465,6 +491,7 @@ extern "C" int paris_b200_proj_d2h(paris_b200_ctx* ctx, const float* d_src, floa
 {
     PB_CHECK_ARG(ctx != nullptr && d_src != nullptr && h_dst != nullptr);
     PB_TRY(bind(ctx));
+    PB_TRY(flush_if_held(ctx, d_src));
     const size_t bytes = static_cast<size_t>(dim_x) * dim_y * sizeof(float);
     PB_CUDA(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, ctx->compute));
     PB_CUDA(cudaStreamSynchronize(ctx->compute));
@@ -560,6 +587,16 @@ extern "C" int paris_b200_filter_create(paris_b200_ctx* ctx, uint32_t size, floa
         k[x] = tau * std::abs(std::sqrt(std::pow(re, 2.f) + std::pow(im, 2.f)));
         kn[x] = k[x] / static_cast<float>(size);
     }
+    // the same table in the order the forward transform leaves its output in (filter.cu)
+    int log2n = 0;
+    while((1u << log2n) < size)
+        ++log2n;
+    std::vector<float> knp(size);
+    for(uint32_t pos = 0; pos < size; ++pos)
+    {
+        const uint32_t fq = static_cast<uint32_t>(frequency_of_position(log2n, static_cast<int>(pos)));
+        knp[pos] = kn[fq <= size / 2 ? fq : size - fq];
+    }
     std::vector<float2> tw(size);
     for(uint32_t i = 0; i < size; ++i)
     {
@@ -573,6 +610,8 @@ extern "C" int paris_b200_filter_create(paris_b200_ctx* ctx, uint32_t size, floa
     f->tau = tau;
     PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&f->d_k), n_trans * sizeof(float)));
     PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&f->d_kn), n_trans * sizeof(float)));
+    PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&f->d_knp), size * sizeof(float)));
+    PB_CUDA(cudaMemcpy(f->d_knp, knp.data(), size * sizeof(float), cudaMemcpyHostToDevice));
     PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&f->d_tw), size * sizeof(float2)));
     PB_CUDA(cudaMemcpy(f->d_k, k.data(), n_trans * sizeof(float), cudaMemcpyHostToDevice));
     PB_CUDA(cudaMemcpy(f->d_kn, kn.data(), n_trans * sizeof(float), cudaMemcpyHostToDevice));
@@ -588,6 +627,7 @@ extern "C" int paris_b200_filter_destroy(paris_b200_filter* f)
     PB_CUDA(cudaSetDevice(f->device));
     cudaFree(f->d_k);
     cudaFree(f->d_kn);
+    cudaFree(f->d_knp);
     cudaFree(f->d_tw);
     delete f;
     return PARIS_B200_OK;
@@ -608,6 +648,7 @@ extern "C" int paris_b200_weight(paris_b200_ctx* ctx, float* d_proj, uint32_t di
 {
     PB_CHECK_ARG(ctx != nullptr && d_proj != nullptr && dim_x > 0 && dim_y > 0);
     PB_TRY(bind(ctx));
+    PB_TRY(flush_if_held(ctx, d_proj));
     return launch_weight(ctx, d_proj, dim_x, dim_y, h_min, v_min, d_sd, l_px_row, l_px_col);
 }
 
@@ -617,6 +658,7 @@ extern "C" int paris_b200_apply_filter(paris_b200_ctx* ctx, float* d_proj, uint3
     PB_CHECK_ARG(ctx != nullptr && d_proj != nullptr && filter != nullptr);
     PB_CHECK_ARG(filter_size == filter->size && n_col == dim_y && dim_x <= filter_size);
     PB_TRY(bind(ctx));
+    PB_TRY(flush_if_held(ctx, d_proj));
     return launch_filter(ctx, d_proj, d_proj, dim_x, dim_y, filter, weight_params{}, false, 0);
 }
 
@@ -627,8 +669,24 @@ extern "C" int paris_b200_weight_filter(paris_b200_ctx* ctx, float* d_proj, uint
     PB_CHECK_ARG(ctx != nullptr && d_proj != nullptr && filter != nullptr);
     PB_CHECK_ARG(filter_size == filter->size && dim_x <= filter_size);
     PB_TRY(bind(ctx));
+    PB_TRY(flush_if_held(ctx, d_proj));
     weight_params w{1, h_min, v_min, d_sd, l_px_row, l_px_col};
     return launch_filter(ctx, d_proj, d_proj, dim_x, dim_y, filter, w, false, 0);
+}
+
+static weight_params weighting_from_detector(const paris_b200_detector_geometry* det)
+{
+    // src/weighting.cpp:37-42
+    const float n_row_f = static_cast<float>(det->n_row);
+    const float n_col_f = static_cast<float>(det->n_col);
+    weight_params w{};
+    w.enable = 1;
+    w.h_min = (det->delta_s * det->l_px_row) - ((n_row_f * det->l_px_row) / 2);
+    w.v_min = (det->delta_t * det->l_px_col) - ((n_col_f * det->l_px_col) / 2);
+    w.d_sd = std::fabs(det->d_so) + std::fabs(det->d_od);
+    w.l_px_row = det->l_px_row;
+    w.l_px_col = det->l_px_col;
+    return w;
 }
 
 // ---- deferred backprojection ------------------------------------------------------------------------------
@@ -675,16 +733,55 @@ static int ensure_stack(paris_b200_ctx* ctx, uint32_t n_row, uint32_t n_col)
     return PARIS_B200_OK;
 }
 
+// enqueue the deferred fused weight+filter launch of the pending batch and let go of its raw buffers
+static int run_pending_filter(paris_b200_ctx* ctx)
+{
+    if(ctx->pend_raw_count == 0)
+        return PARIS_B200_OK;
+    const int n = ctx->pend_raw_count;
+    ctx->pend_raw_count = 0;
+    const int rc = launch_filter_batch(ctx, ctx->pend_raw, nullptr, static_cast<uint32_t>(n), ctx->stack,
+                                       static_cast<uint32_t>(ctx->pend_raw_first), ctx->stack_slot_floats,
+                                       ctx->stack_n_row, ctx->stack_n_col, ctx->pend_filter, ctx->pend_w, true,
+                                       ctx->stack_pitch);
+    for(auto& b : ctx->pool)
+    {
+        if(!b.held)
+            continue;
+        b.held = false;
+        if(b.free_pending)
+        {
+            b.free_pending = false;
+            PB_CUDA(cudaEventRecord(b.freed, ctx->compute));
+            b.freed_valid = true;
+            b.in_use = false;
+            ctx->free_fifo.push_back(static_cast<size_t>(&b - ctx->pool.data()));
+        }
+    }
+    return rc;
+}
+
 extern "C" int paris_b200_flush(paris_b200_ctx* ctx)
 {
     PB_CHECK_ARG(ctx != nullptr);
     if(ctx->pending == 0)
         return PARIS_B200_OK;
     PB_TRY(bind(ctx));
+    PB_TRY(run_pending_filter(ctx));
+    ++ctx->stat_flush;
     const int n = ctx->pending;
     ctx->pending = 0;
     return launch_backproject(ctx, ctx->stack, ctx->stack_slot_floats, ctx->stack_pitch, 0u, static_cast<uint32_t>(n),
                               ctx->pend_sin, ctx->pend_cos, ctx->target);
+}
+
+// a buffer a deferred launch still has to read must not be touched before that launch is enqueued
+static int flush_if_held(paris_b200_ctx* ctx, const void* d_ptr)
+{
+    for(const auto& b : ctx->pool)
+        if(b.ptr == d_ptr && b.held)
+            return paris_b200_flush(ctx);
+    return PARIS_B200_OK;
 }
 
 extern "C" int paris_b200_backproject(paris_b200_ctx* ctx, const float* d_proj, uint32_t dim_x, uint32_t dim_y,
@@ -725,11 +822,7 @@ extern "C" int paris_b200_backproject(paris_b200_ctx* ctx, const float* d_proj, 
     float* slot = ctx->stack + ctx->stack_slot_floats * static_cast<size_t>(ctx->pending);
     if(fuse)
     {
-        // src/weighting.cpp:37-42
-        const float n_row_f = static_cast<float>(det->n_row);
-        const float n_col_f = static_cast<float>(det->n_col);
-        weight_params w{};
-        w.enable = 1;
+        weight_params w = weighting_from_detector(det);
         if(weighting != nullptr)
         {
             w.h_min = weighting->h_min;
@@ -738,18 +831,34 @@ extern "C" int paris_b200_backproject(paris_b200_ctx* ctx, const float* d_proj, 
             w.l_px_row = weighting->l_px_row;
             w.l_px_col = weighting->l_px_col;
         }
-        else
+        pb::raw_buffer* buf = find_buffer(ctx, d_proj);
+        if(buf != nullptr && buf->in_use)
         {
-            w.h_min = (det->delta_s * det->l_px_row) - ((n_row_f * det->l_px_row) / 2);
-            w.v_min = (det->delta_t * det->l_px_col) - ((n_col_f * det->l_px_col) / 2);
-            w.d_sd = std::fabs(det->d_so) + std::fabs(det->d_od);
-            w.l_px_row = det->l_px_row;
-            w.l_px_col = det->l_px_col;
+            // Pooled buffer: defer the fused weight+filter kernel so that the whole batch is ONE launch
+            // (filter.cu).  The deferred run must be a consecutive range of slots with one filter and one
+            // set of weighting scalars.
+            const bool extends = ctx->pend_raw_count > 0 && ctx->pend_filter == filter
+                              && std::memcmp(&ctx->pend_w, &w, sizeof(w)) == 0
+                              && ctx->pend_raw_first + ctx->pend_raw_count == ctx->pending;
+            if(ctx->pend_raw_count > 0 && !extends)
+                PB_TRY(run_pending_filter(ctx));
+            if(ctx->pend_raw_count == 0)
+            {
+                ctx->pend_raw_first = ctx->pending;
+                ctx->pend_filter = filter;
+                ctx->pend_w = w;
+            }
+            ctx->pend_raw[ctx->pend_raw_count++] = d_proj;
+            buf->held = true;
         }
-        PB_TRY(launch_filter(ctx, d_proj, slot, dim_x, dim_y, filter, w, true, ctx->stack_pitch));
+        else
+            PB_TRY(launch_filter(ctx, d_proj, slot, dim_x, dim_y, filter, w, true, ctx->stack_pitch));
     }
     else
+    {
+        PB_TRY(flush_if_held(ctx, d_proj));
         PB_TRY(launch_transpose_to_slot(ctx, d_proj, slot, dim_x, dim_y, ctx->stack_pitch));
+    }
 
     ctx->pend_sin[ctx->pending] = sin_phi;
     ctx->pend_cos[ctx->pending] = cos_phi;
@@ -761,25 +870,37 @@ extern "C" int paris_b200_backproject(paris_b200_ctx* ctx, const float* d_proj, 
 
 // ---- stack-level entry points -----------------------------------------------------------------------------
 
+extern "C" int paris_b200_filter_to_stack_batch(paris_b200_ctx* ctx, const float* d_raw, size_t raw_stride,
+                                                uint32_t count, const paris_b200_detector_geometry* det,
+                                                const paris_b200_filter* filter, float* d_stack, uint32_t first_slot)
+{
+    PB_CHECK_ARG(ctx != nullptr && d_raw != nullptr && det != nullptr && filter != nullptr && d_stack != nullptr);
+    PB_CHECK_ARG(det->n_row <= filter->size);
+    PB_CHECK_ARG(count <= 1u || raw_stride >= static_cast<size_t>(det->n_row) * det->n_col);
+    PB_TRY(bind(ctx));
+    const uint32_t pitch = stack_pitch_for(det->n_col);
+    const size_t slot_floats = static_cast<size_t>(pitch) * det->n_row;
+    const weight_params w = weighting_from_detector(det);
+    const float* src[kMaxBatch];
+    for(uint32_t done = 0; done < count;)
+    {
+        const uint32_t n = std::min<uint32_t>(count - done, static_cast<uint32_t>(kMaxBatch));
+        for(uint32_t i = 0; i < n; ++i)
+            src[i] = d_raw + raw_stride * (done + i);
+        PB_TRY(launch_filter_batch(ctx, src, nullptr, n, d_stack, first_slot + done, slot_floats, det->n_row, det->n_col,
+                                   filter, w, true, pitch));
+        done += n;
+    }
+    return PARIS_B200_OK;
+}
+
 extern "C" int paris_b200_filter_to_stack(paris_b200_ctx* ctx, const float* d_raw,
                                           const paris_b200_detector_geometry* det, const paris_b200_filter* filter,
                                           float* d_stack, uint32_t slot)
 {
-    PB_CHECK_ARG(ctx != nullptr && d_raw != nullptr && det != nullptr && filter != nullptr && d_stack != nullptr);
-    PB_CHECK_ARG(det->n_row <= filter->size);
-    PB_TRY(bind(ctx));
-    const uint32_t pitch = stack_pitch_for(det->n_col);
-    const size_t slot_floats = static_cast<size_t>(pitch) * det->n_row;
-    const float n_row_f = static_cast<float>(det->n_row);
-    const float n_col_f = static_cast<float>(det->n_col);
-    weight_params w{};
-    w.enable = 1;
-    w.h_min = (det->delta_s * det->l_px_row) - ((n_row_f * det->l_px_row) / 2);
-    w.v_min = (det->delta_t * det->l_px_col) - ((n_col_f * det->l_px_col) / 2);
-    w.d_sd = std::fabs(det->d_so) + std::fabs(det->d_od);
-    w.l_px_row = det->l_px_row;
-    w.l_px_col = det->l_px_col;
-    return launch_filter(ctx, d_raw, d_stack + slot_floats * slot, det->n_row, det->n_col, filter, w, true, pitch);
+    PB_CHECK_ARG(ctx != nullptr);
+    PB_TRY(flush_if_held(ctx, d_raw));
+    return paris_b200_filter_to_stack_batch(ctx, d_raw, 0, 1u, det, filter, d_stack, slot);
 }
 
 extern "C" int paris_b200_backproject_stack(paris_b200_ctx* ctx, const float* d_stack, uint32_t first, uint32_t count,

@@ -27,6 +27,8 @@ namespace pb
         bool in_use = false;
         cudaEvent_t freed = nullptr;   // recorded on the compute stream at dev_free
         bool freed_valid = false;
+        bool held = false;          // read by a deferred filter launch that has not been enqueued yet
+        bool free_pending = false;  // dev_free arrived while held
     };
 
     // Geometry of one pending backprojection batch: everything but the angles must match for
@@ -40,6 +42,12 @@ namespace pb
         int enable_roi = 0;
         paris_b200_roi roi{};
         float delta_s_mm = 0.f, delta_t_mm = 0.f;
+    };
+
+    struct weight_params
+    {
+        int enable = 0;
+        float h_min = 0.f, v_min = 0.f, d_sd = 0.f, l_px_row = 0.f, l_px_col = 0.f;
     };
 
     struct tma_desc_cache
@@ -58,6 +66,7 @@ struct paris_b200_filter
     float tau = 0.f;
     float* d_k = nullptr;    // K[x], x = 0..N/2 (as the reference defines it)
     float* d_kn = nullptr;   // K[x] / N  (exact: N is a power of two)
+    float* d_knp = nullptr;  // K/N per STORAGE position of the forward transform (digit-reversed order), N entries
     float2* d_tw = nullptr;  // exp(-2 pi i k / N), k = 0..N-1
 };
 
@@ -71,9 +80,11 @@ struct paris_b200_ctx
     bool h2d_any = false;
     cudaEvent_t scratch_ev = nullptr;
     uint64_t launches = 0;
+    // pool statistics (paris_b200_ctx_stats)
+    uint64_t stat_pool_malloc = 0, stat_pool_ready = 0, stat_pool_busy = 0, stat_flush = 0;
 
     // options
-    int bp_batch = 32;
+    int bp_batch = 64;
     int bp_kernel = 0;
 
     // pooled raw projection buffers (dev_alloc / dev_free)
@@ -90,6 +101,12 @@ struct paris_b200_ctx
     int pending = 0;
     float pend_sin[pb::kMaxBatch];
     float pend_cos[pb::kMaxBatch];
+    // raw projections of the pending batch whose fused weight+filter launch is deferred to the flush
+    const float* pend_raw[pb::kMaxBatch];
+    int pend_raw_first = 0;   // they are consecutive: slots pend_raw_first .. pend_raw_first + pend_raw_count - 1
+    int pend_raw_count = 0;
+    pb::weight_params pend_w{};
+    const paris_b200_filter* pend_filter = nullptr;
 
     pb::tma_desc_cache tma;
 };
@@ -129,16 +146,19 @@ namespace pb
     int launch_weight(paris_b200_ctx* ctx, float* d_proj, uint32_t dim_x, uint32_t dim_y, float h_min, float v_min,
                       float d_sd, float l_px_row, float l_px_col);
 
-    struct weight_params
-    {
-        int enable = 0;
-        float h_min = 0.f, v_min = 0.f, d_sd = 0.f, l_px_row = 0.f, l_px_col = 0.f;
-    };
-
     // src rows -> (optional weight) -> ramp filter -> dst.  dst_transposed: write dst[s*dst_pitch + t]
     // (stack slot layout) instead of dst[t*dim_x + s].
     int launch_filter(paris_b200_ctx* ctx, const float* d_src, float* d_dst, uint32_t dim_x, uint32_t dim_y,
                       const paris_b200_filter* f, const weight_params& w, bool dst_transposed, uint32_t dst_pitch);
+
+    // `count` (<= kMaxBatch) projections in one launch.  Transposed: src[i] -> slot first_slot + i of d_stack;
+    // row-major: src[i] -> dst[i] (may alias).
+    int launch_filter_batch(paris_b200_ctx* ctx, const float* const* d_src, float* const* d_dst, uint32_t count,
+                            float* d_stack, uint32_t first_slot, size_t slot_floats, uint32_t dim_x, uint32_t dim_y,
+                            const paris_b200_filter* f, const weight_params& w, bool transposed, uint32_t pitch);
+
+    // frequency index stored at position p after the forward passes of the size-2^log2n transform
+    int frequency_of_position(int log2n, int p);
 
     int launch_transpose_to_slot(paris_b200_ctx* ctx, const float* d_src, float* d_slot, uint32_t dim_x,
                                  uint32_t dim_y, uint32_t pitch);

@@ -8,11 +8,18 @@
 //   * two detector rows a, b are packed as ONE complex sequence z = a + i b.  The filter K is real and
 //     even (src/openmp/filtering.cpp:155-161 stores tau*|R| in re and im), so filtering z filters both
 //     rows at once and no Hermitian untangling pass is needed;
-//   * zero padding to N = filter_size happens in shared memory;
-//   * forward transform: in-place decimation-in-frequency radix-4 passes (natural order in,
-//     digit-reversed out); K/N is applied in digit-reversed order; inverse transform: decimation-in-time
-//     passes that consume digit-reversed input and deliver natural order -- no reordering pass at all;
-//   * 1/N is folded into the table (exact, N is a power of two).
+//   * zero padding to N = filter_size is implicit: the padded half is a compile-time zero in the first
+//     butterfly group and the discarded half of the output is never computed in the last one;
+//   * the transform is a chain of radix-4 decimation-in-frequency passes (natural order in, digit-reversed
+//     out), K/N applied in digit-reversed order, then decimation-in-time passes back (digit-reversed in,
+//     natural out) -- no reordering pass.  Passes are executed in GROUPS held in registers: every thread
+//     owns 16 points and runs two radix-4 passes on them between shared-memory exchanges (an effective
+//     radix-16 step); the last forward passes, the multiplication by K and the first inverse passes are
+//     one register-resident step.  N = 2048 and 4096 need 4 exchanges in total;
+//   * the first group reads its points straight from global memory (weighted on the fly), the last one
+//     writes straight to global memory or, for the filtered stack, to a staging tile so that the
+//     TRANSPOSED slot (detector-row index fastest) is written in 32-byte runs;
+//   * one launch covers a whole batch of projections (blockIdx.y), 8 detector rows per CTA.
 //
 // No cuFFT, and the weighted / padded / transformed row never exists in HBM.
 #include "common.cuh"
@@ -20,208 +27,400 @@
 
 namespace pb
 {
-    constexpr int kStageRows = 8;     // detector rows per CTA in transposed-output mode
+    constexpr int kRowsPerCta = 8;    // detector rows (4 row pairs) per CTA
     constexpr int kStagePitch = 10;   // floats per staged sample line: 8 rows + 2 pad (conflict-free float2 stores)
+}
 
-    // frequency index held at storage position p after the forward passes (mixed-radix digit reversal)
-    template <int LOG2N>
-    __device__ __forceinline__ int frequency_of_position(int p)
+#include "filter_small.cuh"
+
+namespace pb
+{
+    // shared-memory index of point i: one float2 of padding per 16 points keeps both the strided group
+    // accesses and the contiguous 16-point accesses of the middle step conflict-free
+    __host__ __device__ constexpr int pad(int i) { return i + (i >> 4); }
+
+    // frequency index held at storage position p after the forward passes (mixed-radix digit reversal:
+    // radix-4 passes with spans N, N/4, ... then one radix-2 pass if log2 N is odd)
+    int frequency_of_position(int log2n, int p)
     {
-        constexpr int N = 1 << LOG2N;
         int k = 0;
         int rem = p;
-        #pragma unroll
-        for(int m = LOG2N; m >= 2; m -= 2)
+        for(int m = log2n; m >= 2; m -= 2)
         {
-            // pass with span M = 2^m: digit = rem / (M/4), weight N/M
             const int d = rem >> (m - 2);
             rem &= (1 << (m - 2)) - 1;
-            k += d << (LOG2N - m);
+            k += d << (log2n - m);
         }
-        if(LOG2N & 1)
-            k += rem * (N / 2);
+        if(log2n & 1)
+            k += rem << (log2n - 1);
         return k;
     }
 
-    template <int LOG2N>
-    __device__ __forceinline__ void forward_passes(float2* x, const float2* __restrict__ tw, int tid, int nt)
+    // ---- radix-4 butterflies: output q carries X[4k+q] of the sub-transform -------------------------------------
+
+    __device__ __forceinline__ void dif4(float2& a0, float2& a1, float2& a2, float2& a3)
     {
-        constexpr int N = 1 << LOG2N;
-        #pragma unroll 1
-        for(int m = LOG2N; m >= 2; m -= 2)
+        const float2 t0 = make_float2(a0.x + a2.x, a0.y + a2.y);
+        const float2 t1 = make_float2(a0.x - a2.x, a0.y - a2.y);
+        const float2 t2 = make_float2(a1.x + a3.x, a1.y + a3.y);
+        const float2 t3 = make_float2(a1.y - a3.y, a3.x - a1.x); // (a1 - a3) * (-i)
+        a0 = make_float2(t0.x + t2.x, t0.y + t2.y);
+        a1 = make_float2(t1.x + t3.x, t1.y + t3.y);
+        a2 = make_float2(t0.x - t2.x, t0.y - t2.y);
+        a3 = make_float2(t1.x - t3.x, t1.y - t3.y);
+    }
+
+    __device__ __forceinline__ void dit4(float2& b0, float2& b1, float2& b2, float2& b3)
+    {
+        const float2 t0 = make_float2(b0.x + b2.x, b0.y + b2.y);
+        const float2 t1 = make_float2(b0.x - b2.x, b0.y - b2.y);
+        const float2 t2 = make_float2(b1.x + b3.x, b1.y + b3.y);
+        const float2 t3 = make_float2(b3.y - b1.y, b1.x - b3.x); // (b1 - b3) * (+i)
+        b0 = make_float2(t0.x + t2.x, t0.y + t2.y);
+        b1 = make_float2(t1.x + t3.x, t1.y + t3.y);
+        b2 = make_float2(t0.x - t2.x, t0.y - t2.y);
+        b3 = make_float2(t1.x - t3.x, t1.y - t3.y);
+    }
+
+    __device__ __forceinline__ void bfly2(float2& a0, float2& a1)
+    {
+        const float2 s = make_float2(a0.x + a1.x, a0.y + a1.y);
+        a1 = make_float2(a0.x - a1.x, a0.y - a1.y);
+        a0 = s;
+    }
+
+    // One radix-4 pass of span 2^M on 4 register points whose position inside the quarter is j:
+    // forward = butterfly, then twiddle W_span^(q j) on output q; inverse = conjugate twiddle, then butterfly.
+    template <int LOG2N, int M, bool INVERSE>
+    __device__ __forceinline__ void pass4(float2& e0, float2& e1, float2& e2, float2& e3, int j,
+                                          const float2* __restrict__ tw)
+    {
+        const int t = j << (LOG2N - M);
+        if(!INVERSE)
         {
-            const int q_log = m - 2;           // Q = M/4
-            const int Q = 1 << q_log;
-            const int tw_shift = LOG2N - m;     // twiddle stride N/M
-            for(int b = tid; b < N / 4; b += nt)
+            dif4(e0, e1, e2, e3);
+            if(M > 2)
             {
-                const int j = b & (Q - 1);
-                const int base = ((b >> q_log) << m) + j;
-                const float2 a0 = x[base], a1 = x[base + Q], a2 = x[base + 2 * Q], a3 = x[base + 3 * Q];
-                const float2 t0 = make_float2(a0.x + a2.x, a0.y + a2.y);
-                const float2 t1 = make_float2(a0.x - a2.x, a0.y - a2.y);
-                const float2 t2 = make_float2(a1.x + a3.x, a1.y + a3.y);
-                // (a1 - a3) * (-i)
-                const float2 t3 = make_float2(a1.y - a3.y, a3.x - a1.x);
-                const float2 y0 = make_float2(t0.x + t2.x, t0.y + t2.y);
-                const float2 y1 = make_float2(t1.x + t3.x, t1.y + t3.y);
-                const float2 y2 = make_float2(t0.x - t2.x, t0.y - t2.y);
-                const float2 y3 = make_float2(t1.x - t3.x, t1.y - t3.y);
-                const int e = j << tw_shift;
-                x[base] = y0;
-                x[base + Q] = cmul(y1, __ldg(tw + e));
-                x[base + 2 * Q] = cmul(y2, __ldg(tw + 2 * e));
-                x[base + 3 * Q] = cmul(y3, __ldg(tw + 3 * e));
+                e1 = cmul(e1, __ldg(tw + t));
+                e2 = cmul(e2, __ldg(tw + 2 * t));
+                e3 = cmul(e3, __ldg(tw + 3 * t));
             }
-            __syncthreads();
         }
-        if(LOG2N & 1)
+        else
         {
-            for(int b = tid; b < N / 2; b += nt)
+            if(M > 2)
             {
-                const float2 a0 = x[2 * b], a1 = x[2 * b + 1];
-                x[2 * b] = make_float2(a0.x + a1.x, a0.y + a1.y);
-                x[2 * b + 1] = make_float2(a0.x - a1.x, a0.y - a1.y);
+                e1 = cmul_conj(e1, __ldg(tw + t));
+                e2 = cmul_conj(e2, __ldg(tw + 2 * t));
+                e3 = cmul_conj(e3, __ldg(tw + 3 * t));
             }
-            __syncthreads();
+            dit4(e0, e1, e2, e3);
         }
     }
 
-    template <int LOG2N>
-    __device__ __forceinline__ void inverse_passes(float2* x, const float2* __restrict__ tw, int tid, int nt)
+    // Two consecutive passes (spans 2^M and 2^(M-2)) on the 16 points e[k] = x[block*2^M + j + k*2^(M-4)].
+    template <int LOG2N, int M, bool INVERSE>
+    __device__ __forceinline__ void group16(float2 (&e)[16], int j, const float2* __restrict__ tw)
     {
-        constexpr int N = 1 << LOG2N;
-        if(LOG2N & 1)
+        constexpr int Q2 = 1 << (M - 4);
+        if(!INVERSE)
         {
-            for(int b = tid; b < N / 2; b += nt)
-            {
-                const float2 a0 = x[2 * b], a1 = x[2 * b + 1];
-                x[2 * b] = make_float2(a0.x + a1.x, a0.y + a1.y);
-                x[2 * b + 1] = make_float2(a0.x - a1.x, a0.y - a1.y);
-            }
-            __syncthreads();
+            #pragma unroll
+            for(int r = 0; r < 4; ++r)
+                pass4<LOG2N, M, false>(e[r], e[r + 4], e[r + 8], e[r + 12], j + r * Q2, tw);
+            #pragma unroll
+            for(int q = 0; q < 4; ++q)
+                pass4<LOG2N, M - 2, false>(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3], j, tw);
         }
-        #pragma unroll 1
-        for(int m = 2 + (LOG2N & 1); m <= LOG2N; m += 2)
+        else
         {
-            const int q_log = m - 2;
-            const int Q = 1 << q_log;
-            const int tw_shift = LOG2N - m;
-            for(int b = tid; b < N / 4; b += nt)
-            {
-                const int j = b & (Q - 1);
-                const int base = ((b >> q_log) << m) + j;
-                const int e = j << tw_shift;
-                const float2 b0 = x[base];
-                const float2 b1 = cmul_conj(x[base + Q], __ldg(tw + e));
-                const float2 b2 = cmul_conj(x[base + 2 * Q], __ldg(tw + 2 * e));
-                const float2 b3 = cmul_conj(x[base + 3 * Q], __ldg(tw + 3 * e));
-                const float2 t0 = make_float2(b0.x + b2.x, b0.y + b2.y);
-                const float2 t1 = make_float2(b0.x - b2.x, b0.y - b2.y);
-                const float2 t2 = make_float2(b1.x + b3.x, b1.y + b3.y);
-                // (b1 - b3) * (+i)
-                const float2 t3 = make_float2(b3.y - b1.y, b1.x - b3.x);
-                x[base] = make_float2(t0.x + t2.x, t0.y + t2.y);
-                x[base + Q] = make_float2(t1.x + t3.x, t1.y + t3.y);
-                x[base + 2 * Q] = make_float2(t0.x - t2.x, t0.y - t2.y);
-                x[base + 3 * Q] = make_float2(t1.x - t3.x, t1.y - t3.y);
-            }
-            __syncthreads();
+            #pragma unroll
+            for(int q = 0; q < 4; ++q)
+                pass4<LOG2N, M - 2, true>(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3], j, tw);
+            #pragma unroll
+            for(int r = 0; r < 4; ++r)
+                pass4<LOG2N, M, true>(e[r], e[r + 4], e[r + 8], e[r + 12], j + r * Q2, tw);
         }
     }
 
-    // One CTA filters PAIRS pairs of detector rows.  TRANSPOSED: results are staged in shared memory and
-    // written as dst[s * dst_pitch + t] in 32-byte runs (8 consecutive t per sample s); otherwise each row is
-    // written back in place / row-major right after its transform.
+    // shared-memory positions of a thread's 16 points for the double group at span 2^M
+    template <int M>
+    __device__ __forceinline__ int group_pos(int b, int k)
+    {
+        constexpr int Q2LOG = M - 4;
+        return ((b >> Q2LOG) << M) + (b & ((1 << Q2LOG) - 1)) + (k << Q2LOG);
+    }
+
+    // A lone radix-4 pass of span 2^M: thread b runs the butterflies b, b+T, b+2T, b+3T (T threads per transform);
+    // butterfly t occupies e[4t .. 4t+3].
+    template <int LOG2N, int M, bool INVERSE>
+    __device__ __forceinline__ void lone_group(float2* x, int b, const float2* __restrict__ tw)
+    {
+        constexpr int T = (1 << LOG2N) / 16;
+        constexpr int QLOG = M - 2;
+        float2 e[16];
+        int base[4], j[4];
+        #pragma unroll
+        for(int t = 0; t < 4; ++t)
+        {
+            const int bb = b + t * T;
+            j[t] = bb & ((1 << QLOG) - 1);
+            base[t] = ((bb >> QLOG) << M) + j[t];
+            #pragma unroll
+            for(int q = 0; q < 4; ++q)
+                e[4 * t + q] = x[pad(base[t] + (q << QLOG))];
+        }
+        #pragma unroll
+        for(int t = 0; t < 4; ++t)
+            pass4<LOG2N, M, INVERSE>(e[4 * t], e[4 * t + 1], e[4 * t + 2], e[4 * t + 3], j[t], tw);
+        #pragma unroll
+        for(int t = 0; t < 4; ++t)
+        {
+            #pragma unroll
+            for(int q = 0; q < 4; ++q)
+                x[pad(base[t] + (q << QLOG))] = e[4 * t + q];
+        }
+    }
+
+    // The register-resident middle: the passes with span <= 16 on the 16 CONTIGUOUS points 16b..16b+15,
+    // forward, then K/N (table permuted to storage order on the host), then the same passes backwards.
+    template <int LOG2N>
+    __device__ __forceinline__ void middle_group(float2* x, const float* __restrict__ knp, int b,
+                                                 const float2* __restrict__ tw)
+    {
+        float2 e[16];
+        #pragma unroll
+        for(int k = 0; k < 16; ++k)
+            e[k] = x[pad(16 * b) + k];
+
+        if(LOG2N % 2 == 0)
+        {
+            #pragma unroll
+            for(int r = 0; r < 4; ++r)
+                pass4<LOG2N, 4, false>(e[r], e[r + 4], e[r + 8], e[r + 12], r, tw);
+            #pragma unroll
+            for(int q = 0; q < 4; ++q)
+                pass4<LOG2N, 2, false>(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3], 0, tw);
+        }
+        else
+        {
+            #pragma unroll
+            for(int u = 0; u < 2; ++u)
+            {
+                #pragma unroll
+                for(int r = 0; r < 2; ++r)
+                    pass4<LOG2N, 3, false>(e[8 * u + r], e[8 * u + r + 2], e[8 * u + r + 4], e[8 * u + r + 6], r, tw);
+            }
+            #pragma unroll
+            for(int p = 0; p < 8; ++p)
+                bfly2(e[2 * p], e[2 * p + 1]);
+        }
+
+        const float4* k4 = reinterpret_cast<const float4*>(knp + 16 * b);
+        #pragma unroll
+        for(int v = 0; v < 4; ++v)
+        {
+            const float4 k = __ldg(k4 + v);
+            e[4 * v + 0].x *= k.x; e[4 * v + 0].y *= k.x;
+            e[4 * v + 1].x *= k.y; e[4 * v + 1].y *= k.y;
+            e[4 * v + 2].x *= k.z; e[4 * v + 2].y *= k.z;
+            e[4 * v + 3].x *= k.w; e[4 * v + 3].y *= k.w;
+        }
+
+        if(LOG2N % 2 == 0)
+        {
+            #pragma unroll
+            for(int q = 0; q < 4; ++q)
+                pass4<LOG2N, 2, true>(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3], 0, tw);
+            #pragma unroll
+            for(int r = 0; r < 4; ++r)
+                pass4<LOG2N, 4, true>(e[r], e[r + 4], e[r + 8], e[r + 12], r, tw);
+        }
+        else
+        {
+            #pragma unroll
+            for(int p = 0; p < 8; ++p)
+                bfly2(e[2 * p], e[2 * p + 1]);
+            #pragma unroll
+            for(int u = 0; u < 2; ++u)
+            {
+                #pragma unroll
+                for(int r = 0; r < 2; ++r)
+                    pass4<LOG2N, 3, true>(e[8 * u + r], e[8 * u + r + 2], e[8 * u + r + 4], e[8 * u + r + 6], r, tw);
+            }
+        }
+
+        #pragma unroll
+        for(int k = 0; k < 16; ++k)
+            x[pad(16 * b) + k] = e[k];
+    }
+
+    // ---- group plan ------------------------------------------------------------------------------------------
+    // Passes with span > 16 ("outer"), first to last: 2^LOG2N, 2^(LOG2N-2), ... down to 2^6 (LOG2N even) or
+    // 2^5 (odd).  They are taken two at a time from the top; an odd one out is a lone radix-4 group.
+    template <int LOG2N>
+    struct plan
+    {
+        static_assert(LOG2N >= 8 && LOG2N <= 13, "register-grouped kernel covers 256..8192 points");
+        static constexpr int N = 1 << LOG2N;
+        static constexpr int T = N / 16;                                  // threads per transform
+        static constexpr int LOW = (LOG2N % 2 == 0) ? 6 : 5;
+        static constexpr int OUTER = (LOG2N - LOW) / 2 + 1;               // 2 (256) .. 5 (8192)
+        static constexpr int DOUBLES = OUTER / 2;                         // 1 or 2
+        static constexpr bool LONE = (OUTER % 2) != 0;
+        static constexpr int PAIRS = (512 / T) < 4 ? ((512 / T) < 1 ? 1 : 512 / T) : 4;  // row pairs side by side
+        static constexpr int ROUNDS = 4 / PAIRS;
+        static constexpr int THREADS = PAIRS * T;
+        static constexpr int NPAD = pad(N);
+    };
+
+    struct filter_batch
+    {
+        const float* src[kMaxBatch];
+        float* dst[kMaxBatch];   // row-major destinations (TRANSPOSED == false)
+    };
+
     template <int LOG2N, bool TRANSPOSED>
-    __global__ void __launch_bounds__(((1 << LOG2N) / 4 > 1024) ? 1024 : (1 << LOG2N) / 4)
-    filter_kernel(const float* src, float* dst, uint32_t dim_x, uint32_t dim_y,
-                  const float* __restrict__ kn, const float2* __restrict__ tw, weight_params w, uint32_t dst_pitch)
+    __global__ void __launch_bounds__(plan<LOG2N>::THREADS, 1)
+    filter_kernel(const filter_batch io, float* dst_stack, uint32_t first_slot, size_t slot_floats, uint32_t dim_x,
+                  uint32_t dim_y, const float* __restrict__ knp, const float2* __restrict__ tw, weight_params w,
+                  uint32_t dst_pitch)
     {
-        constexpr int N = 1 << LOG2N;
-        constexpr int PAIRS = TRANSPOSED ? kStageRows / 2 : 1;
+        using P = plan<LOG2N>;
+        constexpr int N = P::N;
         extern __shared__ __align__(16) unsigned char smem_raw[];
-        float2* x = reinterpret_cast<float2*>(smem_raw);
-        float* stage = reinterpret_cast<float*>(smem_raw + sizeof(float2) * N); // [dim_x][kStagePitch], TRANSPOSED only
+        float* stage = reinterpret_cast<float*>(smem_raw + sizeof(float2) * P::NPAD * P::PAIRS); // [dim_x][kStagePitch]
 
-        const int tid = threadIdx.x;
-        const int nt = blockDim.x;
-        const uint32_t row_base = blockIdx.x * (2u * PAIRS);
+        const int lp = threadIdx.x / P::T;                 // row pair slot inside this round
+        const int b = threadIdx.x % P::T;                  // thread index inside the transform
+        float2* x = reinterpret_cast<float2*>(smem_raw) + lp * P::NPAD;
+
+        const float* src = io.src[blockIdx.y];
+        const uint32_t row_base = blockIdx.x * kRowsPerCta;
 
         #pragma unroll 1
-        for(int pair = 0; pair < PAIRS; ++pair)
+        for(int round = 0; round < P::ROUNDS; ++round)
         {
-            const uint32_t row0 = row_base + 2u * pair;
-            const uint32_t row1 = row0 + 1u;
-            const bool has0 = row0 < dim_y;
-            const bool has1 = row1 < dim_y;
-            if(!has0)
-                break; // uniform for the CTA; staged rows >= dim_y are never written out
+            const int pair = round * P::PAIRS + lp;        // 0..3 within the CTA's 8 rows
+            const uint32_t row0 = row_base + 2u * pair, row1 = row0 + 1u;
+            const bool has0 = row0 < dim_y, has1 = row1 < dim_y;
 
-            // load + weight + zero-pad
-            for(int i = tid; i < N; i += nt)
+            float2 e[16];
+            // ---- first group: points b + k*N/16 straight from global memory; k >= 8 is the zero padding ----------
+            #pragma unroll
+            for(int k = 0; k < 16; ++k)
             {
-                float a = 0.f, b = 0.f;
-                if(static_cast<uint32_t>(i) < dim_x)
+                float a = 0.f, c = 0.f;
+                if(k < 8)
                 {
-                    if(has0)
+                    const uint32_t i = b + k * (N / 16);
+                    if(i < dim_x)
                     {
-                        a = __ldg(src + static_cast<size_t>(row0) * dim_x + i);
-                        if(w.enable)
-                            a = __fmul_rn(a, pixel_weight(i, row0, w.h_min, w.v_min, w.d_sd, w.l_px_row, w.l_px_col));
-                    }
-                    if(has1)
-                    {
-                        b = __ldg(src + static_cast<size_t>(row1) * dim_x + i);
-                        if(w.enable)
-                            b = __fmul_rn(b, pixel_weight(i, row1, w.h_min, w.v_min, w.d_sd, w.l_px_row, w.l_px_col));
+                        if(has0)
+                        {
+                            a = __ldg(src + static_cast<size_t>(row0) * dim_x + i);
+                            if(w.enable)
+                                a = __fmul_rn(a, pixel_weight(i, row0, w.h_min, w.v_min, w.d_sd, w.l_px_row, w.l_px_col));
+                        }
+                        if(has1)
+                        {
+                            c = __ldg(src + static_cast<size_t>(row1) * dim_x + i);
+                            if(w.enable)
+                                c = __fmul_rn(c, pixel_weight(i, row1, w.h_min, w.v_min, w.d_sd, w.l_px_row, w.l_px_col));
+                        }
                     }
                 }
-                x[i] = make_float2(a, b);
+                e[k] = make_float2(a, c);
             }
+            group16<LOG2N, LOG2N, false>(e, b, tw);
+            #pragma unroll
+            for(int k = 0; k < 16; ++k)
+                x[pad(group_pos<LOG2N>(b, k))] = e[k];
             __syncthreads();
 
-            forward_passes<LOG2N>(x, tw, tid, nt);
-
-            // scale by K/N (real, even): position p holds frequency k
-            for(int p = tid; p < N; p += nt)
+            // ---- remaining outer groups, forward -------------------------------------------------------------------
+            if(P::DOUBLES == 2)
             {
-                const int k = frequency_of_position<LOG2N>(p);
-                const float s = __ldg(kn + (k <= N / 2 ? k : N - k));
-                float2 v = x[p];
-                v.x *= s;
-                v.y *= s;
-                x[p] = v;
+                constexpr int M = LOG2N - 4;
+                #pragma unroll
+                for(int k = 0; k < 16; ++k)
+                    e[k] = x[pad(group_pos<M>(b, k))];
+                group16<LOG2N, M, false>(e, b & ((1 << (M - 4)) - 1), tw);
+                #pragma unroll
+                for(int k = 0; k < 16; ++k)
+                    x[pad(group_pos<M>(b, k))] = e[k];
+                __syncthreads();
             }
+            if(P::LONE)
+            {
+                lone_group<LOG2N, P::LOW, false>(x, b, tw);
+                __syncthreads();
+            }
+
+            // ---- middle: last forward passes, K/N, first inverse passes ------------------------------------------------
+            middle_group<LOG2N>(x, knp, b, tw);
             __syncthreads();
 
-            inverse_passes<LOG2N>(x, tw, tid, nt);
+            // ---- outer groups, inverse --------------------------------------------------------------------------------
+            if(P::LONE)
+            {
+                lone_group<LOG2N, P::LOW, true>(x, b, tw);
+                __syncthreads();
+            }
+            if(P::DOUBLES == 2)
+            {
+                constexpr int M = LOG2N - 4;
+                #pragma unroll
+                for(int k = 0; k < 16; ++k)
+                    e[k] = x[pad(group_pos<M>(b, k))];
+                group16<LOG2N, M, true>(e, b & ((1 << (M - 4)) - 1), tw);
+                #pragma unroll
+                for(int k = 0; k < 16; ++k)
+                    x[pad(group_pos<M>(b, k))] = e[k];
+                __syncthreads();
+            }
+            #pragma unroll
+            for(int k = 0; k < 16; ++k)
+                e[k] = x[pad(group_pos<LOG2N>(b, k))];
+            group16<LOG2N, LOG2N, true>(e, b, tw);
 
-            // keep the first dim_x samples
+            // ---- keep the first dim_x samples (k < 8; the rest is never computed) ------------------------------------------
             if(TRANSPOSED)
             {
-                for(int i = tid; i < static_cast<int>(dim_x); i += nt)
-                    *reinterpret_cast<float2*>(stage + i * kStagePitch + 2 * pair) = x[i];
+                #pragma unroll
+                for(int k = 0; k < 8; ++k)
+                {
+                    const uint32_t i = b + k * (N / 16);
+                    if(i < dim_x)
+                        *reinterpret_cast<float2*>(stage + i * kStagePitch + 2 * pair) = e[k];
+                }
             }
             else
             {
-                for(int i = tid; i < static_cast<int>(dim_x); i += nt)
+                float* dst = io.dst[blockIdx.y];
+                #pragma unroll
+                for(int k = 0; k < 8; ++k)
                 {
-                    const float2 v = x[i];
-                    dst[static_cast<size_t>(row0) * dim_x + i] = v.x;
-                    if(has1)
-                        dst[static_cast<size_t>(row1) * dim_x + i] = v.y;
+                    const uint32_t i = b + k * (N / 16);
+                    if(i < dim_x)
+                    {
+                        if(has0)
+                            dst[static_cast<size_t>(row0) * dim_x + i] = e[k].x;
+                        if(has1)
+                            dst[static_cast<size_t>(row1) * dim_x + i] = e[k].y;
+                    }
                 }
             }
-            __syncthreads();
+            __syncthreads(); // x is reused by the next round; the stage tile is complete after the last one
         }
 
         if(TRANSPOSED)
         {
             // 4 lanes cover the 8 staged rows of one sample: 32 contiguous bytes in the stack slot
-            for(int e = tid; e < static_cast<int>(dim_x) * 4; e += nt)
+            float* dst = dst_stack + slot_floats * (first_slot + blockIdx.y);
+            for(int el = threadIdx.x; el < static_cast<int>(dim_x) * 4; el += P::THREADS)
             {
-                const int i = e >> 2, q = e & 3;
+                const int i = el >> 2, q = el & 3;
                 const uint32_t t = row_base + 2u * q;
                 if(t < dim_y)
                 {
@@ -235,54 +434,94 @@ namespace pb
     }
 
     template <int LOG2N>
-    static int launch_filter_n(paris_b200_ctx* ctx, const float* d_src, float* d_dst, uint32_t dim_x, uint32_t dim_y,
-                               const paris_b200_filter* f, const weight_params& w, bool transposed, uint32_t pitch)
+    static int launch_grouped(paris_b200_ctx* ctx, const filter_batch& io, uint32_t count, float* d_stack,
+                              uint32_t first_slot, size_t slot_floats, uint32_t dim_x, uint32_t dim_y,
+                              const paris_b200_filter* f, const weight_params& w, bool transposed, uint32_t pitch)
     {
-        constexpr int N = 1 << LOG2N;
-        constexpr int threads = (N / 4 > 1024) ? 1024 : N / 4;
+        using P = plan<LOG2N>;
+        const size_t smem = sizeof(float2) * P::NPAD * P::PAIRS + (transposed ? sizeof(float) * kStagePitch * dim_x : 0);
+        const dim3 grid((dim_y + kRowsPerCta - 1) / kRowsPerCta, count);
         if(transposed)
         {
-            const size_t smem = sizeof(float2) * N + sizeof(float) * kStagePitch * dim_x;
             auto kern = filter_kernel<LOG2N, true>;
             PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            const uint32_t grid = (dim_y + kStageRows - 1) / kStageRows;
-            kern<<<grid, threads, smem, ctx->compute>>>(d_src, d_dst, dim_x, dim_y, f->d_kn, f->d_tw, w, pitch);
+            kern<<<grid, P::THREADS, smem, ctx->compute>>>(io, d_stack, first_slot, slot_floats, dim_x, dim_y, f->d_knp,
+                                                          f->d_tw, w, pitch);
         }
         else
         {
-            const size_t smem = sizeof(float2) * N;
             auto kern = filter_kernel<LOG2N, false>;
             PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            const uint32_t grid = (dim_y + 1) / 2;
-            kern<<<grid, threads, smem, ctx->compute>>>(d_src, d_dst, dim_x, dim_y, f->d_kn, f->d_tw, w, 0u);
+            kern<<<grid, P::THREADS, smem, ctx->compute>>>(io, nullptr, 0u, 0, dim_x, dim_y, f->d_knp, f->d_tw, w, 0u);
         }
         PB_CUDA(cudaGetLastError());
         ++ctx->launches;
         return PARIS_B200_OK;
     }
 
-    int launch_filter(paris_b200_ctx* ctx, const float* d_src, float* d_dst, uint32_t dim_x, uint32_t dim_y,
-                      const paris_b200_filter* f, const weight_params& w, bool dst_transposed, uint32_t dst_pitch)
+    // `count` projections in one launch.  Transposed: src[i] -> slot first_slot + i of d_stack.
+    // Row-major: src[i] -> dst[i] (may alias).
+    int launch_filter_batch(paris_b200_ctx* ctx, const float* const* d_src, float* const* d_dst, uint32_t count,
+                            float* d_stack, uint32_t first_slot, size_t slot_floats, uint32_t dim_x, uint32_t dim_y,
+                            const paris_b200_filter* f, const weight_params& w, bool transposed, uint32_t pitch)
     {
         if(f->device != ctx->device)
         {
             set_error("filter lives on device %d, context on device %d", f->device, ctx->device);
             return PARIS_B200_EINVAL;
         }
+        if(count == 0)
+            return PARIS_B200_OK;
+        if(count > static_cast<uint32_t>(kMaxBatch))
+        {
+            set_error("filter batch of %u exceeds %d", count, kMaxBatch);
+            return PARIS_B200_EINVAL;
+        }
+        if(f->size < 256)
+        {
+            // small transforms: the all-shared-memory kernel, one projection per launch
+            for(uint32_t i = 0; i < count; ++i)
+            {
+                float* dst = transposed ? d_stack + slot_floats * (first_slot + i) : d_dst[i];
+                int rc = PARIS_B200_EINVAL;
+                switch(f->size)
+                {
+                    case 32: rc = launch_filter_small<5>(ctx, d_src[i], dst, dim_x, dim_y, f, w, transposed, pitch); break;
+                    case 64: rc = launch_filter_small<6>(ctx, d_src[i], dst, dim_x, dim_y, f, w, transposed, pitch); break;
+                    case 128: rc = launch_filter_small<7>(ctx, d_src[i], dst, dim_x, dim_y, f, w, transposed, pitch); break;
+                    default: set_error("unsupported filter size %u", f->size); break;
+                }
+                PB_TRY(rc);
+            }
+            return PARIS_B200_OK;
+        }
+        filter_batch io{};
+        for(uint32_t i = 0; i < count; ++i)
+        {
+            io.src[i] = d_src[i];
+            io.dst[i] = transposed ? nullptr : d_dst[i];
+        }
         switch(f->size)
         {
-            case 32: return launch_filter_n<5>(ctx, d_src, d_dst, dim_x, dim_y, f, w, dst_transposed, dst_pitch);
-            case 64: return launch_filter_n<6>(ctx, d_src, d_dst, dim_x, dim_y, f, w, dst_transposed, dst_pitch);
-            case 128: return launch_filter_n<7>(ctx, d_src, d_dst, dim_x, dim_y, f, w, dst_transposed, dst_pitch);
-            case 256: return launch_filter_n<8>(ctx, d_src, d_dst, dim_x, dim_y, f, w, dst_transposed, dst_pitch);
-            case 512: return launch_filter_n<9>(ctx, d_src, d_dst, dim_x, dim_y, f, w, dst_transposed, dst_pitch);
-            case 1024: return launch_filter_n<10>(ctx, d_src, d_dst, dim_x, dim_y, f, w, dst_transposed, dst_pitch);
-            case 2048: return launch_filter_n<11>(ctx, d_src, d_dst, dim_x, dim_y, f, w, dst_transposed, dst_pitch);
-            case 4096: return launch_filter_n<12>(ctx, d_src, d_dst, dim_x, dim_y, f, w, dst_transposed, dst_pitch);
-            case 8192: return launch_filter_n<13>(ctx, d_src, d_dst, dim_x, dim_y, f, w, dst_transposed, dst_pitch);
+            case 256: return launch_grouped<8>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch);
+            case 512: return launch_grouped<9>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch);
+            case 1024: return launch_grouped<10>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch);
+            case 2048: return launch_grouped<11>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch);
+            case 4096: return launch_grouped<12>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch);
+            case 8192: return launch_grouped<13>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch);
             default: break;
         }
         set_error("unsupported filter size %u", f->size);
         return PARIS_B200_EINVAL;
+    }
+
+    int launch_filter(paris_b200_ctx* ctx, const float* d_src, float* d_dst, uint32_t dim_x, uint32_t dim_y,
+                      const paris_b200_filter* f, const weight_params& w, bool dst_transposed, uint32_t dst_pitch)
+    {
+        // single projection; for the transposed case d_dst is the slot itself (a one-slot stack)
+        const float* src[1] = {d_src};
+        float* dst[1] = {d_dst};
+        return launch_filter_batch(ctx, src, dst, 1u, dst_transposed ? d_dst : nullptr, 0u, 0, dim_x, dim_y, f, w,
+                                   dst_transposed, dst_pitch);
     }
 }

@@ -38,7 +38,7 @@ class SlabPlan:
 
 class MultiGpuReconstructor:
     def __init__(self, device: int, det: capi.DetectorGeometry, vol: capi.VolumeGeometry, n_proj: int,
-                 plan: SlabPlan, dist=None, batch: int = 32):
+                 plan: SlabPlan, dist=None, batch: int = 64):
         self.det, self.vol, self.n_proj, self.plan, self.dist = det, vol, n_proj, plan, dist
         self.device = device
         # the C++ layer's per-thread context, so the e2e loop and the stack-level calls share streams
@@ -103,8 +103,8 @@ class MultiGpuReconstructor:
         ctx = self.ctx
         e0 = ctx.event() if timed else None
         ctx.volume_clear(self.d_vol, *self.slab_dims)
-        for i in range(self.my_count):
-            ctx.filter_to_stack(self.d_raw + i * self.px * 4, self.det, self.filter, self.d_stack, self.lo + i)
+        if self.my_count:
+            ctx.filter_to_stack_batch(self.d_raw, self.px, self.my_count, self.det, self.filter, self.d_stack, self.lo)
         e1 = ctx.event() if timed else None
         self._allgather()
         e2 = ctx.event() if timed else None

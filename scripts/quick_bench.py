@@ -42,8 +42,7 @@ d_vol = ctx.volume_alloc(*dims)
 updates = vol.dim_x * vol.dim_y * vol.dim_z * n
 for rep in range(a.reps):
     e0 = ctx.event()
-    for i in range(n):
-        ctx.filter_to_stack(raw + i * a.det * a.det * 4, det, filt, stack, i)
+    ctx.filter_to_stack_batch(raw, a.det * a.det, n, det, filt, stack, 0)
     e1 = ctx.event()
     ctx.backproject_stack(stack, 0, n, sc[:, 0], sc[:, 1], d_vol, dims, 0, det, vol)
     e2 = ctx.event()

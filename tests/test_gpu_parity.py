@@ -100,7 +100,7 @@ def test_backproject_exact_kernel_bit_exact(ctx, port, batch):
     pl.free_volume(v)
     pl.close()
     ctx.set_option("bp_kernel", 0)
-    ctx.set_option("bp_batch", 32)
+    ctx.set_option("bp_batch", 64)
     assert np.array_equal(got, ref)
 
 
