@@ -124,6 +124,10 @@ namespace pb
         g.d_sd = std::fabs(t.det.d_so) + std::fabs(t.det.d_od);     // :177
         g.delta_s = t.delta_s_mm;
         g.delta_t = t.delta_t_mm;
+        g.so_over_sd = g.d_so / g.d_sd;
+        g.min_v_d = -(static_cast<double>(g.p_dim_y) * (static_cast<double>(g.l_px_y) / 2.0)) - static_cast<double>(g.delta_t);
+        g.inv_l_px_y_d = 1.0 / static_cast<double>(g.l_px_y);
+        g.dv_scale_d = static_cast<double>(g.l_vx_z) / static_cast<double>(g.l_px_y);
         return g;
     }
 

@@ -14,6 +14,11 @@ namespace pb
         uint32_t p_dim_x, p_dim_y, pitch;     // n_row, n_col, slot line pitch
         float l_px_x, l_px_y;
         float d_so, d_sd, delta_s, delta_t;   // delta_* in millimetres
+        // derived once on the host for the table builder of the TMA kernel
+        float so_over_sd;                     // d_so / d_sd
+        double min_v_d;                       // -(dim_y * l_px_y / 2) - delta_t
+        double inv_l_px_y_d;                  // 1 / l_px_y
+        double dv_scale_d;                    // l_vx_z / l_px_y
     };
 
     struct bp_angles

@@ -44,7 +44,7 @@ namespace pb
         static constexpr int WARPS = COLS / CPW;          // one warp per group of CPW columns
         static constexpr int THREADS = 32 * WARPS;
         static constexpr int STAGE_BYTES = BH * BV * 4;
-        static constexpr int TAB_BYTES = COLS * (16 + 4);  // float4 + float per column
+        static constexpr int TAB_BYTES = COLS * (16 + 4 + 4);  // float4 + 2 floats per column
         static constexpr size_t SMEM = size_t(STAGES) * STAGE_BYTES + 2 * TAB_BYTES + kMaxBatch * 16 + STAGES * 8 + 128;
         // fixed point: rows are carried with a bias of BV so that they stay non-negative on boundary tiles
         static constexpr int FRAC = 23;
@@ -62,7 +62,7 @@ namespace pb
         int h0, v0;      // detector coordinates of the box's first element
         int all_valid;   // 1: every bilinear cell the tile touches lies inside the detector and the box;
                          // 2: the tile's shadow misses the detector altogether (nothing to add); 0: mixed
-        int pad;
+        int fits;        // the box covers the tile's footprint (guaranteed by the host-side check; else rows are clamped)
     };
 
     // ---- small PTX wrappers -----------------------------------------------------------------------------
@@ -140,16 +140,14 @@ namespace pb
         const float size2 = g.l_px_x / 2.f;
         const float min_h = __fsub_rn(-__fmul_rn(static_cast<float>(g.p_dim_x), size2), g.delta_s);
         c.h = __fsub_rn(__fdiv_rn(__fsub_rn(__fmul_rn(t, c.factor), min_h), g.l_px_x), 0.5f);
-        c.u = __fdiv_rn(g.d_so, denom);
+        c.u = c.factor * g.so_over_sd;   // d_so / (s + d_so); scales the sample only, no decision hangs on it
         return c;
     }
 
     // fractional detector row of slice coordinate z_m (double): (z_m*factor - min_v)/l_px_y - 0.5 (:130-133)
     __device__ __forceinline__ double row_of(double z_m, double factor, const bp_geometry& g)
     {
-        const double min_v = -(static_cast<double>(g.p_dim_y) * (static_cast<double>(g.l_px_y) / 2.0))
-                           - static_cast<double>(g.delta_t);
-        return (z_m * factor - min_v) / static_cast<double>(g.l_px_y) - 0.5;
+        return (z_m * factor - g.min_v_d) * g.inv_l_px_y_d - 0.5;
     }
 
     __device__ __forceinline__ double centered_d(uint32_t coord, uint32_t dim, float size)
@@ -160,33 +158,65 @@ namespace pb
 
     // ---- the kernel ------------------------------------------------------------------------------------------
 
-    template <class CFG, bool CHECKED>
+    // Boundary handling.  The reference adds a sample only if all four bilinear neighbours lie on the detector
+    // (src/openmp/backprojection.cpp:65-71); at rows 0 and dim_y - 1 that is a DISCONTINUITY, so a row that
+    // rounds to the other side of the border would add or drop a whole sample.  Columns whose rows keep at
+    // least one cell of distance from the border for every slice of the tile cannot flip and take the plain
+    // path.  The others ("careful", flagged by the builder in the sign of w*(1-fx)) test validity on the
+    // fixed-point row and, only for voxels within 1/64 of a row of the border, redo the row with exactly the
+    // reference's float operations (:130-133, :45-50, :39-43) to take the reference's side of the decision.
+    struct border_rows
+    {
+        uint32_t b0;      // 9.23 box-relative (biased) position of detector row 0, clamped into range
+        uint32_t span;    // 9.23 distance from row 0 to row dim_y - 1 (clamped)
+    };
+
+    // The reference's own verdict for one voxel: v = (z_m * factor - min_v) / l_px_y - 0.5 with its float
+    // operations, then "row >= 0 and row + 1 < dim_y".  Rarely executed (voxels within 1/64 row of the border).
+    __device__ __noinline__ bool reference_row_valid(uint32_t z_global, float factor, const bp_geometry& g)
+    {
+        const float size2 = g.l_vx_z / 2.f;
+        const float z_m = __fadd_rn(__fadd_rn(-__fmul_rn(static_cast<float>(g.full_z), size2), size2),
+                                    __fmul_rn(static_cast<float>(z_global), g.l_vx_z));
+        const float min_v = __fsub_rn(-__fmul_rn(static_cast<float>(g.p_dim_y), g.l_px_y / 2.f), g.delta_t);
+        const float v = __fsub_rn(__fdiv_rn(__fsub_rn(__fmul_rn(z_m, factor), min_v), g.l_px_y), 0.5f);
+        const float y1 = floorf(v);
+        return y1 >= 0.f && __fadd_rn(y1, 1.f) < static_cast<float>(g.p_dim_y);
+    }
+
+    template <class CFG, bool MIXED>
     __device__ __forceinline__ void consume(float (&acc)[CFG::NZ][CFG::CPW], const float4* __restrict__ tab_a,
-                                            const float* __restrict__ tab_b, int col0, uint32_t lane,
-                                            int row_shift, uint32_t row_span)
+                                            const float* __restrict__ tab_b, const float* __restrict__ tab_c,
+                                            int col0, uint32_t lane, uint32_t z_first, const border_rows& br,
+                                            const bp_geometry& g)
     {
         // kept in registers so the fraction -> float assembly is a single three-input LOP3
         uint32_t frac_mask = (1u << CFG::FRAC) - 1u, one_bits = 0x3f800000u;
         asm volatile("" : "+r"(frac_mask), "+r"(one_bits));
+        constexpr uint32_t kNear = 1u << (CFG::FRAC - 6);
         #pragma unroll
         for(int i = 0; i < CFG::CPW; ++i)
         {
-            // {stage address of (column x1, row -BIAS), v_base (9.23, biased), dv (9.23), w*(1-fx)} and w*fx
+            // {stage address of (column x1, row -BIAS), v_base (9.23, biased), dv (9.23), +-w*(1-fx)}, w*fx
             const float4 ea = tab_a[col0 + i];
             const float wb = tab_b[col0 + i];
             const uint32_t base = __float_as_uint(ea.x);
             const uint32_t dv = __float_as_uint(ea.z);
+            const float wa = fabsf(ea.w);
             uint32_t vfix = dv * lane + __float_as_uint(ea.y);
+            const bool careful = MIXED && (__float_as_uint(ea.w) >> 31) != 0u;   // uniform across the warp
             #pragma unroll
             for(int j = 0; j < CFG::NZ; ++j)
             {
                 uint32_t row = vfix >> CFG::FRAC;                                 // biased row inside the box
                 const float fy = __uint_as_float(and_or(vfix, frac_mask, one_bits)) - 1.0f;
                 bool ok = true;
-                if(CHECKED)
+                if(careful)
                 {
-                    // all four neighbours inside the detector (rows r and r+1), else the term is 0
-                    ok = (row + static_cast<uint32_t>(row_shift)) < row_span;
+                    const uint32_t d0 = vfix - br.b0;
+                    ok = d0 < br.span;                                            // 0 <= row and row + 1 < dim_y
+                    if((d0 + kNear) < 2u * kNear || (d0 - br.span + kNear) < 2u * kNear)
+                        ok = reference_row_valid(z_first + lane + 32u * j, tab_c[col0 + i], g);
                     row = min(max(row, static_cast<uint32_t>(CFG::BIAS)), static_cast<uint32_t>(CFG::BIAS + CFG::BV - 2));
                 }
                 const uint32_t addr = base + 4u * row;
@@ -194,10 +224,10 @@ namespace pb
                 const float q12 = lds_f32(addr + 4);
                 const float q21 = lds_f32(addr + 4 * CFG::BV);
                 const float q22 = lds_f32(addr + 4 * CFG::BV + 4);
-                const float g0 = fmaf(wb, q21, ea.w * q11);
-                const float g1 = fmaf(wb, q22, ea.w * q12);
+                const float g0 = fmaf(wb, q21, wa * q11);
+                const float g1 = fmaf(wb, q22, wa * q12);
                 float d = fmaf(fy, g1 - g0, g0);
-                if(CHECKED)
+                if(MIXED)
                     d = ok ? d : 0.f;
                 acc[j][i] += d;
                 vfix += dv << 5;   // next slice of this lane: 32 rows of dv further
@@ -214,7 +244,8 @@ namespace pb
         unsigned char* stage_mem = smem;                                                   // STAGES x BH x BV floats
         float4* tab_a = reinterpret_cast<float4*>(smem + size_t(CFG::STAGES) * CFG::STAGE_BYTES);
         float* tab_b = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tab_a) + 2 * CFG::COLS * 16);
-        box_origin* origin = reinterpret_cast<box_origin*>(reinterpret_cast<unsigned char*>(tab_b) + 2 * CFG::COLS * 4);
+        float* tab_c = tab_b + 2 * CFG::COLS;
+        box_origin* origin = reinterpret_cast<box_origin*>(reinterpret_cast<unsigned char*>(tab_c) + 2 * CFG::COLS * 4);
         uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(origin) + kMaxBatch * 16);
 
         const int tid = threadIdx.x;
@@ -229,10 +260,6 @@ namespace pb
         const uint32_t x0 = (g.off_x / CFG::TX + blockIdx.x) * CFG::TX;   // global index of the tile's first voxel
         const uint32_t y0 = (g.off_y / CFG::TY + blockIdx.y) * CFG::TY;
         const uint32_t z0 = (g.off_z / CFG::TZ + blockIdx.z) * CFG::TZ;
-        const bool full_tile = x0 >= g.off_x && x0 + CFG::TX <= g.off_x + g.v_dim_x
-                            && y0 >= g.off_y && y0 + CFG::TY <= g.off_y + g.v_dim_y
-                            && z0 >= g.off_z && z0 + CFG::TZ <= g.off_z + g.v_dim_z;
-
         // ---- prologue 1: barriers, box origins for every projection of the batch ---------------------------
         if(tid == 0)
         {
@@ -284,8 +311,8 @@ namespace pb
             // for every column, or the same for the rows (two cells of slack on the safe side)
             const bool outside = hmax < -2.f || hmin > static_cast<float>(g.p_dim_x) + 1.f
                               || vmax < -2.0 || vmin > static_cast<double>(g.p_dim_y) + 1.0;
-            o.all_valid = !finite ? 0 : outside ? 2 : (fits && inside && full_tile) ? 1 : 0;
-            o.pad = 0;
+            o.all_valid = !finite ? 0 : outside ? 2 : (fits && inside) ? 1 : 0;
+            o.fits = (fits && finite) ? 1 : 0;
             origin[tid] = o;
         }
         __syncthreads();
@@ -352,26 +379,37 @@ namespace pb
             // a dead entry reads row 0 of column 0 of the box with zero weights
             float4 ea = make_float4(0.f, __uint_as_float(static_cast<uint32_t>(CFG::BIAS) << CFG::FRAC),
                                     __uint_as_float(0u), 0.f);
-            float eb = 0.f;
+            float eb = 0.f, ec = 0.f;
             int x1rel = 0;
             if(valid_x)
             {
                 const double fd = static_cast<double>(ct.factor);
-                const double dv = static_cast<double>(g.l_vx_z) * fd / static_cast<double>(g.l_px_y);
+                ec = ct.factor;
+                const double dv = fd * g.dv_scale_d;   // l_vx_z * factor / l_px_y
                 // biased, box-relative row of the tile's first slice
                 const double vb = row_of(z_m0, fd, g) - static_cast<double>(o.v0) + static_cast<double>(CFG::BIAS);
                 const double vend = vb + dv * static_cast<double>(CFG::TZ - 1);
-                // representable in 9.23 unsigned for every slice of the tile?  (always true when the host-side
-                // footprint check holds; columns of a far-off tile that fail it cannot touch the detector)
+                const float fx = ct.h - x1;
+                const float w = 0.5f * ct.u * ct.u;
+                x1rel = min(max(static_cast<int>(x1) - o.h0, 0), CFG::BH - 2);
+                ea.w = w * (1.f - fx);
+                eb = w * fx;
+                // representable in 9.23 unsigned for every slice of the tile: always, for a tile that is not
+                // skipped, when the host-side footprint check holds (the box then covers the tile's rows)
                 if(dv >= 0.0 && vb >= 0.0 && vend < static_cast<double>(2 * CFG::BV + 16))
                 {
-                    const float fx = ct.h - x1;
-                    const float w = 0.5f * ct.u * ct.u;
-                    x1rel = min(max(static_cast<int>(x1) - o.h0, 0), CFG::BH - 2);
                     ea.y = __uint_as_float(static_cast<uint32_t>(__double2ll_rn(vb * kOne)));
                     ea.z = __uint_as_float(static_cast<uint32_t>(__double2ll_rn(dv * kOne)));
-                    ea.w = w * (1.f - fx);
-                    eb = w * fx;
+                    // detector rows of the first and last slice; one cell of slack against rounding
+                    const double first = vb + static_cast<double>(o.v0 - CFG::BIAS), last = first + dv * (CFG::TZ - 1);
+                    const bool safe = fmin(first, last) >= 1.0 && fmax(first, last) + 2.0 <= static_cast<double>(g.p_dim_y) - 1.0;
+                    if(!safe || !o.fits)
+                        ea.w = -ea.w;   // "careful" flag
+                }
+                else
+                {
+                    ea.w = 0.f;         // unreachable rows: contributes nothing
+                    eb = 0.f;
                 }
             }
             // address of (column x1, row -BIAS): the biased row index is added as is
@@ -380,6 +418,7 @@ namespace pb
             ea.x = __uint_as_float(base);
             tab_a[(p & 1) * CFG::COLS + tid] = ea;
             tab_b[(p & 1) * CFG::COLS + tid] = eb;
+            tab_c[(p & 1) * CFG::COLS + tid] = ec;
         };
 
         if(builder && count > 0)
@@ -387,6 +426,9 @@ namespace pb
         __syncthreads();
 
         // ---- main loop over the projections of the batch -----------------------------------------------------------
+        border_rows br;
+        br.b0 = 0u;
+        br.span = 0u;
         #pragma unroll 1
         for(int p = 0; p < count; ++p)
         {
@@ -399,11 +441,18 @@ namespace pb
             const box_origin o = origin[p];
             const float4* ta = tab_a + (p & 1) * CFG::COLS;
             const float* tb = tab_b + (p & 1) * CFG::COLS;
+            const float* tc = tab_c + (p & 1) * CFG::COLS;
             if(o.all_valid == 1)
-                consume<CFG, false>(acc, ta, tb, col0, lane, 0, 0u);
+                consume<CFG, false>(acc, ta, tb, tc, col0, lane, z0, br, g);
             else if(o.all_valid == 0)
-                // detector row of biased box row r is r - BIAS + v0; valid iff 0 <= row < dim_y - 1
-                consume<CFG, true>(acc, ta, tb, col0, lane, o.v0 - CFG::BIAS, static_cast<uint32_t>(g.p_dim_y - 1u));
+            {
+                // box-relative (biased) positions of detector rows 0 and dim_y - 1, clamped to what 9.23 can hold
+                const int b0r = max(CFG::BIAS - o.v0, -2);
+                const int b1r = min(CFG::BIAS + static_cast<int>(g.p_dim_y) - 1 - o.v0, 2 * CFG::BV + 20);
+                br.b0 = static_cast<uint32_t>(b0r) << CFG::FRAC;
+                br.span = static_cast<uint32_t>(max(b1r - b0r, 0)) << CFG::FRAC;
+                consume<CFG, true>(acc, ta, tb, tc, col0, lane, z0, br, g);
+            }
 
             __syncthreads(); // stage and table[p&1] are free again; table[(p+1)&1] is complete
             if(tid == 0 && p + CFG::STAGES < count)
