@@ -211,17 +211,27 @@ int paris_b200_flush(paris_b200_ctx* ctx);
 /* ---- stack-level entry points (multi-GPU path: filter 1/N of the projections, all-gather the
  *      stack, backproject all of them into the local slab) ---------------------------------- */
 
-/* Size in bytes of one stack slot (one filtered projection, TRANSPOSED: n_row lines of pitch floats,
- * detector-row index fastest) and its pitch in floats. */
+/* A stack slot holds one filtered projection TRANSPOSED: n_row lines (one per detector column) of `pitch`
+ * floats, detector-row index v fastest.  Two line layouts exist:
+ *   PARIS_B200_LAYOUT_PLAIN   line[v]
+ *   PARIS_B200_LAYOUT_SPLIT2  even rows, then odd rows: line[(v & 1) * pitch/2 + (v >> 1)]
+ * The backprojection kernel prefers SPLIT2 when one voxel step in z spans about two detector rows (volumes of
+ * K^3 voxels from a (2K)^2 detector); paris_b200_choose_stack_layout picks it from the geometry.  Filter and
+ * backprojection calls on the same stack must be given the same layout. */
+#define PARIS_B200_LAYOUT_PLAIN 0u
+#define PARIS_B200_LAYOUT_SPLIT2 1u
+int paris_b200_choose_stack_layout(const paris_b200_detector_geometry* det, const paris_b200_volume_geometry* vol_full,
+                                   uint32_t* layout);
+/* Size in bytes of one stack slot and its pitch in floats. */
 int paris_b200_stack_slot_bytes(uint32_t n_row, uint32_t n_col, size_t* bytes, uint32_t* pitch);
 /* weight + filter a RAW device projection into slot `slot` of an external stack buffer */
 int paris_b200_filter_to_stack(paris_b200_ctx* ctx, const float* d_raw, const paris_b200_detector_geometry* det,
-                               const paris_b200_filter* filter, float* d_stack, uint32_t slot);
+                               const paris_b200_filter* filter, float* d_stack, uint32_t slot, uint32_t layout);
 /* the same for `count` raw projections laid out raw_stride floats apart, into slots first_slot.. ; one
  * launch per 64 projections */
 int paris_b200_filter_to_stack_batch(paris_b200_ctx* ctx, const float* d_raw, size_t raw_stride, uint32_t count,
                                      const paris_b200_detector_geometry* det, const paris_b200_filter* filter,
-                                     float* d_stack, uint32_t first_slot);
+                                     float* d_stack, uint32_t first_slot, uint32_t layout);
 /* backproject slots [first, first+count) of an external stack into d_vol; sin_phi/cos_phi are host
  * arrays of `count` entries (slot first+i uses entry i). */
 int paris_b200_backproject_stack(paris_b200_ctx* ctx, const float* d_stack, uint32_t first, uint32_t count,
@@ -229,7 +239,7 @@ int paris_b200_backproject_stack(paris_b200_ctx* ctx, const float* d_stack, uint
                                  float* d_vol, uint32_t v_dim_x, uint32_t v_dim_y, uint32_t v_dim_z,
                                  uint32_t v_offset, const paris_b200_detector_geometry* det,
                                  const paris_b200_volume_geometry* vol_full, int enable_roi,
-                                 const paris_b200_roi* roi);
+                                 const paris_b200_roi* roi, uint32_t layout);
 
 /* ---- synthetic input (bench / tests): analytic cone-beam line integrals of ellipsoids ------ */
 

@@ -98,10 +98,12 @@ SIGNATURES = {
     "paris_b200_h2d_wait": (C.c_int, [_vp]),
     "paris_b200_flush": (C.c_int, [_vp]),
     "paris_b200_stack_slot_bytes": (C.c_int, [_u32, _u32, _P(C.c_size_t), _P(_u32)]),
-    "paris_b200_filter_to_stack": (C.c_int, [_vp, _fp, _P(DetectorGeometry), _vp, _fp, _u32]),
-    "paris_b200_filter_to_stack_batch": (C.c_int, [_vp, _fp, C.c_size_t, _u32, _P(DetectorGeometry), _vp, _fp, _u32]),
+    "paris_b200_choose_stack_layout": (C.c_int, [_P(DetectorGeometry), _P(VolumeGeometry), _P(_u32)]),
+    "paris_b200_filter_to_stack": (C.c_int, [_vp, _fp, _P(DetectorGeometry), _vp, _fp, _u32, _u32]),
+    "paris_b200_filter_to_stack_batch": (C.c_int, [_vp, _fp, C.c_size_t, _u32, _P(DetectorGeometry), _vp, _fp, _u32,
+                                                   _u32]),
     "paris_b200_backproject_stack": (C.c_int, [_vp, _fp, _u32, _u32, _P(_f), _P(_f), _fp, _u32, _u32, _u32, _u32,
-                                               _P(DetectorGeometry), _P(VolumeGeometry), C.c_int, _P(Roi)]),
+                                               _P(DetectorGeometry), _P(VolumeGeometry), C.c_int, _P(Roi), _u32]),
     "paris_b200_phantom_project": (C.c_int, [_vp, _P(C.c_double), _u32, _P(DetectorGeometry), _u32, _u32, _fp]),
 }
 
@@ -157,6 +159,15 @@ def apply_roi(vol: VolumeGeometry, roi: Roi) -> VolumeGeometry:
     out = VolumeGeometry()
     check(lib().paris_b200_apply_roi(C.byref(vol), C.byref(roi), C.byref(out)))
     return out
+
+
+LAYOUT_PLAIN, LAYOUT_SPLIT2 = 0, 1
+
+
+def choose_stack_layout(det: DetectorGeometry, vol_full: VolumeGeometry) -> int:
+    out = _u32(0)
+    check(lib().paris_b200_choose_stack_layout(C.byref(det), C.byref(vol_full), C.byref(out)))
+    return out.value
 
 
 def stack_slot_bytes(n_row: int, n_col: int):
@@ -324,17 +335,18 @@ class Context:
     def flush(self):
         check(self._L.paris_b200_flush(self.h))
 
-    def filter_to_stack(self, d_raw: int, det: DetectorGeometry, filt: int, d_stack: int, slot: int):
-        check(self._L.paris_b200_filter_to_stack(self.h, d_raw, C.byref(det), filt, d_stack, slot))
+    def filter_to_stack(self, d_raw: int, det: DetectorGeometry, filt: int, d_stack: int, slot: int,
+                        layout: int = LAYOUT_PLAIN):
+        check(self._L.paris_b200_filter_to_stack(self.h, d_raw, C.byref(det), filt, d_stack, slot, layout))
 
     def filter_to_stack_batch(self, d_raw: int, raw_stride: int, count: int, det: DetectorGeometry, filt: int,
-                              d_stack: int, first_slot: int):
+                              d_stack: int, first_slot: int, layout: int = LAYOUT_PLAIN):
         check(self._L.paris_b200_filter_to_stack_batch(self.h, d_raw, raw_stride, count, C.byref(det), filt, d_stack,
-                                                       first_slot))
+                                                       first_slot, layout))
 
     def backproject_stack(self, d_stack: int, first: int, count: int, sin_phi: np.ndarray, cos_phi: np.ndarray,
                           d_vol: int, v_dims, v_offset: int, det: DetectorGeometry, vol_full: VolumeGeometry,
-                          roi: Roi | None = None):
+                          roi: Roi | None = None, layout: int = LAYOUT_PLAIN):
         sn = np.ascontiguousarray(sin_phi, dtype=np.float32)
         cs = np.ascontiguousarray(cos_phi, dtype=np.float32)
         assert sn.size >= count and cs.size >= count
@@ -342,7 +354,7 @@ class Context:
                                                    sn.ctypes.data_as(_P(_f)), cs.ctypes.data_as(_P(_f)),
                                                    d_vol, v_dims[0], v_dims[1], v_dims[2], v_offset,
                                                    C.byref(det), C.byref(vol_full), int(roi is not None),
-                                                   C.byref(roi) if roi is not None else None))
+                                                   C.byref(roi) if roi is not None else None, layout))
 
     def phantom_project(self, ellipsoids_mm: np.ndarray, det: DetectorGeometry, first_idx: int, n_proj: int,
                         d_stack_raw: int):

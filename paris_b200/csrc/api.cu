@@ -691,6 +691,14 @@ static weight_params weighting_from_detector(const paris_b200_detector_geometry*
 
 // ---- deferred backprojection ------------------------------------------------------------------------------
 
+extern "C" int paris_b200_choose_stack_layout(const paris_b200_detector_geometry* det,
+                                              const paris_b200_volume_geometry* vol_full, uint32_t* layout)
+{
+    PB_CHECK_ARG(det != nullptr && vol_full != nullptr && layout != nullptr);
+    *layout = choose_stack_layout(*det, *vol_full);
+    return PARIS_B200_OK;
+}
+
 extern "C" int paris_b200_stack_slot_bytes(uint32_t n_row, uint32_t n_col, size_t* bytes, uint32_t* pitch)
 {
     PB_CHECK_ARG(n_row > 0 && n_col > 0);
@@ -709,8 +717,9 @@ static bool same_target(const bp_target& a, const bp_target& b)
         && a.delta_t_mm == b.delta_t_mm;
 }
 
-static int ensure_stack(paris_b200_ctx* ctx, uint32_t n_row, uint32_t n_col)
+static int ensure_stack(paris_b200_ctx* ctx, uint32_t n_row, uint32_t n_col, uint32_t layout)
 {
+    ctx->stack_layout = layout; // (callers flush before changing the layout of a non-empty batch)
     const uint32_t pitch = stack_pitch_for(n_col);
     const uint32_t slots = static_cast<uint32_t>(ctx->bp_batch);
     if(ctx->stack != nullptr && ctx->stack_n_row == n_row && ctx->stack_n_col == n_col && ctx->stack_slots >= slots)
@@ -743,7 +752,7 @@ static int run_pending_filter(paris_b200_ctx* ctx)
     const int rc = launch_filter_batch(ctx, ctx->pend_raw, nullptr, static_cast<uint32_t>(n), ctx->stack,
                                        static_cast<uint32_t>(ctx->pend_raw_first), ctx->stack_slot_floats,
                                        ctx->stack_n_row, ctx->stack_n_col, ctx->pend_filter, ctx->pend_w, true,
-                                       ctx->stack_pitch);
+                                       ctx->stack_pitch, ctx->stack_layout);
     for(auto& b : ctx->pool)
     {
         if(!b.held)
@@ -772,7 +781,7 @@ extern "C" int paris_b200_flush(paris_b200_ctx* ctx)
     const int n = ctx->pending;
     ctx->pending = 0;
     return launch_backproject(ctx, ctx->stack, ctx->stack_slot_floats, ctx->stack_pitch, 0u, static_cast<uint32_t>(n),
-                              ctx->pend_sin, ctx->pend_cos, ctx->target);
+                              ctx->pend_sin, ctx->pend_cos, ctx->target, ctx->stack_layout);
 }
 
 // a buffer a deferred launch still has to read must not be touched before that launch is enqueued
@@ -816,7 +825,8 @@ extern "C" int paris_b200_backproject(paris_b200_ctx* ctx, const float* d_proj, 
 
     if(ctx->pending > 0 && !same_target(ctx->target, t))
         PB_TRY(paris_b200_flush(ctx));
-    PB_TRY(ensure_stack(ctx, dim_x, dim_y));
+    // (the layout is a function of the target geometry, so it is constant within a batch)
+    PB_TRY(ensure_stack(ctx, dim_x, dim_y, choose_stack_layout(*det, *vol_full)));
     ctx->target = t;
 
     float* slot = ctx->stack + ctx->stack_slot_floats * static_cast<size_t>(ctx->pending);
@@ -852,12 +862,12 @@ extern "C" int paris_b200_backproject(paris_b200_ctx* ctx, const float* d_proj, 
             buf->held = true;
         }
         else
-            PB_TRY(launch_filter(ctx, d_proj, slot, dim_x, dim_y, filter, w, true, ctx->stack_pitch));
+            PB_TRY(launch_filter(ctx, d_proj, slot, dim_x, dim_y, filter, w, true, ctx->stack_pitch, ctx->stack_layout));
     }
     else
     {
         PB_TRY(flush_if_held(ctx, d_proj));
-        PB_TRY(launch_transpose_to_slot(ctx, d_proj, slot, dim_x, dim_y, ctx->stack_pitch));
+        PB_TRY(launch_transpose_to_slot(ctx, d_proj, slot, dim_x, dim_y, ctx->stack_pitch, ctx->stack_layout));
     }
 
     ctx->pend_sin[ctx->pending] = sin_phi;
@@ -872,8 +882,10 @@ extern "C" int paris_b200_backproject(paris_b200_ctx* ctx, const float* d_proj, 
 
 extern "C" int paris_b200_filter_to_stack_batch(paris_b200_ctx* ctx, const float* d_raw, size_t raw_stride,
                                                 uint32_t count, const paris_b200_detector_geometry* det,
-                                                const paris_b200_filter* filter, float* d_stack, uint32_t first_slot)
+                                                const paris_b200_filter* filter, float* d_stack, uint32_t first_slot,
+                                                uint32_t layout)
 {
+    PB_CHECK_ARG(layout == kLayoutPlain || layout == kLayoutSplit2);
     PB_CHECK_ARG(ctx != nullptr && d_raw != nullptr && det != nullptr && filter != nullptr && d_stack != nullptr);
     PB_CHECK_ARG(det->n_row <= filter->size);
     PB_CHECK_ARG(count <= 1u || raw_stride >= static_cast<size_t>(det->n_row) * det->n_col);
@@ -888,7 +900,7 @@ extern "C" int paris_b200_filter_to_stack_batch(paris_b200_ctx* ctx, const float
         for(uint32_t i = 0; i < n; ++i)
             src[i] = d_raw + raw_stride * (done + i);
         PB_TRY(launch_filter_batch(ctx, src, nullptr, n, d_stack, first_slot + done, slot_floats, det->n_row, det->n_col,
-                                   filter, w, true, pitch));
+                                   filter, w, true, pitch, layout));
         done += n;
     }
     return PARIS_B200_OK;
@@ -896,11 +908,11 @@ extern "C" int paris_b200_filter_to_stack_batch(paris_b200_ctx* ctx, const float
 
 extern "C" int paris_b200_filter_to_stack(paris_b200_ctx* ctx, const float* d_raw,
                                           const paris_b200_detector_geometry* det, const paris_b200_filter* filter,
-                                          float* d_stack, uint32_t slot)
+                                          float* d_stack, uint32_t slot, uint32_t layout)
 {
     PB_CHECK_ARG(ctx != nullptr);
     PB_TRY(flush_if_held(ctx, d_raw));
-    return paris_b200_filter_to_stack_batch(ctx, d_raw, 0, 1u, det, filter, d_stack, slot);
+    return paris_b200_filter_to_stack_batch(ctx, d_raw, 0, 1u, det, filter, d_stack, slot, layout);
 }
 
 extern "C" int paris_b200_backproject_stack(paris_b200_ctx* ctx, const float* d_stack, uint32_t first, uint32_t count,
@@ -908,9 +920,10 @@ extern "C" int paris_b200_backproject_stack(paris_b200_ctx* ctx, const float* d_
                                             uint32_t v_dim_x, uint32_t v_dim_y, uint32_t v_dim_z, uint32_t v_offset,
                                             const paris_b200_detector_geometry* det,
                                             const paris_b200_volume_geometry* vol_full, int enable_roi,
-                                            const paris_b200_roi* roi)
+                                            const paris_b200_roi* roi, uint32_t layout)
 {
     PB_CHECK_ARG(ctx != nullptr && d_stack != nullptr && d_vol != nullptr && det != nullptr && vol_full != nullptr);
+    PB_CHECK_ARG(layout == kLayoutPlain || layout == kLayoutSplit2);
     PB_CHECK_ARG(sin_phi != nullptr && cos_phi != nullptr);
     PB_CHECK_ARG(!enable_roi || roi != nullptr);
     PB_TRY(bind(ctx));
@@ -934,7 +947,8 @@ extern "C" int paris_b200_backproject_stack(paris_b200_ctx* ctx, const float* d_
     for(uint32_t done = 0; done < count;)
     {
         const uint32_t n = std::min<uint32_t>(count - done, static_cast<uint32_t>(ctx->bp_batch));
-        PB_TRY(launch_backproject(ctx, d_stack, slot_floats, pitch, first + done, n, sin_phi + done, cos_phi + done, t));
+        PB_TRY(launch_backproject(ctx, d_stack, slot_floats, pitch, first + done, n, sin_phi + done, cos_phi + done, t,
+                                  layout));
         done += n;
     }
     return PARIS_B200_OK;

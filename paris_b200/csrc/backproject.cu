@@ -39,8 +39,8 @@ namespace pb
     }
 
     // src/openmp/backprojection.cpp:52-84, on a transposed slot: p[x + y*dim_x] lives at slot[x*pitch + y]
-    __device__ __forceinline__ float interpolate_exact(const float* __restrict__ slot, uint32_t pitch, float x, float y,
-                                                       uint32_t dim_x, uint32_t dim_y)
+    __device__ __forceinline__ float interpolate_exact(const float* __restrict__ slot, uint32_t pitch, uint32_t layout,
+                                                       float x, float y, uint32_t dim_x, uint32_t dim_y)
     {
         const float x1 = floorf(x);
         const float x2 = __fadd_rn(x1, 1.f);
@@ -50,11 +50,12 @@ namespace pb
         if(x1 >= 0.f && x2 < static_cast<float>(dim_x) && y1 >= 0.f && y2 < static_cast<float>(dim_y))
         {
             const uint32_t x1u = static_cast<uint32_t>(x1), y1u = static_cast<uint32_t>(y1);
-            const float* c0 = slot + static_cast<size_t>(x1u) * pitch + y1u;
-            const float q11 = __ldg(c0);
-            const float q12 = __ldg(c0 + 1);
-            const float q21 = __ldg(c0 + pitch);
-            const float q22 = __ldg(c0 + pitch + 1);
+            const float* c0 = slot + static_cast<size_t>(x1u) * pitch;
+            const uint32_t o1 = line_offset(y1u, pitch, layout), o2 = line_offset(y1u + 1u, pitch, layout);
+            const float q11 = __ldg(c0 + o1);
+            const float q12 = __ldg(c0 + o2);
+            const float q21 = __ldg(c0 + pitch + o1);
+            const float q22 = __ldg(c0 + pitch + o2);
             const float dx = __fsub_rn(x2, x1), dy = __fsub_rn(y2, y1);
             const float wx1 = __fdiv_rn(__fsub_rn(x2, x), dx), wx2 = __fdiv_rn(__fsub_rn(x, x1), dx);
             const float interp_y1 = __fadd_rn(__fmul_rn(wx1, q11), __fmul_rn(wx2, q21));
@@ -92,7 +93,7 @@ namespace pb
             const float factor = __fdiv_rn(g.d_sd, denom);
             const float h = proj_real_coordinate(__fmul_rn(t, factor), g.p_dim_x, g.l_px_x, g.delta_s);
             const float v = proj_real_coordinate(__fmul_rn(z_m, factor), g.p_dim_y, g.l_px_y, g.delta_t);
-            const float det = interpolate_exact(stack + slot_floats * p, g.pitch, h, v, g.p_dim_x, g.p_dim_y);
+            const float det = interpolate_exact(stack + slot_floats * p, g.pitch, g.layout, h, v, g.p_dim_x, g.p_dim_y);
             const float u = -__fdiv_rn(g.d_so, denom);
             // 0.5f * det * u * u, left to right
             acc = __fadd_rn(acc, __fmul_rn(__fmul_rn(__fmul_rn(0.5f, det), u), u));
@@ -100,9 +101,10 @@ namespace pb
         vol[coord] = acc;
     }
 
-    bp_geometry make_bp_geometry(const bp_target& t, uint32_t pitch)
+    bp_geometry make_bp_geometry(const bp_target& t, uint32_t pitch, uint32_t layout)
     {
         bp_geometry g{};
+        g.layout = layout;
         g.v_dim_x = t.v_dim_x;
         g.v_dim_y = t.v_dim_y;
         g.v_dim_z = t.v_dim_z;
@@ -131,6 +133,16 @@ namespace pb
         return g;
     }
 
+    uint32_t choose_stack_layout(const paris_b200_detector_geometry& det, const paris_b200_volume_geometry& vol_full)
+    {
+        // detector rows per voxel step in z on the rotation axis: l_vx_z * (d_sd / d_so) / l_px_col
+        const double d_so = det.d_so, d_sd = std::fabs(det.d_so) + std::fabs(det.d_od);
+        if(!(d_so > 0.0) || det.n_row <= 64u)
+            return kLayoutPlain;
+        const double dv = static_cast<double>(vol_full.l_vx_z) * (d_sd / d_so) / static_cast<double>(det.l_px_col);
+        return (dv >= 1.45 && dv <= 2.75) ? kLayoutSplit2 : kLayoutPlain;
+    }
+
     static int launch_exact(paris_b200_ctx* ctx, const float* d_first_slot, size_t slot_floats, const bp_geometry& g,
                             const bp_angles& a, float* d_vol)
     {
@@ -148,7 +160,8 @@ namespace pb
     }
 
     int launch_backproject(paris_b200_ctx* ctx, const float* d_stack, size_t slot_floats, uint32_t pitch,
-                           uint32_t first, uint32_t count, const float* sn, const float* cs, const bp_target& t)
+                           uint32_t first, uint32_t count, const float* sn, const float* cs, const bp_target& t,
+                           uint32_t layout)
     {
         if(count == 0)
             return PARIS_B200_OK;
@@ -157,7 +170,7 @@ namespace pb
             set_error("batch of %u exceeds %d", count, kMaxBatch);
             return PARIS_B200_EINVAL;
         }
-        const bp_geometry g = make_bp_geometry(t, pitch);
+        const bp_geometry g = make_bp_geometry(t, pitch, layout);
         bp_angles a{};
         a.count = static_cast<int>(count);
         for(uint32_t i = 0; i < count; ++i)

@@ -12,6 +12,7 @@ namespace pb
         uint32_t off_x, off_y, off_z;         // ROI origin (+ slab offset on z)
         float l_vx_x, l_vx_y, l_vx_z;
         uint32_t p_dim_x, p_dim_y, pitch;     // n_row, n_col, slot line pitch
+        uint32_t layout;                      // kLayoutPlain / kLayoutSplit2
         float l_px_x, l_px_y;
         float d_so, d_sd, delta_s, delta_t;   // delta_* in millimetres
         // derived once on the host for the table builder of the TMA kernel
@@ -28,7 +29,7 @@ namespace pb
         float cs[kMaxBatch];
     };
 
-    bp_geometry make_bp_geometry(const bp_target& t, uint32_t pitch);
+    bp_geometry make_bp_geometry(const bp_target& t, uint32_t pitch, uint32_t layout);
 
     // *handled = false when the geometry does not fit the kernel's tiles (caller falls back to the exact
     // kernel) unless `required`, in which case that is an error.

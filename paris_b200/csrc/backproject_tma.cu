@@ -35,9 +35,12 @@
 namespace pb
 {
     // ---- tile configuration ---------------------------------------------------------------------------
-    template <int TX_, int TY_, int NZ_, int CPW_, int BH_, int BV_, int STAGES_>
+    template <int TX_, int TY_, int NZ_, int CPW_, int BH_, int BV_, int STAGES_, bool SPLIT_ = false>
     struct tile_cfg
     {
+        // SPLIT: the stack (and the staged box) keeps even detector rows and odd detector rows in two planes
+        static constexpr bool SPLIT = SPLIT_;
+        static constexpr int BVH = BV_ / 2;                 // rows per parity plane of a staged column
         static constexpr int TX = TX_, TY = TY_, NZ = NZ_, CPW = CPW_, BH = BH_, BV = BV_, STAGES = STAGES_;
         static constexpr int TZ = 32 * NZ;                // slices per tile; lane l owns l, l+32, ...
         static constexpr int COLS = TX * TY;
@@ -55,6 +58,7 @@ namespace pb
         static_assert(BH <= 256 && BV <= 256, "TMA box extents are limited to 256");
         static_assert(2 * BV + 32 < (1 << (32 - FRAC)), "biased rows must fit the 9 integer bits");
         static_assert(STAGE_BYTES % 128 == 0, "stages must keep the 128-byte TMA destination alignment");
+        static_assert(!SPLIT || (BV % 8 == 0 && BIAS % 2 == 0), "parity planes: even bias, 16-byte plane rows");
     };
 
     struct box_origin
@@ -104,6 +108,24 @@ namespace pb
         uint32_t d;
         asm("lop3.b32 %0, %1, %2, %3, 0xEA;" : "=r"(d) : "r"(a), "r"(b), "r"(c));
         return d;
+    }
+
+    __device__ __forceinline__ void tma_load_4d(uint32_t dst, const CUtensorMap* map, uint32_t bar, int c0, int c1, int c2,
+                                                int c3)
+    {
+        asm volatile(
+            "cp.async.bulk.tensor.4d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4, %5, %6}], [%2];"
+            ::"r"(dst), "l"(map), "r"(bar), "r"(c0), "r"(c1), "r"(c2), "r"(c3) : "memory");
+    }
+
+    // one staged box: rows v0.. of columns h0.. of slot `slot` (v0 a multiple of 4, of 8 for the split layout)
+    template <class CFG>
+    __device__ __forceinline__ void load_box(uint32_t dst, const CUtensorMap* map, uint32_t bar, int v0, int h0, int slot)
+    {
+        if(CFG::SPLIT)
+            tma_load_4d(dst, map, bar, v0 >> 1, 0, h0, slot);   // {row pair, parity, column, slot}
+        else
+            tma_load_3d(dst, map, bar, v0, h0, slot);
     }
 
     __device__ __forceinline__ float lds_f32(uint32_t addr)
@@ -208,25 +230,55 @@ namespace pb
             #pragma unroll
             for(int j = 0; j < CFG::NZ; ++j)
             {
-                uint32_t row = vfix >> CFG::FRAC;                                 // biased row inside the box
-                const float fy = __uint_as_float(and_or(vfix, frac_mask, one_bits)) - 1.0f;
                 bool ok = true;
+                uint32_t vrow = vfix;   // the 9.23 row used for addressing and weights
                 if(careful)
                 {
                     const uint32_t d0 = vfix - br.b0;
                     ok = d0 < br.span;                                            // 0 <= row and row + 1 < dim_y
                     if((d0 + kNear) < 2u * kNear || (d0 - br.span + kNear) < 2u * kNear)
                         ok = reference_row_valid(z_first + lane + 32u * j, tab_c[col0 + i], g);
-                    row = min(max(row, static_cast<uint32_t>(CFG::BIAS)), static_cast<uint32_t>(CFG::BIAS + CFG::BV - 2));
+                    // keep the address inside the box whatever happens (only matters if the host-side footprint
+                    // check were wrong); the value is discarded when ok is false
+                    const uint32_t lo = static_cast<uint32_t>(CFG::BIAS) << CFG::FRAC;
+                    const uint32_t hi = static_cast<uint32_t>(CFG::BIAS + CFG::BV - 2) << CFG::FRAC;
+                    vrow = min(max(vrow, lo), hi);
                 }
-                const uint32_t addr = base + 4u * row;
-                const float q11 = lds_f32(addr);
-                const float q12 = lds_f32(addr + 4);
-                const float q21 = lds_f32(addr + 4 * CFG::BV);
-                const float q22 = lds_f32(addr + 4 * CFG::BV + 4);
-                const float g0 = fmaf(wb, q21, wa * q11);
-                const float g1 = fmaf(wb, q22, wa * q12);
-                float d = fmaf(fy, g1 - g0, g0);
+                float d;
+                if(!CFG::SPLIT)
+                {
+                    const uint32_t row = vrow >> CFG::FRAC;                       // biased row inside the box
+                    const float fy = __uint_as_float(and_or(vrow, frac_mask, one_bits)) - 1.0f;
+                    const uint32_t addr = base + 4u * row;
+                    const float q11 = lds_f32(addr);
+                    const float q12 = lds_f32(addr + 4);
+                    const float q21 = lds_f32(addr + 4 * CFG::BV);
+                    const float q22 = lds_f32(addr + 4 * CFG::BV + 4);
+                    const float g0 = fmaf(wb, q21, wa * q11);
+                    const float g1 = fmaf(wb, q22, wa * q12);
+                    d = fmaf(fy, g1 - g0, g0);
+                }
+                else
+                {
+                    // Rows r and r+1 are one even and one odd row.  With r = 2k + p (p = parity):
+                    //   odd  row sits in the odd plane at pair index k,
+                    //   even row sits in the even plane at pair index k + p,
+                    // and the odd row's weight is fy for p = 0 (it is row r+1), 1 - fy for p = 1 (it is row r).
+                    // Across a warp both planes are read with (nearly) unit stride.
+                    const uint32_t pair4 = (vrow >> (CFG::FRAC - 1)) & ~3u;       // 4 * k
+                    const uint32_t par4 = (vrow >> (CFG::FRAC - 2)) & 4u;         // 4 * p
+                    const uint32_t a_odd = base + pair4;                          // base points at the odd plane
+                    const uint32_t a_even = a_odd + par4;
+                    const float f1 = __uint_as_float(and_or(vrow, frac_mask, one_bits));   // 1 + fy
+                    const float w_odd = par4 ? 2.0f - f1 : f1 - 1.0f;
+                    const float e1 = lds_f32(a_even - 4 * CFG::BVH);
+                    const float e2 = lds_f32(a_even - 4 * CFG::BVH + 4 * CFG::BV);
+                    const float o1 = lds_f32(a_odd);
+                    const float o2 = lds_f32(a_odd + 4 * CFG::BV);
+                    const float ge = fmaf(wb, e2, wa * e1);
+                    const float go = fmaf(wb, o2, wa * o1);
+                    d = fmaf(w_odd, go - ge, ge);
+                }
                 if(MIXED)
                     d = ok ? d : 0.f;
                 acc[j][i] += d;
@@ -302,7 +354,8 @@ namespace pb
             o.h0 = hlo - 1;
             // the TMA unit wants the innermost start coordinate on a 16-byte boundary (measured on B200:
             // anything else raises an illegal-instruction fault), so round down to a multiple of 4 floats
-            o.v0 = ((vlo - 1) >> 2) << 2;
+            // (a multiple of 8 rows = 4 row pairs for the split layout)
+            o.v0 = CFG::SPLIT ? ((vlo - 1) >> 3) << 3 : ((vlo - 1) >> 2) << 2;
             // cells used: columns hlo-1 .. hhi+2, rows vlo-1 .. vhi+2 (one cell of slack for float rounding)
             const bool fits = (hhi + 2 - o.h0) < CFG::BH && (vhi + 2 - o.v0) < CFG::BV;
             const bool inside = hlo - 1 >= 0 && hhi + 2 <= static_cast<int>(g.p_dim_x) - 1
@@ -351,8 +404,8 @@ namespace pb
             {
                 const uint32_t bar = smem_u32(&bars[p]);
                 mbar_expect_tx(bar, CFG::STAGE_BYTES);
-                tma_load_3d(smem_u32(stage_mem + size_t(p) * CFG::STAGE_BYTES), &tmap, bar, origin[p].v0, origin[p].h0,
-                            static_cast<int>(first_slot) + p);
+                load_box<CFG>(smem_u32(stage_mem + size_t(p) * CFG::STAGE_BYTES), &tmap, bar, origin[p].v0, origin[p].h0,
+                              static_cast<int>(first_slot) + p);
             }
         }
 
@@ -412,9 +465,12 @@ namespace pb
                     eb = 0.f;
                 }
             }
-            // address of (column x1, row -BIAS): the biased row index is added as is
+            // plain: address of (column x1, row -BIAS), the biased row index is added as is;
+            // split: address of (column x1, odd plane, pair index -BIAS/2), 4 * (biased row >> 1) is added
             const uint32_t base = stage_base0 + static_cast<uint32_t>(p % CFG::STAGES) * CFG::STAGE_BYTES
-                                + 4u * static_cast<uint32_t>(x1rel * CFG::BV) - 4u * static_cast<uint32_t>(CFG::BIAS);
+                                + 4u * static_cast<uint32_t>(x1rel * CFG::BV)
+                                + (CFG::SPLIT ? 4u * static_cast<uint32_t>(CFG::BVH) - 2u * static_cast<uint32_t>(CFG::BIAS)
+                                              : 0u - 4u * static_cast<uint32_t>(CFG::BIAS));
             ea.x = __uint_as_float(base);
             tab_a[(p & 1) * CFG::COLS + tid] = ea;
             tab_b[(p & 1) * CFG::COLS + tid] = eb;
@@ -460,8 +516,8 @@ namespace pb
                 const int q = p + CFG::STAGES;
                 const uint32_t bar = smem_u32(&bars[stage]);
                 mbar_expect_tx(bar, CFG::STAGE_BYTES);
-                tma_load_3d(smem_u32(stage_mem + size_t(stage) * CFG::STAGE_BYTES), &tmap, bar, origin[q].v0,
-                            origin[q].h0, static_cast<int>(first_slot) + q);
+                load_box<CFG>(smem_u32(stage_mem + size_t(stage) * CFG::STAGE_BYTES), &tmap, bar, origin[q].v0,
+                              origin[q].h0, static_cast<int>(first_slot) + q);
             }
         }
 
@@ -501,11 +557,12 @@ namespace pb
     }
 
     static int make_tensor_map(paris_b200_ctx* ctx, const float* d_stack, uint32_t n_row, uint32_t pitch, uint32_t slots,
-                               size_t slot_floats, uint32_t box_v, uint32_t box_h)
+                               size_t slot_floats, uint32_t box_v, uint32_t box_h, bool split)
     {
         auto& c = ctx->tma;
+        const uint32_t layout = split ? kLayoutSplit2 : kLayoutPlain;
         if(c.valid && c.base == d_stack && c.n_row == n_row && c.pitch == pitch && c.slots == slots && c.box_v == box_v
-           && c.box_h == box_h)
+           && c.box_h == box_h && c.layout == layout)
             return PARIS_B200_OK;
         auto encode = get_encode();
         if(encode == nullptr)
@@ -513,13 +570,30 @@ namespace pb
             set_error("cuTensorMapEncodeTiled is not available from the driver");
             return PARIS_B200_ECUDA;
         }
-        const cuuint64_t dims[3] = {pitch, n_row, slots};
-        const cuuint64_t strides[2] = {static_cast<cuuint64_t>(pitch) * 4u, static_cast<cuuint64_t>(slot_floats) * 4u};
-        const cuuint32_t box[3] = {box_v, box_h, 1u};
-        const cuuint32_t elem[3] = {1u, 1u, 1u};
-        const CUresult r = encode(&c.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(d_stack), dims, strides,
-                                  box, elem, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE,
-                                  CU_TENSOR_MAP_L2_PROMOTION_L2_128B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        CUresult r;
+        if(!split)
+        {
+            // {detector row, detector column, slot}
+            const cuuint64_t dims[3] = {pitch, n_row, slots};
+            const cuuint64_t strides[2] = {static_cast<cuuint64_t>(pitch) * 4u, static_cast<cuuint64_t>(slot_floats) * 4u};
+            const cuuint32_t box[3] = {box_v, box_h, 1u};
+            const cuuint32_t elem[3] = {1u, 1u, 1u};
+            r = encode(&c.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 3, const_cast<float*>(d_stack), dims, strides, box, elem,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
+        else
+        {
+            // {row pair, parity plane, detector column, slot}: the box lands as [column][parity][row pair]
+            const cuuint64_t dims[4] = {pitch / 2u, 2u, n_row, slots};
+            const cuuint64_t strides[3] = {static_cast<cuuint64_t>(pitch / 2u) * 4u, static_cast<cuuint64_t>(pitch) * 4u,
+                                           static_cast<cuuint64_t>(slot_floats) * 4u};
+            const cuuint32_t box[4] = {box_v / 2u, 2u, box_h, 1u};
+            const cuuint32_t elem[4] = {1u, 1u, 1u, 1u};
+            r = encode(&c.map, CU_TENSOR_MAP_DATA_TYPE_FLOAT32, 4, const_cast<float*>(d_stack), dims, strides, box, elem,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_NONE, CU_TENSOR_MAP_L2_PROMOTION_L2_128B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        }
         if(r != CUDA_SUCCESS)
         {
             set_error("cuTensorMapEncodeTiled failed with CUresult %d", static_cast<int>(r));
@@ -531,6 +605,7 @@ namespace pb
         c.slots = slots;
         c.box_v = box_v;
         c.box_h = box_h;
+        c.layout = layout;
         c.valid = true;
         return PARIS_B200_OK;
     }
@@ -568,7 +643,7 @@ namespace pb
         const double span_v = ((tz - 1) * static_cast<double>(g.l_vx_z) * fmax + rz * dfac) / g.l_px_y;
         // kernel needs (floor(max) + 2) - (floor(min) - 1) < B  <=  span + 1 + 3 < B
         f.need_h = static_cast<int>(std::ceil(span_h)) + 5;
-        f.need_v = static_cast<int>(std::ceil(span_v)) + 5 + 3; // + alignment of the box start to 4 floats
+        f.need_v = static_cast<int>(std::ceil(span_v)) + 5; // + 3 (plain) or 7 (split) for the box start alignment
         f.ok = true;
         return f;
     }
@@ -579,7 +654,7 @@ namespace pb
     {
         // the tensor map spans the slots this launch can touch: [0, first + count)
         const uint32_t slots = first + static_cast<uint32_t>(a.count);
-        PB_TRY(make_tensor_map(ctx, d_stack, g.p_dim_x, g.pitch, slots, slot_floats, CFG::BV, CFG::BH));
+        PB_TRY(make_tensor_map(ctx, d_stack, g.p_dim_x, g.pitch, slots, slot_floats, CFG::BV, CFG::BH, CFG::SPLIT));
         auto kern = bp_tma_kernel<CFG>;
         PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(CFG::SMEM)));
         // tiles anchored at global multiples of the tile size: first tile holds off, last holds off + dim - 1
@@ -597,25 +672,41 @@ namespace pb
         return PARIS_B200_OK;
     }
 
-    //                      TX  TY  NZ CPW  BH   BV  STAGES
-    using cfg_fine   = tile_cfg<16, 16, 2, 16, 40, 96, 6>;    // ~1 detector pixel per voxel (PARIS-derived volumes)
-    using cfg_coarse = tile_cfg<16, 16, 2, 16, 64, 164, 4>;   // ~2 detector pixels per voxel (K^3 from a (2K)^2 detector)
+    //                            TX  TY  NZ CPW  BH   BV  STAGES SPLIT
+    using cfg_fine         = tile_cfg<16, 16, 2, 16, 40, 96, 6>;          // ~1 detector row per voxel (PARIS-derived volumes)
+    using cfg_coarse       = tile_cfg<16, 16, 2, 16, 64, 164, 4>;         // ~2 rows per voxel, plain stack layout
+    using cfg_coarse_split = tile_cfg<16, 16, 2, 16, 64, 168, 4, true>;   // ~2 rows per voxel, parity-split stack layout
+
+    template <class CFG>
+    static bool fits_cfg(const footprint& f)
+    {
+        return f.need_h <= CFG::BH && f.need_v + (CFG::SPLIT ? 7 : 3) <= CFG::BV;
+    }
 
     int launch_bp_tma(paris_b200_ctx* ctx, const float* d_stack, size_t slot_floats, uint32_t first,
                       const bp_geometry& g, const bp_angles& a, float* d_vol, bool required, bool* handled)
     {
         *handled = false;
         const footprint f = tile_footprint(g, 16, 16, 64);
-        const bool aligned = (reinterpret_cast<uintptr_t>(d_stack) % 16u) == 0u && (g.pitch % 4u) == 0u;
+        const bool aligned = (reinterpret_cast<uintptr_t>(d_stack) % 16u) == 0u && (g.pitch % 8u) == 0u;
         if(f.ok && aligned)
         {
-            if(f.need_h <= cfg_fine::BH && f.need_v <= cfg_fine::BV)
+            if(g.layout == kLayoutSplit2)
+            {
+                if(fits_cfg<cfg_coarse_split>(f))
+                {
+                    PB_TRY(launch_cfg<cfg_coarse_split>(ctx, d_stack, slot_floats, first, g, a, d_vol));
+                    *handled = true;
+                    return PARIS_B200_OK;
+                }
+            }
+            else if(fits_cfg<cfg_fine>(f))
             {
                 PB_TRY(launch_cfg<cfg_fine>(ctx, d_stack, slot_floats, first, g, a, d_vol));
                 *handled = true;
                 return PARIS_B200_OK;
             }
-            if(f.need_h <= cfg_coarse::BH && f.need_v <= cfg_coarse::BV)
+            else if(fits_cfg<cfg_coarse>(f))
             {
                 PB_TRY(launch_cfg<cfg_coarse>(ctx, d_stack, slot_floats, first, g, a, d_vol));
                 *handled = true;
@@ -624,8 +715,8 @@ namespace pb
         }
         if(required)
         {
-            set_error("geometry does not fit the TMA kernel's tiles (footprint %d x %d detector cells per tile)",
-                      f.need_h, f.need_v);
+            set_error("geometry does not fit the TMA kernel's tiles (footprint %d x %d detector cells per tile, layout %u)",
+                      f.need_h, f.need_v, g.layout);
             return PARIS_B200_ESTATE;
         }
         return PARIS_B200_OK;

@@ -17,6 +17,18 @@ namespace pb
 {
     void set_error(const char* fmt, ...);
 
+    // Layout of one line (fixed detector column, all detector rows v) of a filtered-stack slot:
+    //   plain   line[v]
+    //   split2  even rows first, then odd rows: line[(v & 1) * pitch/2 + (v >> 1)].  Used when a voxel step
+    //           in z moves ~2 detector rows: the 32 lanes of a backprojection warp then read each parity
+    //           plane with unit stride instead of hitting every other shared-memory bank twice.
+    enum : uint32_t { kLayoutPlain = 0u, kLayoutSplit2 = 1u };
+
+    __host__ __device__ inline uint32_t line_offset(uint32_t v, uint32_t pitch, uint32_t layout)
+    {
+        return layout == kLayoutSplit2 ? (v & 1u) * (pitch >> 1) + (v >> 1) : v;
+    }
+
     // Maximum projections accumulated by one backprojection launch (sin/cos travel as kernel parameters).
     constexpr int kMaxBatch = 64;
 
@@ -53,7 +65,7 @@ namespace pb
     struct tma_desc_cache
     {
         const float* base = nullptr;
-        uint32_t n_row = 0, pitch = 0, slots = 0, box_v = 0, box_h = 0;
+        uint32_t n_row = 0, pitch = 0, slots = 0, box_v = 0, box_h = 0, layout = 0;
         CUtensorMap map{};
         bool valid = false;
     };
@@ -93,7 +105,7 @@ struct paris_b200_ctx
 
     // filtered stack owned by the context (deferred backprojection)
     float* stack = nullptr;
-    uint32_t stack_n_row = 0, stack_n_col = 0, stack_pitch = 0, stack_slots = 0;
+    uint32_t stack_n_row = 0, stack_n_col = 0, stack_pitch = 0, stack_slots = 0, stack_layout = 0;
     size_t stack_slot_floats = 0;
 
     // pending batch
@@ -149,22 +161,29 @@ namespace pb
     // src rows -> (optional weight) -> ramp filter -> dst.  dst_transposed: write dst[s*dst_pitch + t]
     // (stack slot layout) instead of dst[t*dim_x + s].
     int launch_filter(paris_b200_ctx* ctx, const float* d_src, float* d_dst, uint32_t dim_x, uint32_t dim_y,
-                      const paris_b200_filter* f, const weight_params& w, bool dst_transposed, uint32_t dst_pitch);
+                      const paris_b200_filter* f, const weight_params& w, bool dst_transposed, uint32_t dst_pitch,
+                      uint32_t layout = kLayoutPlain);
 
     // `count` (<= kMaxBatch) projections in one launch.  Transposed: src[i] -> slot first_slot + i of d_stack;
     // row-major: src[i] -> dst[i] (may alias).
     int launch_filter_batch(paris_b200_ctx* ctx, const float* const* d_src, float* const* d_dst, uint32_t count,
                             float* d_stack, uint32_t first_slot, size_t slot_floats, uint32_t dim_x, uint32_t dim_y,
-                            const paris_b200_filter* f, const weight_params& w, bool transposed, uint32_t pitch);
+                            const paris_b200_filter* f, const weight_params& w, bool transposed, uint32_t pitch,
+                            uint32_t layout = kLayoutPlain);
 
     // frequency index stored at position p after the forward passes of the size-2^log2n transform
     int frequency_of_position(int log2n, int p);
 
     int launch_transpose_to_slot(paris_b200_ctx* ctx, const float* d_src, float* d_slot, uint32_t dim_x,
-                                 uint32_t dim_y, uint32_t pitch);
+                                 uint32_t dim_y, uint32_t pitch, uint32_t layout = kLayoutPlain);
 
     int launch_backproject(paris_b200_ctx* ctx, const float* d_stack, size_t slot_floats, uint32_t pitch,
-                           uint32_t first, uint32_t count, const float* sn, const float* cs, const bp_target& t);
+                           uint32_t first, uint32_t count, const float* sn, const float* cs, const bp_target& t,
+                           uint32_t layout = kLayoutPlain);
+
+    // the layout the backprojection wants for this geometry (from the detector rows one voxel step in z spans
+    // at the rotation axis)
+    uint32_t choose_stack_layout(const paris_b200_detector_geometry& det, const paris_b200_volume_geometry& vol_full);
 
     int launch_phantom(paris_b200_ctx* ctx, const double* h_ellipsoids, uint32_t n, const paris_b200_detector_geometry* det,
                        uint32_t first_idx, uint32_t n_proj, float* d_out);

@@ -284,7 +284,7 @@ namespace pb
     __global__ void __launch_bounds__(plan<LOG2N>::THREADS, 1)
     filter_kernel(const filter_batch io, float* dst_stack, uint32_t first_slot, size_t slot_floats, uint32_t dim_x,
                   uint32_t dim_y, const float* __restrict__ knp, const float2* __restrict__ tw, weight_params w,
-                  uint32_t dst_pitch)
+                  uint32_t dst_pitch, uint32_t layout)
     {
         using P = plan<LOG2N>;
         constexpr int N = P::N;
@@ -416,18 +416,41 @@ namespace pb
 
         if(TRANSPOSED)
         {
-            // 4 lanes cover the 8 staged rows of one sample: 32 contiguous bytes in the stack slot
             float* dst = dst_stack + slot_floats * (first_slot + blockIdx.y);
-            for(int el = threadIdx.x; el < static_cast<int>(dim_x) * 4; el += P::THREADS)
+            if(layout == kLayoutPlain)
             {
-                const int i = el >> 2, q = el & 3;
-                const uint32_t t = row_base + 2u * q;
-                if(t < dim_y)
+                // 4 lanes cover the 8 staged rows of one sample: 32 contiguous bytes in the stack slot
+                for(int el = threadIdx.x; el < static_cast<int>(dim_x) * 4; el += P::THREADS)
                 {
-                    float2 v = *reinterpret_cast<const float2*>(stage + i * kStagePitch + 2 * q);
-                    if(t + 1u >= dim_y)
-                        v.y = 0.f; // the slot's padding columns stay zero
-                    *reinterpret_cast<float2*>(dst + static_cast<size_t>(i) * dst_pitch + t) = v;
+                    const int i = el >> 2, q = el & 3;
+                    const uint32_t t = row_base + 2u * q;
+                    if(t < dim_y)
+                    {
+                        float2 v = *reinterpret_cast<const float2*>(stage + i * kStagePitch + 2 * q);
+                        if(t + 1u >= dim_y)
+                            v.y = 0.f; // the slot's padding columns stay zero
+                        *reinterpret_cast<float2*>(dst + static_cast<size_t>(i) * dst_pitch + t) = v;
+                    }
+                }
+            }
+            else
+            {
+                // split2: the 4 even rows of a sample are 16 contiguous bytes in the even plane, the 4 odd rows
+                // 16 contiguous bytes in the odd plane (row_base is a multiple of 8)
+                for(int el = threadIdx.x; el < static_cast<int>(dim_x) * 2; el += P::THREADS)
+                {
+                    const int i = el >> 1, parity = el & 1;
+                    if(row_base + parity < dim_y)
+                    {
+                        float4 v;
+                        const float* st = stage + i * kStagePitch + parity;
+                        v.x = st[0];
+                        v.y = row_base + 2u + parity < dim_y ? st[2] : 0.f;
+                        v.z = row_base + 4u + parity < dim_y ? st[4] : 0.f;
+                        v.w = row_base + 6u + parity < dim_y ? st[6] : 0.f;
+                        *reinterpret_cast<float4*>(dst + static_cast<size_t>(i) * dst_pitch + parity * (dst_pitch >> 1)
+                                                   + (row_base >> 1)) = v;
+                    }
                 }
             }
         }
@@ -436,7 +459,8 @@ namespace pb
     template <int LOG2N>
     static int launch_grouped(paris_b200_ctx* ctx, const filter_batch& io, uint32_t count, float* d_stack,
                               uint32_t first_slot, size_t slot_floats, uint32_t dim_x, uint32_t dim_y,
-                              const paris_b200_filter* f, const weight_params& w, bool transposed, uint32_t pitch)
+                              const paris_b200_filter* f, const weight_params& w, bool transposed, uint32_t pitch,
+                              uint32_t layout)
     {
         using P = plan<LOG2N>;
         const size_t smem = sizeof(float2) * P::NPAD * P::PAIRS + (transposed ? sizeof(float) * kStagePitch * dim_x : 0);
@@ -446,13 +470,13 @@ namespace pb
             auto kern = filter_kernel<LOG2N, true>;
             PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             kern<<<grid, P::THREADS, smem, ctx->compute>>>(io, d_stack, first_slot, slot_floats, dim_x, dim_y, f->d_knp,
-                                                          f->d_tw, w, pitch);
+                                                          f->d_tw, w, pitch, layout);
         }
         else
         {
             auto kern = filter_kernel<LOG2N, false>;
             PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            kern<<<grid, P::THREADS, smem, ctx->compute>>>(io, nullptr, 0u, 0, dim_x, dim_y, f->d_knp, f->d_tw, w, 0u);
+            kern<<<grid, P::THREADS, smem, ctx->compute>>>(io, nullptr, 0u, 0, dim_x, dim_y, f->d_knp, f->d_tw, w, 0u, kLayoutPlain);
         }
         PB_CUDA(cudaGetLastError());
         ++ctx->launches;
@@ -463,8 +487,14 @@ namespace pb
     // Row-major: src[i] -> dst[i] (may alias).
     int launch_filter_batch(paris_b200_ctx* ctx, const float* const* d_src, float* const* d_dst, uint32_t count,
                             float* d_stack, uint32_t first_slot, size_t slot_floats, uint32_t dim_x, uint32_t dim_y,
-                            const paris_b200_filter* f, const weight_params& w, bool transposed, uint32_t pitch)
+                            const paris_b200_filter* f, const weight_params& w, bool transposed, uint32_t pitch,
+                            uint32_t layout)
     {
+        if(transposed && layout != kLayoutPlain && (f->size < 256 || (pitch & 7u) != 0u))
+        {
+            set_error("the split stack layout needs a filter size >= 256 and a pitch that is a multiple of 8");
+            return PARIS_B200_EINVAL;
+        }
         if(f->device != ctx->device)
         {
             set_error("filter lives on device %d, context on device %d", f->device, ctx->device);
@@ -503,12 +533,12 @@ namespace pb
         }
         switch(f->size)
         {
-            case 256: return launch_grouped<8>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch);
-            case 512: return launch_grouped<9>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch);
-            case 1024: return launch_grouped<10>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch);
-            case 2048: return launch_grouped<11>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch);
-            case 4096: return launch_grouped<12>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch);
-            case 8192: return launch_grouped<13>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch);
+            case 256: return launch_grouped<8>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch, layout);
+            case 512: return launch_grouped<9>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch, layout);
+            case 1024: return launch_grouped<10>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch, layout);
+            case 2048: return launch_grouped<11>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch, layout);
+            case 4096: return launch_grouped<12>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch, layout);
+            case 8192: return launch_grouped<13>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch, layout);
             default: break;
         }
         set_error("unsupported filter size %u", f->size);
@@ -516,12 +546,13 @@ namespace pb
     }
 
     int launch_filter(paris_b200_ctx* ctx, const float* d_src, float* d_dst, uint32_t dim_x, uint32_t dim_y,
-                      const paris_b200_filter* f, const weight_params& w, bool dst_transposed, uint32_t dst_pitch)
+                      const paris_b200_filter* f, const weight_params& w, bool dst_transposed, uint32_t dst_pitch,
+                      uint32_t layout)
     {
         // single projection; for the transposed case d_dst is the slot itself (a one-slot stack)
         const float* src[1] = {d_src};
         float* dst[1] = {d_dst};
         return launch_filter_batch(ctx, src, dst, 1u, dst_transposed ? d_dst : nullptr, 0u, 0, dim_x, dim_y, f, w,
-                                   dst_transposed, dst_pitch);
+                                   dst_transposed, dst_pitch, layout);
     }
 }

@@ -29,10 +29,10 @@ namespace pb
         return PARIS_B200_OK;
     }
 
-    // dst[s * pitch + t] = src[t * dim_x + s]   (32x32 tiles through shared memory, both sides coalesced)
+    // dst[s * pitch + line_offset(t)] = src[t * dim_x + s]   (32x32 tiles through shared memory, both sides coalesced)
     __global__ void __launch_bounds__(256)
     transpose_kernel(const float* __restrict__ src, float* __restrict__ dst, uint32_t dim_x, uint32_t dim_y,
-                     uint32_t pitch)
+                     uint32_t pitch, uint32_t layout)
     {
         __shared__ float tile[32][33];
         const uint32_t s0 = blockIdx.x * 32u, t0 = blockIdx.y * 32u;
@@ -46,16 +46,16 @@ namespace pb
         {
             const uint32_t s = s0 + r, t = t0 + threadIdx.x;
             if(s < dim_x && t < dim_y)
-                dst[static_cast<size_t>(s) * pitch + t] = tile[threadIdx.x][r];
+                dst[static_cast<size_t>(s) * pitch + line_offset(t, pitch, layout)] = tile[threadIdx.x][r];
         }
     }
 
     int launch_transpose_to_slot(paris_b200_ctx* ctx, const float* d_src, float* d_slot, uint32_t dim_x,
-                                 uint32_t dim_y, uint32_t pitch)
+                                 uint32_t dim_y, uint32_t pitch, uint32_t layout)
     {
         const dim3 block(32, 8);
         const dim3 grid((dim_x + 31u) / 32u, (dim_y + 31u) / 32u);
-        transpose_kernel<<<grid, block, 0, ctx->compute>>>(d_src, d_slot, dim_x, dim_y, pitch);
+        transpose_kernel<<<grid, block, 0, ctx->compute>>>(d_src, d_slot, dim_x, dim_y, pitch, layout);
         PB_CUDA(cudaGetLastError());
         ++ctx->launches;
         return PARIS_B200_OK;

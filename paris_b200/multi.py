@@ -50,6 +50,7 @@ class MultiGpuReconstructor:
         self.lo, self.hi, self.chunk = plan.projection_block(n_proj)
         self.my_count = self.hi - self.lo
         self.slot_bytes, self.pitch = capi.stack_slot_bytes(det.n_row, det.n_col)
+        self.layout = capi.choose_stack_layout(det, vol)
         self.slots = self.chunk * plan.world
         self.filter = self.ctx.filter_create(capi.filter_size(det.n_row), float(det.l_px_row))
         sc = np.array([angle_sin_cos(i, det) for i in range(n_proj)], dtype=np.float32).reshape(n_proj, 2)
@@ -104,12 +105,13 @@ class MultiGpuReconstructor:
         e0 = ctx.event() if timed else None
         ctx.volume_clear(self.d_vol, *self.slab_dims)
         if self.my_count:
-            ctx.filter_to_stack_batch(self.d_raw, self.px, self.my_count, self.det, self.filter, self.d_stack, self.lo)
+            ctx.filter_to_stack_batch(self.d_raw, self.px, self.my_count, self.det, self.filter, self.d_stack, self.lo,
+                                      self.layout)
         e1 = ctx.event() if timed else None
         self._allgather()
         e2 = ctx.event() if timed else None
         ctx.backproject_stack(self.d_stack, 0, self.n_proj, self.sin, self.cos, self.d_vol, self.slab_dims,
-                              self.plan.offset, self.det, self.vol)
+                              self.plan.offset, self.det, self.vol, layout=self.layout)
         if not timed:
             return None
         e3 = ctx.event()
@@ -132,11 +134,11 @@ class MultiGpuReconstructor:
         for i in range(self.my_count):
             d = ctx.dev_alloc(self.px * 4)
             ctx.proj_h2d(self.h_raw.ptr + i * self.px * 4, d, self.det.n_row, self.det.n_col)
-            ctx.filter_to_stack(d, self.det, self.filter, self.d_stack, self.lo + i)
+            ctx.filter_to_stack(d, self.det, self.filter, self.d_stack, self.lo + i, self.layout)
             ctx.dev_free(d)
         self._allgather()
         ctx.backproject_stack(self.d_stack, 0, self.n_proj, self.sin, self.cos, self.d_vol, self.slab_dims,
-                              self.plan.offset, self.det, self.vol)
+                              self.plan.offset, self.det, self.vol, layout=self.layout)
         ctx.vol_d2h(self.d_vol, self.h_slab.ptr, self.slab_dims[0] * self.slab_dims[1] * self.slab_dims[2])
 
     def slab(self) -> np.ndarray:

@@ -14,6 +14,7 @@ ap.add_argument("--natural", action="store_true")
 ap.add_argument("--kernel", type=int, default=0)
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--reps", type=int, default=3)
+ap.add_argument("--layout", type=int, default=-1)
 ap.add_argument("--check", action="store_true", help="compare against the exact kernel")
 a = ap.parse_args()
 
@@ -38,13 +39,15 @@ stack = ctx.dev_alloc(n * slot_bytes)
 filt = ctx.filter_create(capi.filter_size(a.det), l_px)
 sc = np.array([angle_sin_cos(i, det) for i in range(n)], dtype=np.float32)
 dims = (vol.dim_x, vol.dim_y, vol.dim_z)
+layout = capi.choose_stack_layout(det, vol) if a.layout < 0 else a.layout
+print('layout', layout)
 d_vol = ctx.volume_alloc(*dims)
 updates = vol.dim_x * vol.dim_y * vol.dim_z * n
 for rep in range(a.reps):
     e0 = ctx.event()
-    ctx.filter_to_stack_batch(raw, a.det * a.det, n, det, filt, stack, 0)
+    ctx.filter_to_stack_batch(raw, a.det * a.det, n, det, filt, stack, 0, layout)
     e1 = ctx.event()
-    ctx.backproject_stack(stack, 0, n, sc[:, 0], sc[:, 1], d_vol, dims, 0, det, vol)
+    ctx.backproject_stack(stack, 0, n, sc[:, 0], sc[:, 1], d_vol, dims, 0, det, vol, layout=layout)
     e2 = ctx.event()
     tf = ctx.elapsed_ms(e0, e1, destroy=False)
     tb = ctx.elapsed_ms(e1, e2, destroy=False)
@@ -55,7 +58,7 @@ if a.check:
     ctx.set_option("bp_kernel", 1)
     d_ref = ctx.volume_alloc(*dims)
     for rep in range(a.reps):
-        ctx.backproject_stack(stack, 0, n, sc[:, 0], sc[:, 1], d_ref, dims, 0, det, vol)
+        ctx.backproject_stack(stack, 0, n, sc[:, 0], sc[:, 1], d_ref, dims, 0, det, vol, layout=layout)
     ref = np.empty_like(out)
     ctx.vol_d2h(d_ref, ref, ref.size)
     c = n / (8 * np.pi) * a.reps

@@ -162,13 +162,15 @@ def test_full_size_config2_fast_kernel_against_exact_kernel(ctx):
     slot_bytes, _ = capi.stack_slot_bytes(n, n)
     stack = ctx.dev_alloc(n_proj * slot_bytes)
     filt = ctx.filter_create(capi.filter_size(n), l_px)
-    ctx.filter_to_stack_batch(raw, n * n, n_proj, det, filt, stack, 0)
+    layout = capi.choose_stack_layout(det, vol)
+    assert layout == capi.LAYOUT_SPLIT2
+    ctx.filter_to_stack_batch(raw, n * n, n_proj, det, filt, stack, 0, layout)
     sc = np.array([angle_sin_cos(i, det) for i in range(n_proj)], dtype=np.float32)
     out = {}
     for kernel in (2, 1):
         ctx.set_option("bp_kernel", kernel)
         v = ctx.volume_alloc(k, k, k)
-        ctx.backproject_stack(stack, 0, n_proj, sc[:, 0], sc[:, 1], v, (k, k, k), 0, det, vol)
+        ctx.backproject_stack(stack, 0, n_proj, sc[:, 0], sc[:, 1], v, (k, k, k), 0, det, vol, layout=layout)
         out[kernel] = np.empty((k, k, k), np.float32)
         ctx.vol_d2h(v, out[kernel], k ** 3)
         ctx.volume_free(v)
