@@ -187,6 +187,11 @@ namespace pb
     // path.  The others ("careful", flagged by the builder in the sign of w*(1-fx)) test validity on the
     // fixed-point row and, only for voxels within 1/64 of a row of the border, redo the row with exactly the
     // reference's float operations (:130-133, :45-50, :39-43) to take the reference's side of the decision.
+#ifdef PB_BP_STATS
+    // developer instrumentation: tile-projections by class and careful columns (make lib EXTRA_NVFLAGS=-DPB_BP_STATS)
+    __device__ unsigned long long g_bp_stats[8];
+#endif
+
     struct border_rows
     {
         uint32_t b0;      // 9.23 box-relative (biased) position of detector row 0, clamped into range
@@ -226,7 +231,9 @@ namespace pb
             const uint32_t dv = __float_as_uint(ea.z);
             const float wa = fabsf(ea.w);
             uint32_t vfix = dv * lane + __float_as_uint(ea.y);
-            const bool careful = MIXED && (__float_as_uint(ea.w) >> 31) != 0u;   // uniform across the warp
+            // every column of a boundary tile takes the careful path: three quarters of them need it anyway
+            // (measured on the bench configurations) and straight-line code schedules better than a branch per column
+            constexpr bool careful = MIXED;
             #pragma unroll
             for(int j = 0; j < CFG::NZ; ++j)
             {
@@ -367,6 +374,9 @@ namespace pb
             o.all_valid = !finite ? 0 : outside ? 2 : (fits && inside) ? 1 : 0;
             o.fits = (fits && finite) ? 1 : 0;
             origin[tid] = o;
+#ifdef PB_BP_STATS
+            atomicAdd(&g_bp_stats[o.all_valid], 1ull);                                 // [0] mixed, [1] interior, [2] skipped
+#endif
         }
         __syncthreads();
 
@@ -472,6 +482,12 @@ namespace pb
                                 + (CFG::SPLIT ? 4u * static_cast<uint32_t>(CFG::BVH) - 2u * static_cast<uint32_t>(CFG::BIAS)
                                               : 0u - 4u * static_cast<uint32_t>(CFG::BIAS));
             ea.x = __uint_as_float(base);
+#ifdef PB_BP_STATS
+            atomicAdd(&g_bp_stats[3], 1ull);                                           // table entries built
+            if(__float_as_uint(ea.w) >> 31) atomicAdd(&g_bp_stats[4], 1ull);           // careful columns
+            if(ea.w == 0.f && eb == 0.f) atomicAdd(&g_bp_stats[5], 1ull);              // dead columns
+            if(o.all_valid == 0) atomicAdd(&g_bp_stats[6], 1ull);                      // entries in mixed tiles
+#endif
             tab_a[(p & 1) * CFG::COLS + tid] = ea;
             tab_b[(p & 1) * CFG::COLS + tid] = eb;
             tab_c[(p & 1) * CFG::COLS + tid] = ec;
@@ -682,6 +698,17 @@ namespace pb
     {
         return f.need_h <= CFG::BH && f.need_v + (CFG::SPLIT ? 7 : 3) <= CFG::BV;
     }
+
+#ifdef PB_BP_STATS
+    extern "C" int paris_b200_debug_bp_stats(unsigned long long* out)
+    {
+        cudaDeviceSynchronize();
+        cudaMemcpyFromSymbol(out, g_bp_stats, sizeof(unsigned long long) * 8);
+        unsigned long long zero[8] = {0};
+        cudaMemcpyToSymbol(g_bp_stats, zero, sizeof(zero));
+        return 0;
+    }
+#endif
 
     int launch_bp_tma(paris_b200_ctx* ctx, const float* d_stack, size_t slot_floats, uint32_t first,
                       const bp_geometry& g, const bp_angles& a, float* d_vol, bool required, bool* handled)
