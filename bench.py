@@ -122,6 +122,27 @@ class ClockSampler:
         return out
 
 
+def ncu_traffic(kernel: str):
+    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu summary
+    (profiles/*_ncu_summary.json, one --set full capture on the same workload shape); None if absent."""
+    import glob
+    best = None
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json"))):
+        try:
+            rec = json.load(open(path)).get(kernel)
+        except (OSError, ValueError):
+            continue
+        if not rec:
+            continue
+        total = 0.0
+        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+            unit = rec.get(key + "__unit", "byte").lower()
+            scale = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+            total += float(rec.get(key, 0.0)) * scale
+        best = total
+    return best
+
+
 def measured_peaks() -> dict:
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -301,20 +322,27 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
             "config": {"workload": CONFIGS[args.config][3], "parallelism": f"z-slab x{world}",
                        "l2": "inputs larger than L2 (raw + filtered stack >= 6 GB at c2)",
-                       "bp_batch": rec.batch, "stack_layout": "transposed, v fastest"},
+                       "bp_batch": rec.batch,
+                       "stack_layout": "transposed, v fastest, " + ("parity-split" if rec.layout else "plain")},
             "backprojection_gups": my_updates * world / bp_s / 1e9,
             "stage_ms": {"filter": filt_s * 1e3, "allgather": t_gather / args.steps, "backproject": bp_s * 1e3},
             "roofline": {"kernel": "bp_tma_kernel", "bound": "smem", "achieved": bp_gbs, "peak": smem_peak,
-                         "unit": "GB/s", "frac": bp_gbs / smem_peak, "traffic": None,
+                         "unit": "GB/s", "frac": bp_gbs / smem_peak, "traffic": ncu_traffic("backprojection"),
+                         "traffic_note": "DRAM bytes per 64-projection launch (ncu, profiles/); algorithmic smem bytes per "
+                                         f"launch = {16.0 * my_updates * min(rec.batch, n_proj) / n_proj:.3e}",
                          "note": "16 B of shared-memory sample fetches per voxel update; peak = 148 SMs x 128 B/clk x "
                                  f"{sm_mhz:.0f} MHz (SM clock sampled during the run); not an HBM- or tensor-bound kernel"},
             "roofline_filter": {"kernel": "filter_kernel", "bound": "hbm", "achieved": filt_gbs, "peak": hbm_peak,
-                                "unit": "GB/s", "frac": filt_gbs / hbm_peak, "traffic": None,
+                                "unit": "GB/s", "frac": filt_gbs / hbm_peak, "traffic": ncu_traffic("fused"),
+                                "traffic_note": "DRAM bytes per 64-projection launch (ncu, profiles/); algorithmic = "
+                                                f"{8.0 * px * min(64, rec.my_count):.3e}",
                                 "note": f"8 B per detector pixel; peak {peak_src} (MEASURED_PEAKS.json hbm_gbs)"},
             "e2e": {"value": updates / (e2e_step / 1e3) / 1e9, "unit": "GUPS", "seconds": e2e_step / 1e3,
                     "h2d_bytes_per_step": 4 * px * n_proj, "d2h_bytes_per_step": 4 * voxels,
                     "ms_steps": [round(x, 2) for x in e2e_ms],
-                    "path": "paris_b200_dropin_reconstruct: per-projection load/weight/filter/backproject + copy_d2h"},
+                    "path": ("paris_b200_dropin_reconstruct: per-projection load/weight/filter/backproject + copy_d2h"
+                             if world == 1 else
+                             "per rank: proj_h2d + filter_to_stack per projection, NCCL all-gather, backproject_stack, vol_d2h")},
             "gpu_launches": int(launches), "clocks": clocks,
             "wall_s_resident": wall_resident,
         }

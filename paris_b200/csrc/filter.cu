@@ -268,7 +268,7 @@ namespace pb
         static constexpr int OUTER = (LOG2N - LOW) / 2 + 1;               // 2 (256) .. 5 (8192)
         static constexpr int DOUBLES = OUTER / 2;                         // 1 or 2
         static constexpr bool LONE = (OUTER % 2) != 0;
-        static constexpr int PAIRS = (512 / T) < 4 ? ((512 / T) < 1 ? 1 : 512 / T) : 4;  // row pairs side by side
+        static constexpr int PAIRS = (256 / T) < 4 ? ((256 / T) < 1 ? 1 : 256 / T) : 4;  // row pairs side by side (<= 256 threads: two CTAs per SM in different phases)
         static constexpr int ROUNDS = 4 / PAIRS;
         static constexpr int THREADS = PAIRS * T;
         static constexpr int NPAD = pad(N);
@@ -281,7 +281,7 @@ namespace pb
     };
 
     template <int LOG2N, bool TRANSPOSED>
-    __global__ void __launch_bounds__(plan<LOG2N>::THREADS, 1)
+    __global__ void __launch_bounds__(plan<LOG2N>::THREADS, plan<LOG2N>::THREADS <= 256 ? 2 : 1)
     filter_kernel(const filter_batch io, float* dst_stack, uint32_t first_slot, size_t slot_floats, uint32_t dim_x,
                   uint32_t dim_y, const float* __restrict__ knp, const float2* __restrict__ tw, weight_params w,
                   uint32_t dst_pitch, uint32_t layout)
