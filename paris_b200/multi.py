@@ -29,11 +29,27 @@ class SlabPlan:
         self.slab_dz = self.dz + (self.remainder if rank == world - 1 else 0)  # src/make_volume.cpp:32-34
 
     def projection_block(self, n_proj: int):
-        """[lo, hi) of the projections this rank uploads and filters, and the common chunk length."""
+        """[lo, hi) of the projections this rank uploads and filters, and the common chunk length
+        (contiguous assignment: one all-gather of the whole stack)."""
         chunk = (n_proj + self.world - 1) // self.world
         lo = min(self.rank * chunk, n_proj)
         hi = min(lo + chunk, n_proj)
         return lo, hi, chunk
+
+    def cyclic_blocks(self, n_proj: int, max_round: int = 64):
+        """Block-cyclic assignment for the pipelined exchange: the scan is cut into rounds of world*m
+        consecutive projections, rank r owns the m projections [round*world*m + r*m, ... + m) of every round,
+        so a round's all-gather output is a contiguous run of stack slots in PROJECTION ORDER (the
+        backprojection then adds projections in the same order as a single GPU does).  Returns m (0 if the
+        scan does not divide evenly: callers fall back to the contiguous scheme)."""
+        if n_proj % self.world:
+            return 0
+        per_rank = n_proj // self.world
+        best = 0
+        for m in range(1, per_rank + 1):
+            if per_rank % m == 0 and self.world * m <= max_round:
+                best = m
+        return best
 
 
 class MultiGpuReconstructor:
@@ -49,6 +65,9 @@ class MultiGpuReconstructor:
         self.px = det.n_row * det.n_col
         self.lo, self.hi, self.chunk = plan.projection_block(n_proj)
         self.my_count = self.hi - self.lo
+        # pipelined exchange (N > 1): block-cyclic ownership, m projections per rank and round
+        self.m = plan.cyclic_blocks(n_proj, batch) if dist is not None else 0
+        self.rounds = (n_proj // (plan.world * self.m)) if self.m else 0
         self.slot_bytes, self.pitch = capi.stack_slot_bytes(det.n_row, det.n_col)
         self.layout = capi.choose_stack_layout(det, vol)
         self.slots = self.chunk * plan.world
@@ -66,6 +85,7 @@ class MultiGpuReconstructor:
                                             device=torch.device("cuda", device))
             self.d_stack = self._torch_stack.data_ptr()
             self._ext_stream = torch.cuda.ExternalStream(self.ctx.stream(), device=torch.device("cuda", device))
+            self._comm_stream = torch.cuda.Stream(device=torch.device("cuda", device), priority=-1)
         else:
             self.d_stack = self.ctx.dev_alloc(self.slots * self.slot_bytes)
         self.d_raw = None
@@ -79,11 +99,24 @@ class MultiGpuReconstructor:
         self.d_raw = self.ctx.dev_alloc(n * self.px * 4)
         self.h_raw = capi.PinnedArray((n, self.det.n_col, self.det.n_row))
         if self.my_count:
-            self.ctx.phantom_project(ellipsoids_mm, self.det, self.lo, self.my_count, self.d_raw)
+            if self.m:
+                # local projection i = round*m + j  <->  global index round*world*m + rank*m + j
+                for rd in range(self.rounds):
+                    self.ctx.phantom_project(ellipsoids_mm, self.det, self.global_index(rd * self.m), self.m,
+                                             self.d_raw + rd * self.m * self.px * 4)
+            else:
+                self.ctx.phantom_project(ellipsoids_mm, self.det, self.lo, self.my_count, self.d_raw)
             for i in range(self.my_count):
                 self.ctx.proj_d2h(self.d_raw + i * self.px * 4, self.h_raw.ptr + i * self.px * 4, self.det.n_row,
                                   self.det.n_col)
         self.ctx.sync()
+
+    def global_index(self, local: int) -> int:
+        """Scan index (= stack slot) of this rank's local projection `local`."""
+        if not self.m:
+            return self.lo + local
+        rd, j = divmod(local, self.m)
+        return rd * self.plan.world * self.m + self.plan.rank * self.m + j
 
     def host_sample(self, count: int, stride: int = 1) -> np.ndarray:
         return np.ascontiguousarray(self.h_raw.array[::stride][:count])
@@ -93,25 +126,83 @@ class MultiGpuReconstructor:
         if self.dist is None:
             return
         torch = self._torch
+        if self.m:
+            slot_floats = self.slot_bytes // 4
+            w, m = self.plan.world, self.m
+            with torch.cuda.stream(self._ext_stream):
+                for rd in range(self.rounds):
+                    first = rd * w * m
+                    mine_first = first + self.plan.rank * m
+                    self.dist.all_gather_into_tensor(self._torch_stack[first * slot_floats:(first + w * m) * slot_floats],
+                                                     self._torch_stack[mine_first * slot_floats:(mine_first + m) * slot_floats])
+            return
         chunk_floats = self.chunk * self.slot_bytes // 4
         mine = self._torch_stack[self.plan.rank * chunk_floats:(self.plan.rank + 1) * chunk_floats]
         with torch.cuda.stream(self._ext_stream):
             self.dist.all_gather_into_tensor(self._torch_stack, mine)
 
     # ---- steps -------------------------------------------------------------------------------------------------
-    def step_resident(self, timed: bool = False):
-        """raw projections already in HBM -> slab in HBM.  Returns (filter, all-gather, backproject) ms if timed."""
+    def _backproject(self, first: int, count: int):
+        self.ctx.backproject_stack(self.d_stack, first, count, self.sin[first:first + count], self.cos[first:first + count],
+                                   self.d_vol, self.slab_dims, self.plan.offset, self.det, self.vol, layout=self.layout)
+
+    def _pipelined(self, upload: bool):
+        """N > 1: per round, filter my m projections -> all-gather the round (comm stream) -> backproject the
+        PREVIOUS round, so the exchange of round c hides behind the backprojection of round c-1."""
+        ctx, torch = self.ctx, self._torch
+        w, m = self.plan.world, self.m
+        slot_floats = self.slot_bytes // 4
+        ctx.volume_clear(self.d_vol, *self.slab_dims)
+        gathered = []
+        for rd in range(self.rounds):
+            first = rd * w * m
+            mine_first = first + self.plan.rank * m
+            if upload:
+                for j in range(m):
+                    i = rd * m + j
+                    d = ctx.dev_alloc(self.px * 4)
+                    ctx.proj_h2d(self.h_raw.ptr + i * self.px * 4, d, self.det.n_row, self.det.n_col)
+                    ctx.filter_to_stack(d, self.det, self.filter, self.d_stack, mine_first + j, self.layout)
+                    ctx.dev_free(d)
+            else:
+                ctx.filter_to_stack_batch(self.d_raw + rd * m * self.px * 4, self.px, m, self.det, self.filter,
+                                          self.d_stack, mine_first, self.layout)
+            filtered = torch.cuda.Event()
+            filtered.record(self._ext_stream)
+            with torch.cuda.stream(self._comm_stream):
+                self._comm_stream.wait_event(filtered)
+                out = self._torch_stack[first * slot_floats:(first + w * m) * slot_floats]
+                mine = self._torch_stack[mine_first * slot_floats:(mine_first + m) * slot_floats]
+                self.dist.all_gather_into_tensor(out, mine)
+                done = torch.cuda.Event()
+                done.record(self._comm_stream)
+            gathered.append(done)
+            if rd >= 1:
+                self._ext_stream.wait_event(gathered[rd - 1])
+                self._backproject((rd - 1) * w * m, w * m)
+        self._ext_stream.wait_event(gathered[-1])
+        self._backproject((self.rounds - 1) * w * m, w * m)
+
+    def step_resident(self, timed: bool = False, overlap: bool = True):
+        """raw projections already in HBM -> slab in HBM.  timed (sequential, for the stage breakdown):
+        returns (filter, all-gather, backproject) milliseconds."""
         ctx = self.ctx
+        if self.dist is not None and self.m and overlap and not timed:
+            self._pipelined(upload=False)
+            return None
         e0 = ctx.event() if timed else None
         ctx.volume_clear(self.d_vol, *self.slab_dims)
-        if self.my_count:
+        if self.m:
+            for rd in range(self.rounds):
+                ctx.filter_to_stack_batch(self.d_raw + rd * self.m * self.px * 4, self.px, self.m, self.det, self.filter,
+                                          self.d_stack, self.global_index(rd * self.m), self.layout)
+        elif self.my_count:
             ctx.filter_to_stack_batch(self.d_raw, self.px, self.my_count, self.det, self.filter, self.d_stack, self.lo,
                                       self.layout)
         e1 = ctx.event() if timed else None
         self._allgather()
         e2 = ctx.event() if timed else None
-        ctx.backproject_stack(self.d_stack, 0, self.n_proj, self.sin, self.cos, self.d_vol, self.slab_dims,
-                              self.plan.offset, self.det, self.vol, layout=self.layout)
+        self._backproject(0, self.n_proj)
         if not timed:
             return None
         e3 = ctx.event()
@@ -130,15 +221,17 @@ class MultiGpuReconstructor:
                                (self.vol.dim_x, self.vol.dim_y, self.vol.dim_z), device=self.device)
             return
         ctx = self.ctx
-        ctx.volume_clear(self.d_vol, *self.slab_dims)
-        for i in range(self.my_count):
-            d = ctx.dev_alloc(self.px * 4)
-            ctx.proj_h2d(self.h_raw.ptr + i * self.px * 4, d, self.det.n_row, self.det.n_col)
-            ctx.filter_to_stack(d, self.det, self.filter, self.d_stack, self.lo + i, self.layout)
-            ctx.dev_free(d)
-        self._allgather()
-        ctx.backproject_stack(self.d_stack, 0, self.n_proj, self.sin, self.cos, self.d_vol, self.slab_dims,
-                              self.plan.offset, self.det, self.vol, layout=self.layout)
+        if self.m:
+            self._pipelined(upload=True)
+        else:
+            ctx.volume_clear(self.d_vol, *self.slab_dims)
+            for i in range(self.my_count):
+                d = ctx.dev_alloc(self.px * 4)
+                ctx.proj_h2d(self.h_raw.ptr + i * self.px * 4, d, self.det.n_row, self.det.n_col)
+                ctx.filter_to_stack(d, self.det, self.filter, self.d_stack, self.lo + i, self.layout)
+                ctx.dev_free(d)
+            self._allgather()
+            self._backproject(0, self.n_proj)
         ctx.vol_d2h(self.d_vol, self.h_slab.ptr, self.slab_dims[0] * self.slab_dims[1] * self.slab_dims[2])
 
     def slab(self) -> np.ndarray:

@@ -94,3 +94,27 @@ def test_projection_blocks_partition_the_scan(n_proj, world):
         assert hi - lo <= chunk and chunk * world >= n_proj
         seen += list(range(lo, hi))
     assert seen == list(range(n_proj))
+
+
+@pytest.mark.parametrize("n_proj,world", [(720, 8), (720, 4), (720, 2), (1440, 8), (2880, 8), (64, 2), (12, 3)])
+def test_block_cyclic_rounds_keep_projection_order(n_proj, world):
+    """Pipelined exchange: every round is world*m CONSECUTIVE projections, rank r owns the r-th block of m;
+    all ranks together cover the scan exactly once and a round fits one backprojection launch."""
+    m = SlabPlan(64, world, 0).cyclic_blocks(n_proj, 64)
+    assert m >= 1 and world * m <= 64 and (n_proj // world) % m == 0
+    rounds = n_proj // (world * m)
+    owner = {}
+    for r in range(world):
+        for local in range(n_proj // world):
+            rd, j = divmod(local, m)
+            g = rd * world * m + r * m + j
+            assert g not in owner
+            owner[g] = r
+    assert sorted(owner) == list(range(n_proj))
+    for rd in range(rounds):
+        block = [owner[g] for g in range(rd * world * m, (rd + 1) * world * m)]
+        assert block == [r for r in range(world) for _ in range(m)]
+
+
+def test_block_cyclic_falls_back_when_uneven():
+    assert SlabPlan(64, 8, 0).cyclic_blocks(721, 64) == 0
