@@ -182,71 +182,98 @@ namespace pb
 
     // Boundary handling.  The reference adds a sample only if all four bilinear neighbours lie on the detector
     // (src/openmp/backprojection.cpp:65-71); at rows 0 and dim_y - 1 that is a DISCONTINUITY, so a row that
-    // rounds to the other side of the border would add or drop a whole sample.  Columns whose rows keep at
-    // least one cell of distance from the border for every slice of the tile cannot flip and take the plain
-    // path.  The others ("careful", flagged by the builder in the sign of w*(1-fx)) test validity on the
-    // fixed-point row and, only for voxels within 1/64 of a row of the border, redo the row with exactly the
-    // reference's float operations (:130-133, :45-50, :39-43) to take the reference's side of the decision.
-#ifdef PB_BP_STATS
-    // developer instrumentation: tile-projections by class and careful columns (make lib EXTRA_NVFLAGS=-DPB_BP_STATS)
-    __device__ unsigned long long g_bp_stats[8];
-#endif
-
-    struct border_rows
-    {
-        uint32_t b0;      // 9.23 box-relative (biased) position of detector row 0, clamped into range
-        uint32_t span;    // 9.23 distance from row 0 to row dim_y - 1 (clamped)
-    };
-
-    // The reference's own verdict for one voxel: v = (z_m * factor - min_v) / l_px_y - 0.5 with its float
-    // operations, then "row >= 0 and row + 1 < dim_y".  Rarely executed (voxels within 1/64 row of the border).
-    __device__ __noinline__ bool reference_row_valid(uint32_t z_global, float factor, const bp_geometry& g)
+    // rounds to the other side of the border would add or drop a whole sample.  The reference's row
+    //     v(z) = (z_m * factor - min_v) / l_px_y - 0.5        (:130-133, :45-50, z_m from :39-43)
+    // is a chain of monotone float operations, hence monotone in z: per (column, projection) the valid slices
+    // of a tile form ONE interval.  For columns that come within a cell of the border the table builder finds
+    // that interval exactly -- it locates the two crossings with the affine model and settles each by
+    // evaluating v(z) with the reference's own float operations at the three candidate slices -- and the inner
+    // loop only compares the slice index with it.  Interior tiles (no column near the border) skip even that.
+    __device__ __forceinline__ float reference_row(uint32_t z_global, float factor, const bp_geometry& g)
     {
         const float size2 = g.l_vx_z / 2.f;
         const float z_m = __fadd_rn(__fadd_rn(-__fmul_rn(static_cast<float>(g.full_z), size2), size2),
                                     __fmul_rn(static_cast<float>(z_global), g.l_vx_z));
         const float min_v = __fsub_rn(-__fmul_rn(static_cast<float>(g.p_dim_y), g.l_px_y / 2.f), g.delta_t);
-        const float v = __fsub_rn(__fdiv_rn(__fsub_rn(__fmul_rn(z_m, factor), min_v), g.l_px_y), 0.5f);
-        const float y1 = floorf(v);
-        return y1 >= 0.f && __fadd_rn(y1, 1.f) < static_cast<float>(g.p_dim_y);
+        return __fsub_rn(__fdiv_rn(__fsub_rn(__fmul_rn(z_m, factor), min_v), g.l_px_y), 0.5f);
+    }
+
+    // First and count of the tile-local slices (0 .. TZ-1) whose rows r = floor(v) satisfy r >= 0 and
+    // r + 1 < dim_y, packed as first | count << 8.  `first_row`/`dv` are the affine model in detector rows.
+    template <int TZ>
+    __device__ __forceinline__ uint32_t valid_slices(uint32_t z0, float factor, double first_row, double dv,
+                                                     const bp_geometry& g)
+    {
+        const float dim_y_f = static_cast<float>(g.p_dim_y);
+        // lower crossing: first slice with floor(v) >= 0
+        int lo = 0;
+        {
+            const double zc = ceil((0.0 - first_row) / dv);
+            const int c = static_cast<int>(fmin(fmax(zc, -2.0), static_cast<double>(TZ + 2)));
+            lo = c + 2;   // if none of the candidates passes (cannot happen while the model is within a slice)
+            #pragma unroll
+            for(int t = 1; t >= -1; --t)
+            {
+                const int z = c + t;
+                if(z < 0 || (z < TZ && floorf(reference_row(z0 + static_cast<uint32_t>(z), factor, g)) >= 0.f))
+                    lo = z;   // monotone: ends at the smallest passing candidate
+            }
+            lo = max(lo, 0);
+        }
+        // upper crossing: last slice with floor(v) + 1 < dim_y
+        int hi = TZ - 1;
+        {
+            const double zc = ceil((static_cast<double>(g.p_dim_y) - 1.0 - first_row) / dv) - 1.0;
+            const int c = static_cast<int>(fmin(fmax(zc, -3.0), static_cast<double>(TZ + 1)));
+            hi = c - 2;
+            #pragma unroll
+            for(int t = -1; t <= 1; ++t)
+            {
+                const int z = c + t;
+                if(z >= TZ
+                   || (z >= 0 && __fadd_rn(floorf(reference_row(z0 + static_cast<uint32_t>(z), factor, g)), 1.f) < dim_y_f))
+                    hi = z;   // monotone: ends at the largest passing candidate
+            }
+            hi = min(hi, TZ - 1);
+        }
+        const int count = max(hi - lo + 1, 0);
+        return static_cast<uint32_t>(min(lo, 255)) | (static_cast<uint32_t>(count) << 8);
     }
 
     template <class CFG, bool MIXED>
     __device__ __forceinline__ void consume(float (&acc)[CFG::NZ][CFG::CPW], const float4* __restrict__ tab_a,
-                                            const float* __restrict__ tab_b, const float* __restrict__ tab_c,
-                                            int col0, uint32_t lane, uint32_t z_first, const border_rows& br,
-                                            const bp_geometry& g)
+                                            const float* __restrict__ tab_b, const uint32_t* __restrict__ tab_c,
+                                            int col0, uint32_t lane)
     {
         // kept in registers so the fraction -> float assembly is a single three-input LOP3
         uint32_t frac_mask = (1u << CFG::FRAC) - 1u, one_bits = 0x3f800000u;
         asm volatile("" : "+r"(frac_mask), "+r"(one_bits));
-        constexpr uint32_t kNear = 1u << (CFG::FRAC - 6);
         #pragma unroll
         for(int i = 0; i < CFG::CPW; ++i)
         {
-            // {stage address of (column x1, row -BIAS), v_base (9.23, biased), dv (9.23), +-w*(1-fx)}, w*fx
+            // {stage address of (column x1, row -BIAS), v_base (9.23, biased), dv (9.23), w*(1-fx)}, w*fx,
+            // valid slices (first | count << 8; boundary tiles only)
             const float4 ea = tab_a[col0 + i];
             const float wb = tab_b[col0 + i];
             const uint32_t base = __float_as_uint(ea.x);
             const uint32_t dv = __float_as_uint(ea.z);
-            const float wa = fabsf(ea.w);
+            const float wa = ea.w;
             uint32_t vfix = dv * lane + __float_as_uint(ea.y);
-            // every column of a boundary tile takes the careful path: three quarters of them need it anyway
-            // (measured on the bench configurations) and straight-line code schedules better than a branch per column
-            constexpr bool careful = MIXED;
+            uint32_t rel = 0u, count = 0u;
+            if(MIXED)
+            {
+                const uint32_t vs = tab_c[col0 + i];
+                rel = lane - (vs & 0xffu);   // slice index relative to the first valid one
+                count = vs >> 8;
+            }
             #pragma unroll
             for(int j = 0; j < CFG::NZ; ++j)
             {
-                bool ok = true;
                 uint32_t vrow = vfix;   // the 9.23 row used for addressing and weights
-                if(careful)
+                if(MIXED)
                 {
-                    const uint32_t d0 = vfix - br.b0;
-                    ok = d0 < br.span;                                            // 0 <= row and row + 1 < dim_y
-                    if((d0 + kNear) < 2u * kNear || (d0 - br.span + kNear) < 2u * kNear)
-                        ok = reference_row_valid(z_first + lane + 32u * j, tab_c[col0 + i], g);
-                    // keep the address inside the box whatever happens (only matters if the host-side footprint
-                    // check were wrong); the value is discarded when ok is false
+                    // rows of slices outside the valid interval may lie outside the staged box: keep the
+                    // address inside, the value is discarded below
                     const uint32_t lo = static_cast<uint32_t>(CFG::BIAS) << CFG::FRAC;
                     const uint32_t hi = static_cast<uint32_t>(CFG::BIAS + CFG::BV - 2) << CFG::FRAC;
                     vrow = min(max(vrow, lo), hi);
@@ -287,7 +314,7 @@ namespace pb
                     d = fmaf(w_odd, go - ge, ge);
                 }
                 if(MIXED)
-                    d = ok ? d : 0.f;
+                    d = (rel + 32u * j) < count ? d : 0.f;   // the reference's "all four neighbours inside"
                 acc[j][i] += d;
                 vfix += dv << 5;   // next slice of this lane: 32 rows of dv further
             }
@@ -303,7 +330,7 @@ namespace pb
         unsigned char* stage_mem = smem;                                                   // STAGES x BH x BV floats
         float4* tab_a = reinterpret_cast<float4*>(smem + size_t(CFG::STAGES) * CFG::STAGE_BYTES);
         float* tab_b = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tab_a) + 2 * CFG::COLS * 16);
-        float* tab_c = tab_b + 2 * CFG::COLS;
+        uint32_t* tab_c = reinterpret_cast<uint32_t*>(tab_b + 2 * CFG::COLS);
         box_origin* origin = reinterpret_cast<box_origin*>(reinterpret_cast<unsigned char*>(tab_c) + 2 * CFG::COLS * 4);
         uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(origin) + kMaxBatch * 16);
 
@@ -442,12 +469,12 @@ namespace pb
             // a dead entry reads row 0 of column 0 of the box with zero weights
             float4 ea = make_float4(0.f, __uint_as_float(static_cast<uint32_t>(CFG::BIAS) << CFG::FRAC),
                                     __uint_as_float(0u), 0.f);
-            float eb = 0.f, ec = 0.f;
+            float eb = 0.f;
+            uint32_t ec = static_cast<uint32_t>(CFG::TZ) << 8;   // every slice valid
             int x1rel = 0;
             if(valid_x)
             {
                 const double fd = static_cast<double>(ct.factor);
-                ec = ct.factor;
                 const double dv = fd * g.dv_scale_d;   // l_vx_z * factor / l_px_y
                 // biased, box-relative row of the tile's first slice
                 const double vb = row_of(z_m0, fd, g) - static_cast<double>(o.v0) + static_cast<double>(CFG::BIAS);
@@ -466,8 +493,8 @@ namespace pb
                     // detector rows of the first and last slice; one cell of slack against rounding
                     const double first = vb + static_cast<double>(o.v0 - CFG::BIAS), last = first + dv * (CFG::TZ - 1);
                     const bool safe = fmin(first, last) >= 1.0 && fmax(first, last) + 2.0 <= static_cast<double>(g.p_dim_y) - 1.0;
-                    if(!safe || !o.fits)
-                        ea.w = -ea.w;   // "careful" flag
+                    if(!safe && o.all_valid == 0)
+                        ec = valid_slices<CFG::TZ>(z0, ct.factor, first, dv, g);
                 }
                 else
                 {
@@ -484,7 +511,7 @@ namespace pb
             ea.x = __uint_as_float(base);
 #ifdef PB_BP_STATS
             atomicAdd(&g_bp_stats[3], 1ull);                                           // table entries built
-            if(__float_as_uint(ea.w) >> 31) atomicAdd(&g_bp_stats[4], 1ull);           // careful columns
+            if(ec != (static_cast<uint32_t>(CFG::TZ) << 8)) atomicAdd(&g_bp_stats[4], 1ull);   // columns near the border
             if(ea.w == 0.f && eb == 0.f) atomicAdd(&g_bp_stats[5], 1ull);              // dead columns
             if(o.all_valid == 0) atomicAdd(&g_bp_stats[6], 1ull);                      // entries in mixed tiles
 #endif
@@ -498,9 +525,6 @@ namespace pb
         __syncthreads();
 
         // ---- main loop over the projections of the batch -----------------------------------------------------------
-        border_rows br;
-        br.b0 = 0u;
-        br.span = 0u;
         #pragma unroll 1
         for(int p = 0; p < count; ++p)
         {
@@ -513,18 +537,11 @@ namespace pb
             const box_origin o = origin[p];
             const float4* ta = tab_a + (p & 1) * CFG::COLS;
             const float* tb = tab_b + (p & 1) * CFG::COLS;
-            const float* tc = tab_c + (p & 1) * CFG::COLS;
+            const uint32_t* tc = tab_c + (p & 1) * CFG::COLS;
             if(o.all_valid == 1)
-                consume<CFG, false>(acc, ta, tb, tc, col0, lane, z0, br, g);
+                consume<CFG, false>(acc, ta, tb, tc, col0, lane);
             else if(o.all_valid == 0)
-            {
-                // box-relative (biased) positions of detector rows 0 and dim_y - 1, clamped to what 9.23 can hold
-                const int b0r = max(CFG::BIAS - o.v0, -2);
-                const int b1r = min(CFG::BIAS + static_cast<int>(g.p_dim_y) - 1 - o.v0, 2 * CFG::BV + 20);
-                br.b0 = static_cast<uint32_t>(b0r) << CFG::FRAC;
-                br.span = static_cast<uint32_t>(max(b1r - b0r, 0)) << CFG::FRAC;
-                consume<CFG, true>(acc, ta, tb, tc, col0, lane, z0, br, g);
-            }
+                consume<CFG, true>(acc, ta, tb, tc, col0, lane);
 
             __syncthreads(); // stage and table[p&1] are free again; table[(p+1)&1] is complete
             if(tid == 0 && p + CFG::STAGES < count)
