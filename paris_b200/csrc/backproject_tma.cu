@@ -128,6 +128,40 @@ namespace pb
             tma_load_3d(dst, map, bar, v0, h0, slot);
     }
 
+    // Blackwell packed FP32: one instruction works on two floats held in a 64-bit register pair
+    __device__ __forceinline__ uint64_t pack2(float lo, float hi)
+    {
+        uint64_t r;
+        asm("mov.b64 %0, {%1, %2};" : "=l"(r) : "f"(lo), "f"(hi));
+        return r;
+    }
+
+    __device__ __forceinline__ void unpack2(uint64_t v, float& lo, float& hi)
+    {
+        asm("mov.b64 {%0, %1}, %2;" : "=f"(lo), "=f"(hi) : "l"(v));
+    }
+
+    __device__ __forceinline__ uint64_t fma2(uint64_t a, uint64_t b, uint64_t c)
+    {
+        uint64_t d;
+        asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
+        return d;
+    }
+
+    __device__ __forceinline__ uint64_t mul2(uint64_t a, uint64_t b)
+    {
+        uint64_t d;
+        asm("mul.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+        return d;
+    }
+
+    __device__ __forceinline__ uint64_t add2(uint64_t a, uint64_t b)
+    {
+        uint64_t d;
+        asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+        return d;
+    }
+
     __device__ __forceinline__ float lds_f32(uint32_t addr)
     {
         float v;
@@ -240,14 +274,57 @@ namespace pb
         return static_cast<uint32_t>(min(lo, 255)) | (static_cast<uint32_t>(count) << 8);
     }
 
+    // The four samples of one voxel update and its y-weight (weight of q?2 against q?1).
+    struct update_samples
+    {
+        float q11, q12, q21, q22, fy;
+    };
+
+    template <class CFG>
+    __device__ __forceinline__ update_samples fetch(uint32_t base, uint32_t vrow, uint32_t frac_mask, uint32_t one_bits)
+    {
+        update_samples u;
+        if(!CFG::SPLIT)
+        {
+            const uint32_t row = vrow >> CFG::FRAC;                               // biased row inside the box
+            u.fy = __uint_as_float(and_or(vrow, frac_mask, one_bits)) - 1.0f;
+            const uint32_t addr = base + 4u * row;
+            u.q11 = lds_f32(addr);
+            u.q12 = lds_f32(addr + 4);
+            u.q21 = lds_f32(addr + 4 * CFG::BV);
+            u.q22 = lds_f32(addr + 4 * CFG::BV + 4);
+        }
+        else
+        {
+            // Rows r and r+1 are one even and one odd row.  With r = 2k + p (p = parity):
+            //   odd  row sits in the odd plane at pair index k,
+            //   even row sits in the even plane at pair index k + p,
+            // and the odd row's weight is fy for p = 0 (it is row r+1), 1 - fy for p = 1 (it is row r).
+            // Across a warp both planes are read with (nearly) unit stride.  Here q?1 = even row, q?2 = odd row.
+            const uint32_t pair4 = (vrow >> (CFG::FRAC - 1)) & ~3u;               // 4 * k
+            const uint32_t par4 = (vrow >> (CFG::FRAC - 2)) & 4u;                 // 4 * p
+            const uint32_t a_odd = base + pair4;                                  // base points at the odd plane
+            const uint32_t a_even = a_odd + par4;
+            const float f1 = __uint_as_float(and_or(vrow, frac_mask, one_bits));  // 1 + fy
+            u.fy = par4 ? 2.0f - f1 : f1 - 1.0f;
+            u.q11 = lds_f32(a_even - 4 * CFG::BVH);
+            u.q21 = lds_f32(a_even - 4 * CFG::BVH + 4 * CFG::BV);
+            u.q12 = lds_f32(a_odd);
+            u.q22 = lds_f32(a_odd + 4 * CFG::BV);
+        }
+        return u;
+    }
+
     template <class CFG, bool MIXED>
-    __device__ __forceinline__ void consume(float (&acc)[CFG::NZ][CFG::CPW], const float4* __restrict__ tab_a,
+    __device__ __forceinline__ void consume(uint64_t (&acc)[CFG::CPW], const float4* __restrict__ tab_a,
                                             const float* __restrict__ tab_b, const uint32_t* __restrict__ tab_c,
                                             int col0, uint32_t lane)
     {
+        static_assert(CFG::NZ == 2, "the two slices of a lane are processed as one packed f32x2 pair");
         // kept in registers so the fraction -> float assembly is a single three-input LOP3
         uint32_t frac_mask = (1u << CFG::FRAC) - 1u, one_bits = 0x3f800000u;
         asm volatile("" : "+r"(frac_mask), "+r"(one_bits));
+        const uint64_t minus_one = pack2(-1.f, -1.f);
         #pragma unroll
         for(int i = 0; i < CFG::CPW; ++i)
         {
@@ -257,67 +334,34 @@ namespace pb
             const float wb = tab_b[col0 + i];
             const uint32_t base = __float_as_uint(ea.x);
             const uint32_t dv = __float_as_uint(ea.z);
-            const float wa = ea.w;
-            uint32_t vfix = dv * lane + __float_as_uint(ea.y);
-            uint32_t rel = 0u, count = 0u;
+            uint32_t v0 = dv * lane + __float_as_uint(ea.y);     // slice `lane`
+            uint32_t v1 = v0 + (dv << 5);                        // slice `lane + 32`: 32 steps of dv further
             if(MIXED)
             {
-                const uint32_t vs = tab_c[col0 + i];
-                rel = lane - (vs & 0xffu);   // slice index relative to the first valid one
-                count = vs >> 8;
+                // rows of slices outside the valid interval may lie outside the staged box: keep the address
+                // inside, the value is discarded below
+                const uint32_t lo = static_cast<uint32_t>(CFG::BIAS) << CFG::FRAC;
+                const uint32_t hi = static_cast<uint32_t>(CFG::BIAS + CFG::BV - 2) << CFG::FRAC;
+                v0 = min(max(v0, lo), hi);
+                v1 = min(max(v1, lo), hi);
             }
-            #pragma unroll
-            for(int j = 0; j < CFG::NZ; ++j)
+            const update_samples s0 = fetch<CFG>(base, v0, frac_mask, one_bits);
+            const update_samples s1 = fetch<CFG>(base, v1, frac_mask, one_bits);
+            // both slices at once: g1 = wa*q11 + wb*q21, g2 = wa*q12 + wb*q22, d = g1 + fy*(g2 - g1)
+            const uint64_t wa2 = pack2(ea.w, ea.w), wb2 = pack2(wb, wb);
+            const uint64_t g1 = fma2(wb2, pack2(s0.q21, s1.q21), mul2(wa2, pack2(s0.q11, s1.q11)));
+            const uint64_t g2 = fma2(wb2, pack2(s0.q22, s1.q22), mul2(wa2, pack2(s0.q12, s1.q12)));
+            uint64_t d = fma2(pack2(s0.fy, s1.fy), fma2(g1, minus_one, g2), g1);
+            if(MIXED)
             {
-                uint32_t vrow = vfix;   // the 9.23 row used for addressing and weights
-                if(MIXED)
-                {
-                    // rows of slices outside the valid interval may lie outside the staged box: keep the
-                    // address inside, the value is discarded below
-                    const uint32_t lo = static_cast<uint32_t>(CFG::BIAS) << CFG::FRAC;
-                    const uint32_t hi = static_cast<uint32_t>(CFG::BIAS + CFG::BV - 2) << CFG::FRAC;
-                    vrow = min(max(vrow, lo), hi);
-                }
-                float d;
-                if(!CFG::SPLIT)
-                {
-                    const uint32_t row = vrow >> CFG::FRAC;                       // biased row inside the box
-                    const float fy = __uint_as_float(and_or(vrow, frac_mask, one_bits)) - 1.0f;
-                    const uint32_t addr = base + 4u * row;
-                    const float q11 = lds_f32(addr);
-                    const float q12 = lds_f32(addr + 4);
-                    const float q21 = lds_f32(addr + 4 * CFG::BV);
-                    const float q22 = lds_f32(addr + 4 * CFG::BV + 4);
-                    const float g0 = fmaf(wb, q21, wa * q11);
-                    const float g1 = fmaf(wb, q22, wa * q12);
-                    d = fmaf(fy, g1 - g0, g0);
-                }
-                else
-                {
-                    // Rows r and r+1 are one even and one odd row.  With r = 2k + p (p = parity):
-                    //   odd  row sits in the odd plane at pair index k,
-                    //   even row sits in the even plane at pair index k + p,
-                    // and the odd row's weight is fy for p = 0 (it is row r+1), 1 - fy for p = 1 (it is row r).
-                    // Across a warp both planes are read with (nearly) unit stride.
-                    const uint32_t pair4 = (vrow >> (CFG::FRAC - 1)) & ~3u;       // 4 * k
-                    const uint32_t par4 = (vrow >> (CFG::FRAC - 2)) & 4u;         // 4 * p
-                    const uint32_t a_odd = base + pair4;                          // base points at the odd plane
-                    const uint32_t a_even = a_odd + par4;
-                    const float f1 = __uint_as_float(and_or(vrow, frac_mask, one_bits));   // 1 + fy
-                    const float w_odd = par4 ? 2.0f - f1 : f1 - 1.0f;
-                    const float e1 = lds_f32(a_even - 4 * CFG::BVH);
-                    const float e2 = lds_f32(a_even - 4 * CFG::BVH + 4 * CFG::BV);
-                    const float o1 = lds_f32(a_odd);
-                    const float o2 = lds_f32(a_odd + 4 * CFG::BV);
-                    const float ge = fmaf(wb, e2, wa * e1);
-                    const float go = fmaf(wb, o2, wa * o1);
-                    d = fmaf(w_odd, go - ge, ge);
-                }
-                if(MIXED)
-                    d = (rel + 32u * j) < count ? d : 0.f;   // the reference's "all four neighbours inside"
-                acc[j][i] += d;
-                vfix += dv << 5;   // next slice of this lane: 32 rows of dv further
+                // the reference's "all four neighbours inside" as a slice interval (see valid_slices)
+                const uint32_t vs = tab_c[col0 + i];
+                const uint32_t rel = lane - (vs & 0xffu), count = vs >> 8;
+                float d0, d1;
+                unpack2(d, d0, d1);
+                d = pack2(rel < count ? d0 : 0.f, (rel + 32u) < count ? d1 : 0.f);
             }
+            acc[i] = add2(acc[i], d);
         }
     }
 
@@ -424,14 +468,10 @@ namespace pb
             scratch[zl * kPitch + c] = ok ? vol[static_cast<size_t>(z) * slice + static_cast<size_t>(y) * g.v_dim_x + x] : 0.f;
         }
         __syncthreads();
-        float acc[CFG::NZ][CFG::CPW];
+        uint64_t acc[CFG::CPW];   // (slice lane, slice lane + 32) of column col0 + i, packed
         #pragma unroll
-        for(int j = 0; j < CFG::NZ; ++j)
-        {
-            #pragma unroll
-            for(int i = 0; i < CFG::CPW; ++i)
-                acc[j][i] = scratch[(lane + 32u * j) * kPitch + col0 + i];
-        }
+        for(int i = 0; i < CFG::CPW; ++i)
+            acc[i] = pack2(scratch[lane * kPitch + col0 + i], scratch[(lane + 32u) * kPitch + col0 + i]);
         __syncthreads(); // scratch is dead: the stages may be filled
 
         if(tid == 0)
@@ -557,11 +597,12 @@ namespace pb
         // ---- epilogue: back through shared memory, one coalesced store per voxel -------------------------------------
         // (the loop's last __syncthreads guarantees nobody reads the stages any more and no TMA load is in flight)
         #pragma unroll
-        for(int j = 0; j < CFG::NZ; ++j)
+        for(int i = 0; i < CFG::CPW; ++i)
         {
-            #pragma unroll
-            for(int i = 0; i < CFG::CPW; ++i)
-                scratch[(lane + 32u * j) * kPitch + col0 + i] = acc[j][i];
+            float lo, hi;
+            unpack2(acc[i], lo, hi);
+            scratch[lane * kPitch + col0 + i] = lo;
+            scratch[(lane + 32u) * kPitch + col0 + i] = hi;
         }
         __syncthreads();
         for(int e = tid; e < CFG::TZ * CFG::COLS; e += CFG::THREADS)
