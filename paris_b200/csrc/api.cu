@@ -604,6 +604,17 @@ extern "C" int paris_b200_filter_create(paris_b200_ctx* ctx, uint32_t size, floa
         tw[i] = make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang)));
     }
 
+    std::vector<float2> twc(3 * (2 * static_cast<size_t>(size) - 8) / 4);
+    for(uint32_t span = 8; span <= size; span <<= 1)
+    {
+        float2* t = twc.data() + 3 * (span - 8) / 4;
+        for(uint32_t i = 0; i < 3 * span / 4; ++i)
+        {
+            const double ang = -2.0 * M_PI * static_cast<double>(i) / static_cast<double>(span);
+            t[i] = make_float2(static_cast<float>(std::cos(ang)), static_cast<float>(std::sin(ang)));
+        }
+    }
+
     auto* f = new paris_b200_filter{};
     f->device = ctx->device;
     f->size = size;
@@ -616,6 +627,8 @@ extern "C" int paris_b200_filter_create(paris_b200_ctx* ctx, uint32_t size, floa
     PB_CUDA(cudaMemcpy(f->d_k, k.data(), n_trans * sizeof(float), cudaMemcpyHostToDevice));
     PB_CUDA(cudaMemcpy(f->d_kn, kn.data(), n_trans * sizeof(float), cudaMemcpyHostToDevice));
     PB_CUDA(cudaMemcpy(f->d_tw, tw.data(), size * sizeof(float2), cudaMemcpyHostToDevice));
+    PB_CUDA(cudaMalloc(reinterpret_cast<void**>(&f->d_twc), twc.size() * sizeof(float2)));
+    PB_CUDA(cudaMemcpy(f->d_twc, twc.data(), twc.size() * sizeof(float2), cudaMemcpyHostToDevice));
     *out = f;
     return PARIS_B200_OK;
 }
@@ -629,6 +642,7 @@ extern "C" int paris_b200_filter_destroy(paris_b200_filter* f)
     cudaFree(f->d_kn);
     cudaFree(f->d_knp);
     cudaFree(f->d_tw);
+    cudaFree(f->d_twc);
     delete f;
     return PARIS_B200_OK;
 }

@@ -80,6 +80,7 @@ struct paris_b200_filter
     float* d_kn = nullptr;   // K[x] / N  (exact: N is a power of two)
     float* d_knp = nullptr;  // K/N per STORAGE position of the forward transform (digit-reversed order), N entries
     float2* d_tw = nullptr;  // exp(-2 pi i k / N), k = 0..N-1
+    float2* d_twc = nullptr; // compact per-span tables: exp(-2 pi i k / 2^m), k < 3*2^m/4, at offset 3*(2^m - 8)/4, m = 3..log2 N
 };
 
 struct paris_b200_ctx

@@ -91,28 +91,31 @@ namespace pb
 
     // One radix-4 pass of span 2^M on 4 register points whose position inside the quarter is j:
     // forward = butterfly, then twiddle W_span^(q j) on output q; inverse = conjugate twiddle, then butterfly.
+    // `twc` holds one COMPACT table per span, W_(2^m)^i for i < 3*2^m/4 at offset 3*(2^m - 8)/4, so that lanes
+    // with consecutive j read consecutive entries (a strided walk through one table of W_N costs up to 32
+    // cache lines per load instruction).
     template <int LOG2N, int M, bool INVERSE>
     __device__ __forceinline__ void pass4(float2& e0, float2& e1, float2& e2, float2& e3, int j,
-                                          const float2* __restrict__ tw)
+                                          const float2* __restrict__ twc)
     {
-        const int t = j << (LOG2N - M);
+        const float2* const t = twc + 3 * ((1 << M) - 8) / 4;
         if(!INVERSE)
         {
             dif4(e0, e1, e2, e3);
             if(M > 2)
             {
-                e1 = cmul(e1, __ldg(tw + t));
-                e2 = cmul(e2, __ldg(tw + 2 * t));
-                e3 = cmul(e3, __ldg(tw + 3 * t));
+                e1 = cmul(e1, __ldg(t + j));
+                e2 = cmul(e2, __ldg(t + 2 * j));
+                e3 = cmul(e3, __ldg(t + 3 * j));
             }
         }
         else
         {
             if(M > 2)
             {
-                e1 = cmul_conj(e1, __ldg(tw + t));
-                e2 = cmul_conj(e2, __ldg(tw + 2 * t));
-                e3 = cmul_conj(e3, __ldg(tw + 3 * t));
+                e1 = cmul_conj(e1, __ldg(t + j));
+                e2 = cmul_conj(e2, __ldg(t + 2 * j));
+                e3 = cmul_conj(e3, __ldg(t + 3 * j));
             }
             dit4(e0, e1, e2, e3);
         }
@@ -143,12 +146,22 @@ namespace pb
         }
     }
 
-    // shared-memory positions of a thread's 16 points for the double group at span 2^M
+    // Shared-memory positions of a thread's 16 points for the double group at span 2^M: padded position of
+    // point 0, and the COMPILE-TIME offset of point k from it.  pad(P0 + k*Q2) = pad(P0) + k*Q2 + (k*Q2 >> 4)
+    // holds for Q2 >= 16 trivially and for Q2 = 8 because the point's index inside its block of 8 never carries
+    // into bit 4 -- so every access of a group is `base + immediate`, no per-element address arithmetic.
     template <int M>
-    __device__ __forceinline__ int group_pos(int b, int k)
+    __device__ __forceinline__ int group_base(int b)
     {
         constexpr int Q2LOG = M - 4;
-        return ((b >> Q2LOG) << M) + (b & ((1 << Q2LOG) - 1)) + (k << Q2LOG);
+        static_assert(Q2LOG >= 3, "the padded offsets of a group are constants only for strides >= 8");
+        return pad(((b >> Q2LOG) << M) + (b & ((1 << Q2LOG) - 1)));
+    }
+
+    template <int M>
+    __host__ __device__ constexpr int group_off(int k)
+    {
+        return (k << (M - 4)) + ((k << (M - 4)) >> 4);
     }
 
     // A lone radix-4 pass of span 2^M: thread b runs the butterflies b, b+T, b+2T, b+3T (T threads per transform);
@@ -165,10 +178,10 @@ namespace pb
         {
             const int bb = b + t * T;
             j[t] = bb & ((1 << QLOG) - 1);
-            base[t] = ((bb >> QLOG) << M) + j[t];
+            base[t] = pad(((bb >> QLOG) << M) + j[t]);   // (offsets of the other three points are constants, as above)
             #pragma unroll
             for(int q = 0; q < 4; ++q)
-                e[4 * t + q] = x[pad(base[t] + (q << QLOG))];
+                e[4 * t + q] = x[base[t] + (q << QLOG) + ((q << QLOG) >> 4)];
         }
         #pragma unroll
         for(int t = 0; t < 4; ++t)
@@ -178,7 +191,7 @@ namespace pb
         {
             #pragma unroll
             for(int q = 0; q < 4; ++q)
-                x[pad(base[t] + (q << QLOG))] = e[4 * t + q];
+                x[base[t] + (q << QLOG) + ((q << QLOG) >> 4)] = e[4 * t + q];
         }
     }
 
@@ -191,7 +204,7 @@ namespace pb
         float2 e[16];
         #pragma unroll
         for(int k = 0; k < 16; ++k)
-            e[k] = x[pad(16 * b) + k];
+            e[k] = x[17 * b + k];   // pad(16 b + k) = 17 b + k
 
         if(LOG2N % 2 == 0)
         {
@@ -252,7 +265,7 @@ namespace pb
 
         #pragma unroll
         for(int k = 0; k < 16; ++k)
-            x[pad(16 * b) + k] = e[k];
+            x[17 * b + k] = e[k];
     }
 
     // ---- group plan ------------------------------------------------------------------------------------------
@@ -262,6 +275,7 @@ namespace pb
     struct plan
     {
         static_assert(LOG2N >= 8 && LOG2N <= 13, "register-grouped kernel covers 256..8192 points");
+        static_assert(true, "lone groups have span 32 or 64: stride 8 or 16, same constant-offset argument");
         static constexpr int N = 1 << LOG2N;
         static constexpr int T = N / 16;                                  // threads per transform
         static constexpr int LOW = (LOG2N % 2 == 0) ? 6 : 5;
@@ -307,6 +321,14 @@ namespace pb
 
             float2 e[16];
             // ---- first group: points b + k*N/16 straight from global memory; k >= 8 is the zero padding ----------
+            // cosine weight d_sd / sqrt(d_sd^2 + h_s^2 + v_t^2) (src/openmp/weighting.cpp:44-52) with one rsqrt per
+            // pixel; the stand-alone weight kernel keeps the reference's exact operation sequence, here a 1-ulp
+            // difference disappears in the float32 transform that follows
+            const float v0 = fmaf(static_cast<float>(row0), w.l_px_col, 0.5f * w.l_px_col + w.v_min);
+            const float v1 = v0 + w.l_px_col;
+            const float c0 = fmaf(v0, v0, w.d_sd * w.d_sd), c1 = fmaf(v1, v1, w.d_sd * w.d_sd);
+            const float* const src0 = src + static_cast<size_t>(row0) * dim_x + b;
+            const float* const src1 = src0 + dim_x;
             #pragma unroll
             for(int k = 0; k < 16; ++k)
             {
@@ -316,42 +338,45 @@ namespace pb
                     const uint32_t i = b + k * (N / 16);
                     if(i < dim_x)
                     {
+                        const float hs = fmaf(static_cast<float>(i), w.l_px_row, 0.5f * w.l_px_row + w.h_min);
                         if(has0)
                         {
-                            a = __ldg(src + static_cast<size_t>(row0) * dim_x + i);
+                            a = __ldg(src0 + k * (N / 16));
                             if(w.enable)
-                                a = __fmul_rn(a, pixel_weight(i, row0, w.h_min, w.v_min, w.d_sd, w.l_px_row, w.l_px_col));
+                                a *= w.d_sd * rsqrtf(fmaf(hs, hs, c0));
                         }
                         if(has1)
                         {
-                            c = __ldg(src + static_cast<size_t>(row1) * dim_x + i);
+                            c = __ldg(src1 + k * (N / 16));
                             if(w.enable)
-                                c = __fmul_rn(c, pixel_weight(i, row1, w.h_min, w.v_min, w.d_sd, w.l_px_row, w.l_px_col));
+                                c *= w.d_sd * rsqrtf(fmaf(hs, hs, c1));
                         }
                     }
                 }
                 e[k] = make_float2(a, c);
             }
             group16<LOG2N, LOG2N, false>(e, b, tw);
+            float2* const x1 = x + group_base<LOG2N>(b);
             #pragma unroll
             for(int k = 0; k < 16; ++k)
-                x[pad(group_pos<LOG2N>(b, k))] = e[k];
+                x1[group_off<LOG2N>(k)] = e[k];
             __syncthreads();
 
             // ---- remaining outer groups, forward -------------------------------------------------------------------
-            if(P::DOUBLES == 2)
+            if constexpr(P::DOUBLES == 2)
             {
                 constexpr int M = LOG2N - 4;
+                float2* const x2 = x + group_base<M>(b);
                 #pragma unroll
                 for(int k = 0; k < 16; ++k)
-                    e[k] = x[pad(group_pos<M>(b, k))];
+                    e[k] = x2[group_off<M>(k)];
                 group16<LOG2N, M, false>(e, b & ((1 << (M - 4)) - 1), tw);
                 #pragma unroll
                 for(int k = 0; k < 16; ++k)
-                    x[pad(group_pos<M>(b, k))] = e[k];
+                    x2[group_off<M>(k)] = e[k];
                 __syncthreads();
             }
-            if(P::LONE)
+            if constexpr(P::LONE)
             {
                 lone_group<LOG2N, P::LOW, false>(x, b, tw);
                 __syncthreads();
@@ -362,26 +387,27 @@ namespace pb
             __syncthreads();
 
             // ---- outer groups, inverse --------------------------------------------------------------------------------
-            if(P::LONE)
+            if constexpr(P::LONE)
             {
                 lone_group<LOG2N, P::LOW, true>(x, b, tw);
                 __syncthreads();
             }
-            if(P::DOUBLES == 2)
+            if constexpr(P::DOUBLES == 2)
             {
                 constexpr int M = LOG2N - 4;
+                float2* const x2 = x + group_base<M>(b);
                 #pragma unroll
                 for(int k = 0; k < 16; ++k)
-                    e[k] = x[pad(group_pos<M>(b, k))];
+                    e[k] = x2[group_off<M>(k)];
                 group16<LOG2N, M, true>(e, b & ((1 << (M - 4)) - 1), tw);
                 #pragma unroll
                 for(int k = 0; k < 16; ++k)
-                    x[pad(group_pos<M>(b, k))] = e[k];
+                    x2[group_off<M>(k)] = e[k];
                 __syncthreads();
             }
             #pragma unroll
             for(int k = 0; k < 16; ++k)
-                e[k] = x[pad(group_pos<LOG2N>(b, k))];
+                e[k] = x1[group_off<LOG2N>(k)];
             group16<LOG2N, LOG2N, true>(e, b, tw);
 
             // ---- keep the first dim_x samples (k < 8; the rest is never computed) ------------------------------------------
@@ -470,13 +496,13 @@ namespace pb
             auto kern = filter_kernel<LOG2N, true>;
             PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             kern<<<grid, P::THREADS, smem, ctx->compute>>>(io, d_stack, first_slot, slot_floats, dim_x, dim_y, f->d_knp,
-                                                          f->d_tw, w, pitch, layout);
+                                                          f->d_twc, w, pitch, layout);
         }
         else
         {
             auto kern = filter_kernel<LOG2N, false>;
             PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            kern<<<grid, P::THREADS, smem, ctx->compute>>>(io, nullptr, 0u, 0, dim_x, dim_y, f->d_knp, f->d_tw, w, 0u, kLayoutPlain);
+            kern<<<grid, P::THREADS, smem, ctx->compute>>>(io, nullptr, 0u, 0, dim_x, dim_y, f->d_knp, f->d_twc, w, 0u, kLayoutPlain);
         }
         PB_CUDA(cudaGetLastError());
         ++ctx->launches;

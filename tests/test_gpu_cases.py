@@ -185,3 +185,31 @@ def test_full_size_config2_fast_kernel_against_exact_kernel(ctx):
     # brain tissue of the phantom (density 1.0 - 0.8 = 0.2) a few voxels off the centre, away from the ventricles
     plateau = out[2][k // 2, k // 2 - 40:k // 2 - 30, k // 2 - 4:k // 2 + 4].mean()
     assert abs(plateau / (0.2 * c) - 1.0) < 0.05
+
+
+@pytest.mark.parametrize("n_row,n_col", [(96, 96), (100, 37), (256, 64), (1024, 16), (2048, 8), (3000, 5)])
+@pytest.mark.parametrize("layout", [capi.LAYOUT_PLAIN, capi.LAYOUT_SPLIT2])
+def test_filter_to_stack_layouts(ctx, port, n_row, n_col, layout):
+    """The fused weight+filter kernel writing a TRANSPOSED stack slot, plain and parity-split line layout."""
+    odet, det = both_det(n_row, n_col, l_px=0.2, delta_s=1.0, delta_t=-1.0)
+    rng = np.random.default_rng(11)
+    p = rng.standard_normal((n_col, n_row)).astype(np.float32)
+    ref = port.filter(port.weight(p, odet), odet)
+    f = ctx.filter_create(capi.filter_size(n_row), 0.2)
+    slot_bytes, pitch = capi.stack_slot_bytes(n_row, n_col)
+    d = ctx.dev_alloc(p.nbytes)
+    ctx.proj_h2d(p, d, n_row, n_col)
+    st = ctx.dev_alloc(slot_bytes * 2)
+    ctx.filter_to_stack(d, det, f, st, 1, layout)
+    out = np.empty((n_row, pitch), np.float32)
+    ctx.proj_d2h(st + slot_bytes, out, pitch, n_row)
+    ctx.dev_free(d)
+    ctx.dev_free(st)
+    ctx.filter_destroy(f)
+    if layout == capi.LAYOUT_SPLIT2:
+        plain = np.empty_like(out)
+        plain[:, 0::2] = out[:, :pitch // 2]
+        plain[:, 1::2] = out[:, pitch // 2:]
+        out = plain
+    assert np.abs(out[:, :n_col].T - ref).max() <= 2e-6 * np.abs(ref).max()
+    assert not out[:, n_col:].any()   # the slot's padding columns stay zero

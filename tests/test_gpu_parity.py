@@ -65,7 +65,8 @@ def test_weight_filter_fused_equals_stages(ctx, port):
     pl.release(a)
     pl.release(b)
     pl.close()
-    assert np.array_equal(ga, gb)
+    # the fused kernel computes the weight with one rsqrt per pixel (<= 2 ulp off the exact stand-alone kernel)
+    assert np.abs(ga - gb).max() <= 1e-6 * np.abs(ga).max()
     ref = port.filter(port.weight(p, odet), odet)
     assert np.abs(ga - ref).max() <= 2e-6 * np.abs(ref).max()
 
