@@ -224,6 +224,10 @@ int paris_b200_choose_stack_layout(const paris_b200_detector_geometry* det, cons
                                    uint32_t* layout);
 /* Size in bytes of one stack slot and its pitch in floats. */
 int paris_b200_stack_slot_bytes(uint32_t n_row, uint32_t n_col, size_t* bytes, uint32_t* pitch);
+/* a zero-initialised stack of `slots` slots (the padding columns pitch > n_col must be zero; a caller that brings
+ * its own buffer, e.g. one NCCL can see, zeroes it itself) */
+int paris_b200_stack_alloc(paris_b200_ctx* ctx, uint32_t n_row, uint32_t n_col, uint32_t slots, float** d_stack);
+int paris_b200_stack_free(paris_b200_ctx* ctx, float* d_stack);
 /* weight + filter a RAW device projection into slot `slot` of an external stack buffer */
 int paris_b200_filter_to_stack(paris_b200_ctx* ctx, const float* d_raw, const paris_b200_detector_geometry* det,
                                const paris_b200_filter* filter, float* d_stack, uint32_t slot, uint32_t layout);

@@ -99,6 +99,8 @@ SIGNATURES = {
     "paris_b200_flush": (C.c_int, [_vp]),
     "paris_b200_stack_slot_bytes": (C.c_int, [_u32, _u32, _P(C.c_size_t), _P(_u32)]),
     "paris_b200_choose_stack_layout": (C.c_int, [_P(DetectorGeometry), _P(VolumeGeometry), _P(_u32)]),
+    "paris_b200_stack_alloc": (C.c_int, [_vp, _u32, _u32, _u32, _P(_vp)]),
+    "paris_b200_stack_free": (C.c_int, [_vp, _fp]),
     "paris_b200_filter_to_stack": (C.c_int, [_vp, _fp, _P(DetectorGeometry), _vp, _fp, _u32, _u32]),
     "paris_b200_filter_to_stack_batch": (C.c_int, [_vp, _fp, C.c_size_t, _u32, _P(DetectorGeometry), _vp, _fp, _u32,
                                                    _u32]),
@@ -334,6 +336,14 @@ class Context:
 
     def flush(self):
         check(self._L.paris_b200_flush(self.h))
+
+    def stack_alloc(self, n_row: int, n_col: int, slots: int) -> int:
+        p = _vp()
+        check(self._L.paris_b200_stack_alloc(self.h, n_row, n_col, slots, C.byref(p)))
+        return p.value
+
+    def stack_free(self, d_stack: int):
+        check(self._L.paris_b200_stack_free(self.h, d_stack))
 
     def filter_to_stack(self, d_raw: int, det: DetectorGeometry, filt: int, d_stack: int, slot: int,
                         layout: int = LAYOUT_PLAIN):

@@ -894,6 +894,28 @@ extern "C" int paris_b200_backproject(paris_b200_ctx* ctx, const float* d_proj, 
 
 // ---- stack-level entry points -----------------------------------------------------------------------------
 
+extern "C" int paris_b200_stack_alloc(paris_b200_ctx* ctx, uint32_t n_row, uint32_t n_col, uint32_t slots, float** d_stack)
+{
+    PB_CHECK_ARG(ctx != nullptr && d_stack != nullptr && n_row > 0 && n_col > 0 && slots > 0);
+    PB_TRY(bind(ctx));
+    const size_t bytes = static_cast<size_t>(stack_pitch_for(n_col)) * n_row * slots * sizeof(float);
+    *d_stack = nullptr;
+    PB_CUDA(cudaMalloc(reinterpret_cast<void**>(d_stack), bytes));
+    PB_CUDA(cudaMemsetAsync(*d_stack, 0, bytes, ctx->compute));
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_stack_free(paris_b200_ctx* ctx, float* d_stack)
+{
+    PB_CHECK_ARG(ctx != nullptr);
+    if(d_stack == nullptr)
+        return PARIS_B200_OK;
+    PB_TRY(bind(ctx));
+    PB_CUDA(cudaStreamSynchronize(ctx->compute));
+    PB_CUDA(cudaFree(d_stack));
+    return PARIS_B200_OK;
+}
+
 extern "C" int paris_b200_filter_to_stack_batch(paris_b200_ctx* ctx, const float* d_raw, size_t raw_stride,
                                                 uint32_t count, const paris_b200_detector_geometry* det,
                                                 const paris_b200_filter* filter, float* d_stack, uint32_t first_slot,

@@ -93,7 +93,8 @@ namespace pb
     // forward = butterfly, then twiddle W_span^(q j) on output q; inverse = conjugate twiddle, then butterfly.
     // `twc` holds one COMPACT table per span, W_(2^m)^i for i < 3*2^m/4 at offset 3*(2^m - 8)/4, so that lanes
     // with consecutive j read consecutive entries (a strided walk through one table of W_N costs up to 32
-    // cache lines per load instruction).
+    // cache lines per load instruction).  The kernel keeps the tables in shared memory: a miss-free 29-cycle load
+    // instead of an L1/L2 round trip in front of every butterfly group.
     template <int LOG2N, int M, bool INVERSE>
     __device__ __forceinline__ void pass4(float2& e0, float2& e1, float2& e2, float2& e3, int j,
                                           const float2* __restrict__ twc)
@@ -104,18 +105,18 @@ namespace pb
             dif4(e0, e1, e2, e3);
             if(M > 2)
             {
-                e1 = cmul(e1, __ldg(t + j));
-                e2 = cmul(e2, __ldg(t + 2 * j));
-                e3 = cmul(e3, __ldg(t + 3 * j));
+                e1 = cmul(e1, t[j]);
+                e2 = cmul(e2, t[2 * j]);
+                e3 = cmul(e3, t[3 * j]);
             }
         }
         else
         {
             if(M > 2)
             {
-                e1 = cmul_conj(e1, __ldg(t + j));
-                e2 = cmul_conj(e2, __ldg(t + 2 * j));
-                e3 = cmul_conj(e3, __ldg(t + 3 * j));
+                e1 = cmul_conj(e1, t[j]);
+                e2 = cmul_conj(e2, t[2 * j]);
+                e3 = cmul_conj(e3, t[3 * j]);
             }
             dit4(e0, e1, e2, e3);
         }
@@ -286,6 +287,7 @@ namespace pb
         static constexpr int ROUNDS = 4 / PAIRS;
         static constexpr int THREADS = PAIRS * T;
         static constexpr int NPAD = pad(N);
+        static constexpr bool TW_SMEM = LOG2N <= 12;                      // 8192 points: the tables stay in global memory
     };
 
     struct filter_batch
@@ -297,20 +299,34 @@ namespace pb
     template <int LOG2N, bool TRANSPOSED>
     __global__ void __launch_bounds__(plan<LOG2N>::THREADS, plan<LOG2N>::THREADS <= 256 ? 2 : 1)
     filter_kernel(const filter_batch io, float* dst_stack, uint32_t first_slot, size_t slot_floats, uint32_t dim_x,
-                  uint32_t dim_y, const float* __restrict__ knp, const float2* __restrict__ tw, weight_params w,
-                  uint32_t dst_pitch, uint32_t layout)
+                  uint32_t dim_y, uint32_t n_proj, const float* __restrict__ knp, const float2* __restrict__ tw,
+                  weight_params w, uint32_t dst_pitch, uint32_t layout)
     {
         using P = plan<LOG2N>;
         constexpr int N = P::N;
+        constexpr int TWC = P::TW_SMEM ? 3 * (2 * N - 8) / 4 : 0;   // entries of the compact twiddle tables kept on chip
         extern __shared__ __align__(16) unsigned char smem_raw[];
-        float* stage = reinterpret_cast<float*>(smem_raw + sizeof(float2) * P::NPAD * P::PAIRS); // [dim_x][kStagePitch]
+        const float2* const twc = P::TW_SMEM ? reinterpret_cast<const float2*>(smem_raw) : tw;
+        unsigned char* const work = smem_raw + sizeof(float2) * TWC;
+        float* stage = reinterpret_cast<float*>(work + sizeof(float2) * P::NPAD * P::PAIRS); // [dim_x][kStagePitch]
 
         const int lp = threadIdx.x / P::T;                 // row pair slot inside this round
         const int b = threadIdx.x % P::T;                  // thread index inside the transform
-        float2* x = reinterpret_cast<float2*>(smem_raw) + lp * P::NPAD;
+        float2* x = reinterpret_cast<float2*>(work) + lp * P::NPAD;
 
-        const float* src = io.src[blockIdx.y];
-        const uint32_t row_base = blockIdx.x * kRowsPerCta;
+        // persistent CTA: the twiddle tables are fetched once, then the CTA walks over its (projection, 8-row
+        // block) work items
+        for(int i = threadIdx.x; i < TWC; i += P::THREADS)
+            reinterpret_cast<float2*>(smem_raw)[i] = __ldg(tw + i);
+        __syncthreads();
+
+        const uint32_t blocks_per_proj = (dim_y + kRowsPerCta - 1) / kRowsPerCta;
+        #pragma unroll 1
+        for(uint32_t item = blockIdx.x; item < blocks_per_proj * n_proj; item += gridDim.x)
+        {
+        const uint32_t proj = item / blocks_per_proj;
+        const float* src = io.src[proj];
+        const uint32_t row_base = (item % blocks_per_proj) * kRowsPerCta;
 
         #pragma unroll 1
         for(int round = 0; round < P::ROUNDS; ++round)
@@ -355,7 +371,7 @@ namespace pb
                 }
                 e[k] = make_float2(a, c);
             }
-            group16<LOG2N, LOG2N, false>(e, b, tw);
+            group16<LOG2N, LOG2N, false>(e, b, twc);
             float2* const x1 = x + group_base<LOG2N>(b);
             #pragma unroll
             for(int k = 0; k < 16; ++k)
@@ -370,7 +386,7 @@ namespace pb
                 #pragma unroll
                 for(int k = 0; k < 16; ++k)
                     e[k] = x2[group_off<M>(k)];
-                group16<LOG2N, M, false>(e, b & ((1 << (M - 4)) - 1), tw);
+                group16<LOG2N, M, false>(e, b & ((1 << (M - 4)) - 1), twc);
                 #pragma unroll
                 for(int k = 0; k < 16; ++k)
                     x2[group_off<M>(k)] = e[k];
@@ -378,18 +394,18 @@ namespace pb
             }
             if constexpr(P::LONE)
             {
-                lone_group<LOG2N, P::LOW, false>(x, b, tw);
+                lone_group<LOG2N, P::LOW, false>(x, b, twc);
                 __syncthreads();
             }
 
             // ---- middle: last forward passes, K/N, first inverse passes ------------------------------------------------
-            middle_group<LOG2N>(x, knp, b, tw);
+            middle_group<LOG2N>(x, knp, b, twc);
             __syncthreads();
 
             // ---- outer groups, inverse --------------------------------------------------------------------------------
             if constexpr(P::LONE)
             {
-                lone_group<LOG2N, P::LOW, true>(x, b, tw);
+                lone_group<LOG2N, P::LOW, true>(x, b, twc);
                 __syncthreads();
             }
             if constexpr(P::DOUBLES == 2)
@@ -399,7 +415,7 @@ namespace pb
                 #pragma unroll
                 for(int k = 0; k < 16; ++k)
                     e[k] = x2[group_off<M>(k)];
-                group16<LOG2N, M, true>(e, b & ((1 << (M - 4)) - 1), tw);
+                group16<LOG2N, M, true>(e, b & ((1 << (M - 4)) - 1), twc);
                 #pragma unroll
                 for(int k = 0; k < 16; ++k)
                     x2[group_off<M>(k)] = e[k];
@@ -408,7 +424,7 @@ namespace pb
             #pragma unroll
             for(int k = 0; k < 16; ++k)
                 e[k] = x1[group_off<LOG2N>(k)];
-            group16<LOG2N, LOG2N, true>(e, b, tw);
+            group16<LOG2N, LOG2N, true>(e, b, twc);
 
             // ---- keep the first dim_x samples (k < 8; the rest is never computed) ------------------------------------------
             if(TRANSPOSED)
@@ -423,7 +439,7 @@ namespace pb
             }
             else
             {
-                float* dst = io.dst[blockIdx.y];
+                float* dst = io.dst[proj];
                 #pragma unroll
                 for(int k = 0; k < 8; ++k)
                 {
@@ -442,7 +458,7 @@ namespace pb
 
         if(TRANSPOSED)
         {
-            float* dst = dst_stack + slot_floats * (first_slot + blockIdx.y);
+            float* dst = dst_stack + slot_floats * (first_slot + proj);
             if(layout == kLayoutPlain)
             {
                 // 4 lanes cover the 8 staged rows of one sample: 32 contiguous bytes in the stack slot
@@ -480,6 +496,8 @@ namespace pb
                 }
             }
         }
+        __syncthreads(); // the staging tile and the transform buffers are reused by the next work item
+        }
     }
 
     template <int LOG2N>
@@ -489,20 +507,26 @@ namespace pb
                               uint32_t layout)
     {
         using P = plan<LOG2N>;
-        const size_t smem = sizeof(float2) * P::NPAD * P::PAIRS + (transposed ? sizeof(float) * kStagePitch * dim_x : 0);
-        const dim3 grid((dim_y + kRowsPerCta - 1) / kRowsPerCta, count);
+        constexpr size_t twc_bytes = P::TW_SMEM ? sizeof(float2) * (3 * (2 * P::N - 8) / 4) : 0;
+        const size_t smem = twc_bytes + sizeof(float2) * P::NPAD * P::PAIRS
+                          + (transposed ? sizeof(float) * kStagePitch * dim_x : 0);
+        const uint32_t items = ((dim_y + kRowsPerCta - 1) / kRowsPerCta) * count;
+        // persistent grid: as many CTAs as can be resident (two per SM when threads/registers/shared memory allow)
+        const uint32_t per_sm = (P::THREADS <= 256 && 2 * smem <= 220u * 1024u) ? 2u : 1u;
+        const uint32_t grid = std::min<uint32_t>(items, per_sm * static_cast<uint32_t>(ctx->sm_count));
         if(transposed)
         {
             auto kern = filter_kernel<LOG2N, true>;
             PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            kern<<<grid, P::THREADS, smem, ctx->compute>>>(io, d_stack, first_slot, slot_floats, dim_x, dim_y, f->d_knp,
+            kern<<<grid, P::THREADS, smem, ctx->compute>>>(io, d_stack, first_slot, slot_floats, dim_x, dim_y, count, f->d_knp,
                                                           f->d_twc, w, pitch, layout);
         }
         else
         {
             auto kern = filter_kernel<LOG2N, false>;
             PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
-            kern<<<grid, P::THREADS, smem, ctx->compute>>>(io, nullptr, 0u, 0, dim_x, dim_y, f->d_knp, f->d_twc, w, 0u, kLayoutPlain);
+            kern<<<grid, P::THREADS, smem, ctx->compute>>>(io, nullptr, 0u, 0, dim_x, dim_y, count, f->d_knp, f->d_twc, w, 0u,
+                                                          kLayoutPlain);
         }
         PB_CUDA(cudaGetLastError());
         ++ctx->launches;

@@ -87,7 +87,7 @@ class MultiGpuReconstructor:
             self._ext_stream = torch.cuda.ExternalStream(self.ctx.stream(), device=torch.device("cuda", device))
             self._comm_stream = torch.cuda.Stream(device=torch.device("cuda", device), priority=-1)
         else:
-            self.d_stack = self.ctx.dev_alloc(self.slots * self.slot_bytes)
+            self.d_stack = self.ctx.stack_alloc(det.n_row, det.n_col, self.slots)
         self.d_raw = None
         self.h_raw = None
         self.h_slab = capi.PinnedArray((plan.slab_dz, vol.dim_y, vol.dim_x))
@@ -242,7 +242,7 @@ class MultiGpuReconstructor:
         self.ctx.filter_destroy(self.filter)
         self.ctx.volume_free(self.d_vol)
         if self.dist is None:
-            self.ctx.dev_free(self.d_stack)
+            self.ctx.stack_free(self.d_stack)
         if self.d_raw is not None:
             self.ctx.dev_free(self.d_raw)
         if self.h_raw is not None:

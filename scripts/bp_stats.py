@@ -14,7 +14,7 @@ if natural:
 ctx = capi.Context(0)
 n = 64
 slot_bytes, _ = capi.stack_slot_bytes(det.n_row, det.n_col)
-stack = ctx.dev_alloc(n * slot_bytes)
+stack = ctx.stack_alloc(det.n_row, det.n_col, n)
 sc = np.array([angle_sin_cos(i * (n_proj // n), det) for i in range(n)], dtype=np.float32)
 dims = (vol.dim_x, vol.dim_y, vol.dim_z)
 v = ctx.volume_alloc(*dims)

@@ -18,7 +18,7 @@ for n_row, n_col in [(96, 96), (100, 37), (256, 64), (1024, 16), (2048, 8)]:
         if layout == 1 and n_row <= 64:
             continue
         d = ctx.dev_alloc(p.nbytes); ctx.proj_h2d(p, d, n_row, n_col)
-        st = ctx.dev_alloc(slot_bytes * 2)
+        st = ctx.stack_alloc(n_row, n_col, 2)
         ctx.filter_to_stack(d, det, f, st, 1, layout)
         out = np.empty((n_row, pitch), np.float32)
         ctx.proj_d2h(st + slot_bytes, out, pitch, n_row)
@@ -27,5 +27,5 @@ for n_row, n_col in [(96, 96), (100, 37), (256, 64), (1024, 16), (2048, 8)]:
         got = out[:, :n_col].T
         err = np.abs(got - ref).max() / np.abs(ref).max()
         print(n_row, n_col, "layout", layout, "rel err", err)
-        ctx.dev_free(d); ctx.dev_free(st)
+        ctx.dev_free(d); ctx.stack_free(st)
     ctx.filter_destroy(f)

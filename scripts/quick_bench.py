@@ -35,7 +35,7 @@ raw = ctx.dev_alloc(n * a.det * a.det * 4)
 r = 0.9 * phantom.fov_radius(a.det, l_px, 0, 500, 500)
 ctx.phantom_project(phantom.scaled_ellipsoids(phantom.SHEPP_LOGAN_3D, r), det, 0, n, raw)
 slot_bytes, pitch = capi.stack_slot_bytes(a.det, a.det)
-stack = ctx.dev_alloc(n * slot_bytes)
+stack = ctx.stack_alloc(a.det, a.det, n)
 filt = ctx.filter_create(capi.filter_size(a.det), l_px)
 sc = np.array([angle_sin_cos(i, det) for i in range(n)], dtype=np.float32)
 dims = (vol.dim_x, vol.dim_y, vol.dim_z)

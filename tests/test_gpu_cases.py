@@ -160,7 +160,7 @@ def test_full_size_config2_fast_kernel_against_exact_kernel(ctx):
     ell = phantom.scaled_ellipsoids(phantom.SHEPP_LOGAN_3D, 0.9 * phantom.fov_radius(n, l_px, 0, 500, 500))
     ctx.phantom_project(ell, det, 0, n_proj, raw)
     slot_bytes, _ = capi.stack_slot_bytes(n, n)
-    stack = ctx.dev_alloc(n_proj * slot_bytes)
+    stack = ctx.stack_alloc(n, n, n_proj)
     filt = ctx.filter_create(capi.filter_size(n), l_px)
     layout = capi.choose_stack_layout(det, vol)
     assert layout == capi.LAYOUT_SPLIT2
@@ -176,7 +176,7 @@ def test_full_size_config2_fast_kernel_against_exact_kernel(ctx):
         ctx.volume_free(v)
     ctx.set_option("bp_kernel", 0)
     ctx.filter_destroy(filt)
-    ctx.dev_free(stack)
+    ctx.stack_free(stack)
     ctx.dev_free(raw)
     c = contrast(n_proj)
     mx, rms = errors(out[2], out[1], c)
@@ -199,12 +199,12 @@ def test_filter_to_stack_layouts(ctx, port, n_row, n_col, layout):
     slot_bytes, pitch = capi.stack_slot_bytes(n_row, n_col)
     d = ctx.dev_alloc(p.nbytes)
     ctx.proj_h2d(p, d, n_row, n_col)
-    st = ctx.dev_alloc(slot_bytes * 2)
+    st = ctx.stack_alloc(n_row, n_col, 2)
     ctx.filter_to_stack(d, det, f, st, 1, layout)
     out = np.empty((n_row, pitch), np.float32)
     ctx.proj_d2h(st + slot_bytes, out, pitch, n_row)
     ctx.dev_free(d)
-    ctx.dev_free(st)
+    ctx.stack_free(st)
     ctx.filter_destroy(f)
     if layout == capi.LAYOUT_SPLIT2:
         plain = np.empty_like(out)
