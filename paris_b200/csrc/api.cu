@@ -82,6 +82,7 @@ extern "C" int paris_b200_ctx_destroy(paris_b200_ctx* ctx)
         if(b.freed) cudaEventDestroy(b.freed);
     }
     if(ctx->stack) cudaFree(ctx->stack);
+    if(ctx->spare_vol) cudaFree(ctx->spare_vol);
     cudaEventDestroy(ctx->h2d_done);
     cudaEventDestroy(ctx->scratch_ev);
     cudaStreamDestroy(ctx->compute);
@@ -404,7 +405,17 @@ extern "C" int paris_b200_volume_alloc(paris_b200_ctx* ctx, uint32_t dim_x, uint
     PB_TRY(bind(ctx));
     const size_t bytes = static_cast<size_t>(dim_x) * dim_y * dim_z * sizeof(float);
     *d_vol = nullptr;
-    PB_CUDA(cudaMalloc(reinterpret_cast<void**>(d_vol), bytes));
+    if(ctx->spare_vol != nullptr && ctx->spare_vol_bytes == bytes)
+    {
+        *d_vol = ctx->spare_vol;   // (its last use was ordered on the compute stream, as is the memset below)
+        ctx->spare_vol = nullptr;
+        ctx->spare_vol_bytes = 0;
+    }
+    else
+    {
+        PB_CUDA(cudaMalloc(reinterpret_cast<void**>(d_vol), bytes));
+        ctx->vol_bytes[*d_vol] = bytes;
+    }
     PB_CUDA(cudaMemsetAsync(*d_vol, 0, bytes, ctx->compute));
     return PARIS_B200_OK;
 }
@@ -428,8 +439,28 @@ extern "C" int paris_b200_volume_free(paris_b200_ctx* ctx, float* d_vol)
     PB_TRY(bind(ctx));
     if(ctx->pending > 0 && ctx->target.d_vol == d_vol)
         PB_TRY(paris_b200_flush(ctx)); // (simplest way to let go of the batch's raw buffers)
-    PB_CUDA(cudaStreamSynchronize(ctx->compute));
-    PB_CUDA(cudaFree(d_vol));
+    if(ctx->target.d_vol == d_vol)
+    {
+        ctx->target = bp_target{};
+        ctx->flushes_for_target = 0;
+    }
+    // keep the most recent buffer for the next volume_alloc of the same size; release the older spare
+    const auto it = ctx->vol_bytes.find(d_vol);
+    if(it == ctx->vol_bytes.end())
+    {
+        set_error("volume_free: %p was not allocated by this context", static_cast<void*>(d_vol));
+        return PARIS_B200_EINVAL;
+    }
+    float* old = ctx->spare_vol;
+    ctx->spare_vol = d_vol;
+    ctx->spare_vol_bytes = it->second;
+    if(old != nullptr)
+        ctx->vol_bytes.erase(old);
+    if(old != nullptr)
+    {
+        PB_CUDA(cudaStreamSynchronize(ctx->compute));
+        PB_CUDA(cudaFree(old));
+    }
     return PARIS_B200_OK;
 }
 
@@ -792,6 +823,7 @@ extern "C" int paris_b200_flush(paris_b200_ctx* ctx)
     PB_TRY(bind(ctx));
     PB_TRY(run_pending_filter(ctx));
     ++ctx->stat_flush;
+    ++ctx->flushes_for_target;
     const int n = ctx->pending;
     ctx->pending = 0;
     return launch_backproject(ctx, ctx->stack, ctx->stack_slot_floats, ctx->stack_pitch, 0u, static_cast<uint32_t>(n),
@@ -837,8 +869,12 @@ extern "C" int paris_b200_backproject(paris_b200_ctx* ctx, const float* d_proj, 
     t.delta_s_mm = delta_s_mm;
     t.delta_t_mm = delta_t_mm;
 
-    if(ctx->pending > 0 && !same_target(ctx->target, t))
-        PB_TRY(paris_b200_flush(ctx));
+    if(!same_target(ctx->target, t))
+    {
+        if(ctx->pending > 0)
+            PB_TRY(paris_b200_flush(ctx));
+        ctx->flushes_for_target = 0;
+    }
     // (the layout is a function of the target geometry, so it is constant within a batch)
     PB_TRY(ensure_stack(ctx, dim_x, dim_y, choose_stack_layout(*det, *vol_full)));
     ctx->target = t;
@@ -887,7 +923,10 @@ extern "C" int paris_b200_backproject(paris_b200_ctx* ctx, const float* d_proj, 
     ctx->pend_sin[ctx->pending] = sin_phi;
     ctx->pend_cos[ctx->pending] = cos_phi;
     ++ctx->pending;
-    if(ctx->pending >= ctx->bp_batch)
+    // the first batch into a volume is kept short so that the backprojection starts while most of the scan is
+    // still being uploaded; afterwards full batches amortise the volume traffic
+    const int threshold = ctx->flushes_for_target == 0 ? std::min(ctx->bp_batch, 16) : ctx->bp_batch;
+    if(ctx->pending >= threshold)
         PB_TRY(paris_b200_flush(ctx));
     return PARIS_B200_OK;
 }

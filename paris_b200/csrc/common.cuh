@@ -9,6 +9,7 @@
 #include <cstring>
 #include <deque>
 #include <string>
+#include <unordered_map>
 #include <vector>
 
 #include "../../include/paris_b200.h"
@@ -103,6 +104,11 @@ struct paris_b200_ctx
     // pooled raw projection buffers (dev_alloc / dev_free)
     std::vector<pb::raw_buffer> pool;
     std::deque<size_t> free_fifo;   // indices into pool, in release order
+    // one cached volume allocation (volume_free keeps the last buffer, volume_alloc reuses it if the size matches):
+    // the reference allocates and frees the slab once per task (src/main.cpp:95,107)
+    std::unordered_map<float*, size_t> vol_bytes;   // every live volume allocation of this context
+    float* spare_vol = nullptr;
+    size_t spare_vol_bytes = 0;
 
     // filtered stack owned by the context (deferred backprojection)
     float* stack = nullptr;
@@ -112,6 +118,7 @@ struct paris_b200_ctx
     // pending batch
     pb::bp_target target{};
     int pending = 0;
+    int flushes_for_target = 0;   // batches already launched into target.d_vol (the first one is kept short)
     float pend_sin[pb::kMaxBatch];
     float pend_cos[pb::kMaxBatch];
     // raw projections of the pending batch whose fused weight+filter launch is deferred to the flush
