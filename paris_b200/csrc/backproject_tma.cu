@@ -366,7 +366,7 @@ namespace pb
     }
 
     template <class CFG>
-    __global__ void __launch_bounds__(CFG::THREADS, 1)
+    __global__ void __launch_bounds__(CFG::THREADS, CFG::THREADS <= 256 ? 2 : 1)
     bp_tma_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ vol, const bp_geometry g,
                   const bp_angles ang, const uint32_t first_slot)
     {
@@ -750,11 +750,16 @@ namespace pb
     using cfg_fine         = tile_cfg<16, 16, 2, 16, 40, 96, 6>;          // ~1 detector row per voxel (PARIS-derived volumes)
     using cfg_coarse       = tile_cfg<16, 16, 2, 16, 64, 164, 4>;         // ~2 rows per voxel, plain stack layout
     using cfg_coarse_split = tile_cfg<16, 16, 2, 16, 64, 168, 4, true>;   // ~2 rows per voxel, parity-split stack layout
+    // half tiles: 256 threads, two CTAs per SM, so that one CTA's barriers, table building and volume tile
+    // traffic are covered by the other CTA's interpolation work
+    using cfg_fine_half         = tile_cfg<16, 8, 2, 16, 32, 96, 5>;
+    using cfg_coarse_split_half = tile_cfg<16, 8, 2, 16, 52, 168, 3, true>;
 
     template <class CFG>
-    static bool fits_cfg(const footprint& f)
+    static bool fits_cfg(const bp_geometry& g)
     {
-        return f.need_h <= CFG::BH && f.need_v + (CFG::SPLIT ? 7 : 3) <= CFG::BV;
+        const footprint f = tile_footprint(g, CFG::TX, CFG::TY, CFG::TZ);
+        return f.ok && f.need_h <= CFG::BH && f.need_v + (CFG::SPLIT ? 7 : 3) <= CFG::BV;
     }
 
 #ifdef PB_BP_STATS
@@ -772,32 +777,33 @@ namespace pb
                       const bp_geometry& g, const bp_angles& a, float* d_vol, bool required, bool* handled)
     {
         *handled = false;
-        const footprint f = tile_footprint(g, 16, 16, 64);
         const bool aligned = (reinterpret_cast<uintptr_t>(d_stack) % 16u) == 0u && (g.pitch % 8u) == 0u;
-        if(f.ok && aligned)
+        const bool half = ctx->bp_tile != 1;   // 0 = automatic (half tiles when they fit), 1 = full tiles only
+#define PB_TRY_CFG(CFG)                                                                            \
+        if(fits_cfg<CFG>(g))                                                                       \
+        {                                                                                          \
+            PB_TRY(launch_cfg<CFG>(ctx, d_stack, slot_floats, first, g, a, d_vol));                \
+            *handled = true;                                                                       \
+            return PARIS_B200_OK;                                                                  \
+        }
+        if(aligned)
         {
             if(g.layout == kLayoutSplit2)
             {
-                if(fits_cfg<cfg_coarse_split>(f))
-                {
-                    PB_TRY(launch_cfg<cfg_coarse_split>(ctx, d_stack, slot_floats, first, g, a, d_vol));
-                    *handled = true;
-                    return PARIS_B200_OK;
-                }
+                if(half)
+                    PB_TRY_CFG(cfg_coarse_split_half)
+                PB_TRY_CFG(cfg_coarse_split)
             }
-            else if(fits_cfg<cfg_fine>(f))
+            else
             {
-                PB_TRY(launch_cfg<cfg_fine>(ctx, d_stack, slot_floats, first, g, a, d_vol));
-                *handled = true;
-                return PARIS_B200_OK;
-            }
-            else if(fits_cfg<cfg_coarse>(f))
-            {
-                PB_TRY(launch_cfg<cfg_coarse>(ctx, d_stack, slot_floats, first, g, a, d_vol));
-                *handled = true;
-                return PARIS_B200_OK;
+                if(half)
+                    PB_TRY_CFG(cfg_fine_half)
+                PB_TRY_CFG(cfg_fine)
+                PB_TRY_CFG(cfg_coarse)
             }
         }
+#undef PB_TRY_CFG
+        const footprint f = tile_footprint(g, 16, 16, 64);
         if(required)
         {
             set_error("geometry does not fit the TMA kernel's tiles (footprint %d x %d detector cells per tile, layout %u)",

@@ -100,6 +100,7 @@ struct paris_b200_ctx
     // options
     int bp_batch = 64;
     int bp_kernel = 0;
+    int bp_tile = 0;     // 0: half tiles (two CTAs per SM) when the footprint fits, 1: full tiles only
 
     // pooled raw projection buffers (dev_alloc / dev_free)
     std::vector<pb::raw_buffer> pool;

@@ -15,6 +15,7 @@ ap.add_argument("--kernel", type=int, default=0)
 ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--layout", type=int, default=-1)
+ap.add_argument("--tile", type=int, default=0)
 ap.add_argument("--check", action="store_true", help="compare against the exact kernel")
 a = ap.parse_args()
 
@@ -30,6 +31,7 @@ print("volume", vol.dim_x, vol.dim_y, vol.dim_z, vol.l_vx_x)
 ctx = capi.Context(0)
 ctx.set_option("bp_batch", a.batch)
 ctx.set_option("bp_kernel", a.kernel)
+ctx.set_option("bp_tile", a.tile)
 n = a.proj
 raw = ctx.dev_alloc(n * a.det * a.det * 4)
 r = 0.9 * phantom.fov_radius(a.det, l_px, 0, 500, 500)
