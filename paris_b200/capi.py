@@ -12,7 +12,7 @@ import os
 import numpy as np
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "libparis_b200.so")
+LIB_PATH = os.environ.get("PARIS_B200_LIB") or os.path.join(_HERE, "libparis_b200.so")   # (override: kernel A/B experiments)
 
 OK, EINVAL, ECUDA, ENOMEM, ESTATE = 0, 1, 2, 3, 4
 BP_FUSE_WEIGHT_FILTER = 1

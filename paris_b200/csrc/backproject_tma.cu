@@ -51,6 +51,7 @@ namespace pb
         static constexpr size_t SMEM = size_t(STAGES) * STAGE_BYTES + 2 * TAB_BYTES + kMaxBatch * 16 + STAGES * 8 + 128;
         // fixed point: rows are carried with a bias of BV so that they stay non-negative on boundary tiles
         static constexpr int FRAC = 23;
+        static constexpr int ROW_SHIFT = SPLIT ? FRAC - 1 : FRAC;   // the split layout's word counts row pairs
         static constexpr int BIAS = BV;
         static_assert(COLS % CPW == 0, "columns per warp must divide the tile");
         static_assert(CPW % TX == 0 || TX % CPW == 0, "a warp's columns must be whole or partial x-runs");
@@ -277,7 +278,7 @@ namespace pb
     // The four samples of one voxel update and its y-weight (weight of q?2 against q?1).
     struct update_samples
     {
-        float q11, q12, q21, q22, fy;
+        float q11, q12, q21, q22, fy;   // fy = weight of q?2 against q?1
     };
 
     template <class CFG>
@@ -299,14 +300,16 @@ namespace pb
             // Rows r and r+1 are one even and one odd row.  With r = 2k + p (p = parity):
             //   odd  row sits in the odd plane at pair index k,
             //   even row sits in the even plane at pair index k + p,
-            // and the odd row's weight is fy for p = 0 (it is row r+1), 1 - fy for p = 1 (it is row r).
-            // Across a warp both planes are read with (nearly) unit stride.  Here q?1 = even row, q?2 = odd row.
-            const uint32_t pair4 = (vrow >> (CFG::FRAC - 1)) & ~3u;               // 4 * k
-            const uint32_t par4 = (vrow >> (CFG::FRAC - 2)) & 4u;                 // 4 * p
-            const uint32_t a_odd = base + pair4;                                  // base points at the odd plane
+            // and the odd row's weight is fy for p = 0 (it is row r+1), 1 - fy for p = 1 (it is row r), i.e.
+            // 1 - |t - 1| with t = p + fy the position inside the pair.  The fixed-point word counts ROW PAIRS
+            // here (k.t/2), so that t/2 is its fraction.  Across a warp both planes are read with (nearly)
+            // unit stride.  Here q?1 = even row, q?2 = odd row.
+            const uint32_t par4 = (vrow >> (CFG::FRAC - 3)) & 4u;                 // 4 * p
+            // base + 4 * k: shift-and-add (one LEA.HI), then the two fraction bits that came along are cleared
+            const uint32_t a_odd = (base + (vrow >> (CFG::FRAC - 2))) & ~3u;      // base points at the odd plane
             const uint32_t a_even = a_odd + par4;
-            const float f1 = __uint_as_float(and_or(vrow, frac_mask, one_bits));  // 1 + fy
-            u.fy = par4 ? 2.0f - f1 : f1 - 1.0f;
+            const float f1 = __uint_as_float(and_or(vrow, frac_mask, one_bits));  // 1 + t/2
+            u.fy = 1.0f - fabsf(fmaf(2.0f, f1, -3.0f));                           // 1 - |t - 1|
             u.q11 = lds_f32(a_even - 4 * CFG::BVH);
             u.q21 = lds_f32(a_even - 4 * CFG::BVH + 4 * CFG::BV);
             u.q12 = lds_f32(a_odd);
@@ -315,7 +318,10 @@ namespace pb
         return u;
     }
 
-    template <class CFG, bool MIXED>
+    // MIXED: the tile has voxels on both sides of the detector border (per-slice validity from the table);
+    // CLAMP: additionally the box may not cover the tile's rows (never the case for launches that passed the
+    // host-side footprint check; kept as the safe path)
+    template <class CFG, bool MIXED, bool CLAMP = false>
     __device__ __forceinline__ void consume(uint64_t (&acc)[CFG::CPW], const float4* __restrict__ tab_a,
                                             const float* __restrict__ tab_b, const uint32_t* __restrict__ tab_c,
                                             int col0, uint32_t lane)
@@ -328,26 +334,26 @@ namespace pb
         #pragma unroll
         for(int i = 0; i < CFG::CPW; ++i)
         {
-            // {stage address of (column x1, row -BIAS), v_base (9.23, biased), dv (9.23), w*(1-fx)}, w*fx,
-            // valid slices (first | count << 8; boundary tiles only)
+            // {stage address of (column x1, row -BIAS), v_base (fixed point, biased), dv (fixed point), w*(1-fx)},
+            // w*fx, valid slices (first | count << 8; boundary tiles only)
             const float4 ea = tab_a[col0 + i];
             const float wb = tab_b[col0 + i];
             const uint32_t base = __float_as_uint(ea.x);
             const uint32_t dv = __float_as_uint(ea.z);
             uint32_t v0 = dv * lane + __float_as_uint(ea.y);     // slice `lane`
             uint32_t v1 = v0 + (dv << 5);                        // slice `lane + 32`: 32 steps of dv further
-            if(MIXED)
+            if(CLAMP)
             {
-                // rows of slices outside the valid interval may lie outside the staged box: keep the address
-                // inside, the value is discarded below
-                const uint32_t lo = static_cast<uint32_t>(CFG::BIAS) << CFG::FRAC;
-                const uint32_t hi = static_cast<uint32_t>(CFG::BIAS + CFG::BV - 2) << CFG::FRAC;
+                // rows may lie outside the staged box: keep the address inside, the value is discarded below
+                const uint32_t lo = static_cast<uint32_t>(CFG::BIAS) << CFG::ROW_SHIFT;
+                const uint32_t hi = static_cast<uint32_t>(CFG::BIAS + CFG::BV - 2) << CFG::ROW_SHIFT;
                 v0 = min(max(v0, lo), hi);
                 v1 = min(max(v1, lo), hi);
             }
             const update_samples s0 = fetch<CFG>(base, v0, frac_mask, one_bits);
             const update_samples s1 = fetch<CFG>(base, v1, frac_mask, one_bits);
             // both slices at once: g1 = wa*q11 + wb*q21, g2 = wa*q12 + wb*q22, d = g1 + fy*(g2 - g1)
+            // (src/openmp/backprojection.cpp:73-83 with the weight 0.5*u^2 of :147 folded into wa, wb)
             const uint64_t wa2 = pack2(ea.w, ea.w), wb2 = pack2(wb, wb);
             const uint64_t g1 = fma2(wb2, pack2(s0.q21, s1.q21), mul2(wa2, pack2(s0.q11, s1.q11)));
             const uint64_t g2 = fma2(wb2, pack2(s0.q22, s1.q22), mul2(wa2, pack2(s0.q12, s1.q12)));
@@ -373,9 +379,9 @@ namespace pb
         extern __shared__ __align__(128) unsigned char smem[];
         unsigned char* stage_mem = smem;                                                   // STAGES x BH x BV floats
         float4* tab_a = reinterpret_cast<float4*>(smem + size_t(CFG::STAGES) * CFG::STAGE_BYTES);
-        float* tab_b = reinterpret_cast<float*>(reinterpret_cast<unsigned char*>(tab_a) + 2 * CFG::COLS * 16);
+        float* tab_b = reinterpret_cast<float*>(tab_a + 2 * CFG::COLS);
         uint32_t* tab_c = reinterpret_cast<uint32_t*>(tab_b + 2 * CFG::COLS);
-        box_origin* origin = reinterpret_cast<box_origin*>(reinterpret_cast<unsigned char*>(tab_c) + 2 * CFG::COLS * 4);
+        box_origin* origin = reinterpret_cast<box_origin*>(tab_c + 2 * CFG::COLS);
         uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(origin) + kMaxBatch * 16);
 
         const int tid = threadIdx.x;
@@ -497,7 +503,7 @@ namespace pb
             z_m0 = centered_d(z0, g.full_z, g.l_vx_z);
         }
         const uint32_t stage_base0 = smem_u32(stage_mem);
-        constexpr double kOne = static_cast<double>(1u << CFG::FRAC);
+        constexpr double kOne = static_cast<double>(1u << CFG::ROW_SHIFT);
 
         auto build = [&](int p) {
             const box_origin o = origin[p];
@@ -507,7 +513,7 @@ namespace pb
             const float x1 = floorf(ct.h);
             const bool valid_x = x1 >= 0.f && x1 + 1.f < static_cast<float>(g.p_dim_x);
             // a dead entry reads row 0 of column 0 of the box with zero weights
-            float4 ea = make_float4(0.f, __uint_as_float(static_cast<uint32_t>(CFG::BIAS) << CFG::FRAC),
+            float4 ea = make_float4(0.f, __uint_as_float(static_cast<uint32_t>(CFG::BIAS) << CFG::ROW_SHIFT),
                                     __uint_as_float(0u), 0.f);
             float eb = 0.f;
             uint32_t ec = static_cast<uint32_t>(CFG::TZ) << 8;   // every slice valid
@@ -581,7 +587,12 @@ namespace pb
             if(o.all_valid == 1)
                 consume<CFG, false>(acc, ta, tb, tc, col0, lane);
             else if(o.all_valid == 0)
-                consume<CFG, true>(acc, ta, tb, tc, col0, lane);
+            {
+                if(o.fits)
+                    consume<CFG, true>(acc, ta, tb, tc, col0, lane);
+                else
+                    consume<CFG, true, true>(acc, ta, tb, tc, col0, lane);
+            }
 
             __syncthreads(); // stage and table[p&1] are free again; table[(p+1)&1] is complete
             if(tid == 0 && p + CFG::STAGES < count)
