@@ -321,11 +321,33 @@ namespace pb
         __syncthreads();
 
         const uint32_t blocks_per_proj = (dim_y + kRowsPerCta - 1) / kRowsPerCta;
+        const uint32_t n_items = blocks_per_proj * n_proj;
+
+        // Raw samples of the NEXT round travel in registers: the loads are issued right after the current
+        // round's first butterfly group and are consumed one round later, so their HBM latency is covered
+        // by four shared-memory phases of arithmetic instead of stalling the warp at the top of every round.
+        float pa[8], pc[8];
+        auto prefetch = [&](uint32_t item, int round) {
+            const uint32_t proj = item / blocks_per_proj;
+            const uint32_t row0 = (item % blocks_per_proj) * kRowsPerCta + 2u * static_cast<uint32_t>(round * P::PAIRS + lp);
+            const bool has0 = row0 < dim_y, has1 = row0 + 1u < dim_y;
+            const float* const src0 = io.src[proj] + static_cast<size_t>(row0) * dim_x + b;
+            const float* const src1 = src0 + dim_x;
+            #pragma unroll
+            for(int k = 0; k < 8; ++k)
+            {
+                const uint32_t i = b + k * (N / 16);
+                pa[k] = (i < dim_x && has0) ? __ldg(src0 + k * (N / 16)) : 0.f;
+                pc[k] = (i < dim_x && has1) ? __ldg(src1 + k * (N / 16)) : 0.f;
+            }
+        };
+        if(blockIdx.x < n_items)
+            prefetch(blockIdx.x, 0);
+
         #pragma unroll 1
-        for(uint32_t item = blockIdx.x; item < blocks_per_proj * n_proj; item += gridDim.x)
+        for(uint32_t item = blockIdx.x; item < n_items; item += gridDim.x)
         {
         const uint32_t proj = item / blocks_per_proj;
-        const float* src = io.src[proj];
         const uint32_t row_base = (item % blocks_per_proj) * kRowsPerCta;
 
         #pragma unroll 1
@@ -336,40 +358,37 @@ namespace pb
             const bool has0 = row0 < dim_y, has1 = row1 < dim_y;
 
             float2 e[16];
-            // ---- first group: points b + k*N/16 straight from global memory; k >= 8 is the zero padding ----------
+            // ---- first group: points b + k*N/16 (prefetched); k >= 8 is the zero padding -----------------------------
             // cosine weight d_sd / sqrt(d_sd^2 + h_s^2 + v_t^2) (src/openmp/weighting.cpp:44-52) with one rsqrt per
             // pixel; the stand-alone weight kernel keeps the reference's exact operation sequence, here a 1-ulp
             // difference disappears in the float32 transform that follows
             const float v0 = fmaf(static_cast<float>(row0), w.l_px_col, 0.5f * w.l_px_col + w.v_min);
             const float v1 = v0 + w.l_px_col;
             const float c0 = fmaf(v0, v0, w.d_sd * w.d_sd), c1 = fmaf(v1, v1, w.d_sd * w.d_sd);
-            const float* const src0 = src + static_cast<size_t>(row0) * dim_x + b;
-            const float* const src1 = src0 + dim_x;
             #pragma unroll
             for(int k = 0; k < 16; ++k)
             {
                 float a = 0.f, c = 0.f;
                 if(k < 8)
                 {
-                    const uint32_t i = b + k * (N / 16);
-                    if(i < dim_x)
+                    a = pa[k];
+                    c = pc[k];
+                    if(w.enable)
                     {
+                        const uint32_t i = b + k * (N / 16);
                         const float hs = fmaf(static_cast<float>(i), w.l_px_row, 0.5f * w.l_px_row + w.h_min);
-                        if(has0)
-                        {
-                            a = __ldg(src0 + k * (N / 16));
-                            if(w.enable)
-                                a *= w.d_sd * rsqrtf(fmaf(hs, hs, c0));
-                        }
-                        if(has1)
-                        {
-                            c = __ldg(src1 + k * (N / 16));
-                            if(w.enable)
-                                c *= w.d_sd * rsqrtf(fmaf(hs, hs, c1));
-                        }
+                        a *= w.d_sd * rsqrtf(fmaf(hs, hs, c0));
+                        c *= w.d_sd * rsqrtf(fmaf(hs, hs, c1));
                     }
                 }
                 e[k] = make_float2(a, c);
+            }
+            {
+                // next round of this item, or the first round of this CTA's next item
+                const bool last_round = round + 1 == P::ROUNDS;
+                const uint32_t nitem = last_round ? item + gridDim.x : item;
+                if(nitem < n_items)
+                    prefetch(nitem, last_round ? 0 : round + 1);
             }
             group16<LOG2N, LOG2N, false>(e, b, twc);
             float2* const x1 = x + group_base<LOG2N>(b);
