@@ -245,6 +245,17 @@ int paris_b200_backproject_stack(paris_b200_ctx* ctx, const float* d_stack, uint
                                  uint32_t v_offset, const paris_b200_detector_geometry* det,
                                  const paris_b200_volume_geometry* vol_full, int enable_roi,
                                  const paris_b200_roi* roi, uint32_t layout);
+/* the same, followed by the download of the volume into h_dst (pinned host memory, v_dim_x*v_dim_y*v_dim_z
+ * floats): the work is cut into z-chunks at the kernel's tile anchors and the copy of each finished chunk runs
+ * behind the backprojection of the next one (what sink::save's copy_d2h does after the last projection,
+ * /root/reference/src/sink.cpp:76-77, without serialising it behind the whole backprojection).  Returns with the
+ * host copy complete. */
+int paris_b200_backproject_stack_d2h(paris_b200_ctx* ctx, const float* d_stack, uint32_t first, uint32_t count,
+                                     const float* sin_phi, const float* cos_phi,
+                                     float* d_vol, uint32_t v_dim_x, uint32_t v_dim_y, uint32_t v_dim_z,
+                                     uint32_t v_offset, const paris_b200_detector_geometry* det,
+                                     const paris_b200_volume_geometry* vol_full, int enable_roi,
+                                     const paris_b200_roi* roi, uint32_t layout, float* h_dst);
 
 /* ---- synthetic input (bench / tests): analytic cone-beam line integrals of ellipsoids ------ */
 

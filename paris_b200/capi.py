@@ -106,6 +106,9 @@ SIGNATURES = {
                                                    _u32]),
     "paris_b200_backproject_stack": (C.c_int, [_vp, _fp, _u32, _u32, _P(_f), _P(_f), _fp, _u32, _u32, _u32, _u32,
                                                _P(DetectorGeometry), _P(VolumeGeometry), C.c_int, _P(Roi), _u32]),
+    "paris_b200_backproject_stack_d2h": (C.c_int, [_vp, _fp, _u32, _u32, _P(_f), _P(_f), _fp, _u32, _u32, _u32, _u32,
+                                                   _P(DetectorGeometry), _P(VolumeGeometry), C.c_int, _P(Roi), _u32,
+                                                   _fp]),
     "paris_b200_phantom_project": (C.c_int, [_vp, _P(C.c_double), _u32, _P(DetectorGeometry), _u32, _u32, _fp]),
 }
 
@@ -365,6 +368,19 @@ class Context:
                                                    d_vol, v_dims[0], v_dims[1], v_dims[2], v_offset,
                                                    C.byref(det), C.byref(vol_full), int(roi is not None),
                                                    C.byref(roi) if roi is not None else None, layout))
+
+    def backproject_stack_d2h(self, d_stack: int, first: int, count: int, sin_phi: np.ndarray, cos_phi: np.ndarray,
+                              d_vol: int, v_dims, v_offset: int, det: DetectorGeometry, vol_full: VolumeGeometry,
+                              h_dst: int, roi: Roi | None = None, layout: int = LAYOUT_PLAIN):
+        """backproject_stack followed by the download to pinned host memory at h_dst, overlapped chunk by chunk."""
+        sn = np.ascontiguousarray(sin_phi, dtype=np.float32)
+        cs = np.ascontiguousarray(cos_phi, dtype=np.float32)
+        assert sn.size >= count and cs.size >= count
+        check(self._L.paris_b200_backproject_stack_d2h(self.h, d_stack, first, count,
+                                                       sn.ctypes.data_as(_P(_f)), cs.ctypes.data_as(_P(_f)),
+                                                       d_vol, v_dims[0], v_dims[1], v_dims[2], v_offset,
+                                                       C.byref(det), C.byref(vol_full), int(roi is not None),
+                                                       C.byref(roi) if roi is not None else None, layout, h_dst))
 
     def phantom_project(self, ellipsoids_mm: np.ndarray, det: DetectorGeometry, first_idx: int, n_proj: int,
                         d_stack_raw: int):

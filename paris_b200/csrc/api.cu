@@ -546,10 +546,61 @@ extern "C" int paris_b200_vol_h2d(paris_b200_ctx* ctx, const float* h_src, float
     return PARIS_B200_OK;
 }
 
+static int run_pending_filter(paris_b200_ctx* ctx);
+
+// Backproject `count` stack slots into the target and bring the volume to the host, z-chunk by z-chunk: the
+// download of chunk c (copy stream) runs behind the backprojection of chunk c+1 (compute stream).  Chunks end
+// at multiples of 64 slices in GLOBAL slice indices -- the kernel's tile anchors -- so no tile is computed twice
+// and the result is bit-identical to the one-piece launch.  Returns with the host copy complete.
+static int backproject_and_download(paris_b200_ctx* ctx, const float* d_stack, size_t slot_floats, uint32_t pitch,
+                                    uint32_t first, uint32_t count, const float* sn, const float* cs, const bp_target& t,
+                                    uint32_t layout, float* h_dst)
+{
+    const uint32_t off0 = (t.enable_roi ? t.roi.z1 : 0u) + t.v_offset;
+    const size_t slice = static_cast<size_t>(t.v_dim_x) * t.v_dim_y;
+    uint32_t step = 64u;
+    while((t.v_dim_z + step - 1u) / step > 32u)
+        step *= 2u;
+    for(uint32_t z = 0; z < t.v_dim_z;)
+    {
+        const uint32_t end = std::min<uint32_t>(((off0 + z) / step + 1u) * step - off0, t.v_dim_z);
+        bp_target c = t;
+        c.d_vol = t.d_vol + static_cast<size_t>(z) * slice;
+        c.v_dim_z = end - z;
+        c.v_offset = t.v_offset + z;
+        for(uint32_t done = 0; done < count;)
+        {
+            const uint32_t n = std::min<uint32_t>(count - done, static_cast<uint32_t>(ctx->bp_batch));
+            PB_TRY(launch_backproject(ctx, d_stack, slot_floats, pitch, first + done, n, sn + done, cs + done, c, layout));
+            done += n;
+        }
+        PB_CUDA(cudaEventRecord(ctx->scratch_ev, ctx->compute));
+        PB_CUDA(cudaStreamWaitEvent(ctx->copy, ctx->scratch_ev, 0));
+        PB_CUDA(cudaMemcpyAsync(h_dst + static_cast<size_t>(z) * slice, c.d_vol, static_cast<size_t>(end - z) * slice * sizeof(float),
+                                cudaMemcpyDeviceToHost, ctx->copy));
+        z = end;
+    }
+    PB_CUDA(cudaStreamSynchronize(ctx->copy));
+    return PARIS_B200_OK;
+}
+
 extern "C" int paris_b200_vol_d2h(paris_b200_ctx* ctx, const float* d_src, float* h_dst, size_t n_voxels)
 {
     PB_CHECK_ARG(ctx != nullptr && d_src != nullptr && h_dst != nullptr);
     PB_TRY(bind(ctx));
+    const bp_target& t = ctx->target;
+    if(ctx->pending > 0 && t.d_vol == d_src
+       && n_voxels == static_cast<size_t>(t.v_dim_x) * t.v_dim_y * t.v_dim_z)
+    {
+        // the pending batch goes into exactly this volume: overlap its backprojection with the download
+        PB_TRY(run_pending_filter(ctx));
+        ++ctx->stat_flush;
+        ++ctx->flushes_for_target;
+        const uint32_t n = static_cast<uint32_t>(ctx->pending);
+        ctx->pending = 0;
+        return backproject_and_download(ctx, ctx->stack, ctx->stack_slot_floats, ctx->stack_pitch, 0u, n, ctx->pend_sin,
+                                        ctx->pend_cos, t, ctx->stack_layout, h_dst);
+    }
     PB_TRY(paris_b200_flush(ctx));
     PB_CUDA(cudaMemcpyAsync(h_dst, d_src, n_voxels * sizeof(float), cudaMemcpyDeviceToHost, ctx->compute));
     PB_CUDA(cudaStreamSynchronize(ctx->compute));
@@ -882,6 +933,17 @@ extern "C" int paris_b200_backproject(paris_b200_ctx* ctx, const float* d_proj, 
             PB_TRY(paris_b200_flush(ctx));
         ctx->flushes_for_target = 0;
     }
+    else
+    {
+        // A full batch is launched when the NEXT projection arrives, not when it fills: the last batch of a
+        // scan is then still pending when the volume is read back, and vol_d2h() can backproject it slab by
+        // slab with the download of each finished slab running behind the next one.
+        // The first batch into a volume is kept short so that the backprojection starts while most of the scan
+        // is still being uploaded; afterwards full batches amortise the volume traffic.
+        const int threshold = ctx->flushes_for_target == 0 ? std::min(ctx->bp_batch, 16) : ctx->bp_batch;
+        if(ctx->pending >= threshold)
+            PB_TRY(paris_b200_flush(ctx));
+    }
     // (the layout is a function of the target geometry, so it is constant within a batch)
     PB_TRY(ensure_stack(ctx, dim_x, dim_y, choose_stack_layout(*det, *vol_full)));
     ctx->target = t;
@@ -930,11 +992,6 @@ extern "C" int paris_b200_backproject(paris_b200_ctx* ctx, const float* d_proj, 
     ctx->pend_sin[ctx->pending] = sin_phi;
     ctx->pend_cos[ctx->pending] = cos_phi;
     ++ctx->pending;
-    // the first batch into a volume is kept short so that the backprojection starts while most of the scan is
-    // still being uploaded; afterwards full batches amortise the volume traffic
-    const int threshold = ctx->flushes_for_target == 0 ? std::min(ctx->bp_batch, 16) : ctx->bp_batch;
-    if(ctx->pending >= threshold)
-        PB_TRY(paris_b200_flush(ctx));
     return PARIS_B200_OK;
 }
 
@@ -1034,6 +1091,37 @@ extern "C" int paris_b200_backproject_stack(paris_b200_ctx* ctx, const float* d_
         done += n;
     }
     return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_backproject_stack_d2h(paris_b200_ctx* ctx, const float* d_stack, uint32_t first, uint32_t count,
+                                                const float* sin_phi, const float* cos_phi, float* d_vol,
+                                                uint32_t v_dim_x, uint32_t v_dim_y, uint32_t v_dim_z, uint32_t v_offset,
+                                                const paris_b200_detector_geometry* det,
+                                                const paris_b200_volume_geometry* vol_full, int enable_roi,
+                                                const paris_b200_roi* roi, uint32_t layout, float* h_dst)
+{
+    PB_CHECK_ARG(ctx != nullptr && d_stack != nullptr && d_vol != nullptr && det != nullptr && vol_full != nullptr);
+    PB_CHECK_ARG(layout == kLayoutPlain || layout == kLayoutSplit2);
+    PB_CHECK_ARG(sin_phi != nullptr && cos_phi != nullptr && h_dst != nullptr);
+    PB_CHECK_ARG(!enable_roi || roi != nullptr);
+    PB_TRY(bind(ctx));
+    PB_TRY(paris_b200_flush(ctx));
+    bp_target t{};
+    t.d_vol = d_vol;
+    t.v_dim_x = v_dim_x;
+    t.v_dim_y = v_dim_y;
+    t.v_dim_z = v_dim_z;
+    t.v_offset = v_offset;
+    t.det = *det;
+    t.vol_full = *vol_full;
+    t.enable_roi = enable_roi ? 1 : 0;
+    if(enable_roi)
+        t.roi = *roi;
+    t.delta_s_mm = det->delta_s * det->l_px_row;   // src/backprojection.cpp:49-50
+    t.delta_t_mm = det->delta_t * det->l_px_col;
+    const uint32_t pitch = stack_pitch_for(det->n_col);
+    const size_t slot_floats = static_cast<size_t>(pitch) * det->n_row;
+    return backproject_and_download(ctx, d_stack, slot_floats, pitch, first, count, sin_phi, cos_phi, t, layout, h_dst);
 }
 
 extern "C" int paris_b200_phantom_project(paris_b200_ctx* ctx, const double* ellipsoids, uint32_t n_ellipsoids,

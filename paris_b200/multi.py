@@ -142,7 +142,13 @@ class MultiGpuReconstructor:
             self.dist.all_gather_into_tensor(self._torch_stack, mine)
 
     # ---- steps -------------------------------------------------------------------------------------------------
-    def _backproject(self, first: int, count: int):
+    def _backproject(self, first: int, count: int, download: bool = False):
+        if download:
+            # last round of an end-to-end step: the slab goes to the host chunk by chunk behind the kernel
+            self.ctx.backproject_stack_d2h(self.d_stack, first, count, self.sin[first:first + count],
+                                           self.cos[first:first + count], self.d_vol, self.slab_dims, self.plan.offset,
+                                           self.det, self.vol, self.h_slab.ptr, layout=self.layout)
+            return
         self.ctx.backproject_stack(self.d_stack, first, count, self.sin[first:first + count], self.cos[first:first + count],
                                    self.d_vol, self.slab_dims, self.plan.offset, self.det, self.vol, layout=self.layout)
 
@@ -181,7 +187,7 @@ class MultiGpuReconstructor:
                 self._ext_stream.wait_event(gathered[rd - 1])
                 self._backproject((rd - 1) * w * m, w * m)
         self._ext_stream.wait_event(gathered[-1])
-        self._backproject((self.rounds - 1) * w * m, w * m)
+        self._backproject((self.rounds - 1) * w * m, w * m, download=upload)
 
     def step_resident(self, timed: bool = False, overlap: bool = True):
         """raw projections already in HBM -> slab in HBM.  timed (sequential, for the stage breakdown):
@@ -222,7 +228,8 @@ class MultiGpuReconstructor:
             return
         ctx = self.ctx
         if self.m:
-            self._pipelined(upload=True)
+            self._pipelined(upload=True)   # (ends with the overlapped backprojection + download of the last round)
+            return
         else:
             ctx.volume_clear(self.d_vol, *self.slab_dims)
             for i in range(self.my_count):
