@@ -297,7 +297,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         barrier()
 
     # ---- end-to-end steps (host -> host through the reference-shaped loop) ---------------------------------------
-    for _ in range(max(1, args.warmup // 2)):
+    for _ in range(max(1, args.warmup)):
         rec.step_e2e()
     barrier()
     sampler_e2e = ClockSampler(local_rank, 500)

@@ -78,9 +78,11 @@ extern "C" int paris_b200_ctx_destroy(paris_b200_ctx* ctx)
     cudaStreamSynchronize(ctx->copy);
     for(auto& b : ctx->pool)
     {
-        if(b.ptr) cudaFree(b.ptr);
+        if(b.ptr && !b.in_slab) cudaFree(b.ptr);
         if(b.freed) cudaEventDestroy(b.freed);
     }
+    for(void* slab : ctx->pool_slabs)
+        cudaFree(slab);
     if(ctx->stack) cudaFree(ctx->stack);
     if(ctx->spare_vol) cudaFree(ctx->spare_vol);
     cudaEventDestroy(ctx->h2d_done);
@@ -369,6 +371,34 @@ extern "C" int paris_b200_dev_alloc(paris_b200_ctx* ctx, size_t bytes, void** d_
         *d_ptr = b.ptr;
         ctx->free_fifo.erase(it);
         return PARIS_B200_OK;
+    }
+    if(same_size == 0 && bytes >= (1u << 16) && bytes <= (64u << 20))   // (projection-sized requests only)
+    {
+        // first projection buffer of this size: one allocation for the whole pool (a cudaMalloc per buffer costs
+        // about a millisecond each and would be paid during the first reconstruction's uploads)
+        const size_t stride = (bytes + 255u) & ~static_cast<size_t>(255u);
+        void* slab = nullptr;
+        if(cudaMalloc(&slab, stride * cap) == cudaSuccess)
+        {
+            ctx->pool_slabs.push_back(slab);
+            ++ctx->stat_pool_malloc;
+            for(size_t i = 0; i < cap; ++i)
+            {
+                pb::raw_buffer sb{};
+                sb.ptr = static_cast<unsigned char*>(slab) + i * stride;
+                sb.bytes = bytes;
+                sb.in_slab = true;
+                PB_CUDA(cudaEventCreateWithFlags(&sb.freed, cudaEventDisableTiming));
+                ctx->pool.push_back(sb);
+                if(i > 0)
+                    ctx->free_fifo.push_back(ctx->pool.size() - 1u);
+            }
+            pb::raw_buffer& first = ctx->pool[ctx->pool.size() - cap];
+            first.in_use = true;
+            *d_ptr = first.ptr;
+            return PARIS_B200_OK;
+        }
+        (void)cudaGetLastError(); // not enough memory for the whole pool: grow buffer by buffer
     }
     pb::raw_buffer nb{};
     ++ctx->stat_pool_malloc;

@@ -42,6 +42,7 @@ namespace pb
         bool freed_valid = false;
         bool held = false;          // read by a deferred filter launch that has not been enqueued yet
         bool free_pending = false;  // dev_free arrived while held
+        bool in_slab = false;       // carved out of one of the context's pool slabs (not freed on its own)
     };
 
     // Geometry of one pending backprojection batch: everything but the angles must match for
@@ -105,6 +106,7 @@ struct paris_b200_ctx
     // pooled raw projection buffers (dev_alloc / dev_free)
     std::vector<pb::raw_buffer> pool;
     std::deque<size_t> free_fifo;   // indices into pool, in release order
+    std::vector<void*> pool_slabs;  // one allocation per projection size, carved into the pool's first buffers
     // one cached volume allocation (volume_free keeps the last buffer, volume_alloc reuses it if the size matches):
     // the reference allocates and frees the slab once per task (src/main.cpp:95,107)
     std::unordered_map<float*, size_t> vol_bytes;   // every live volume allocation of this context

@@ -12,6 +12,9 @@ single-GPU pipeline and the end-to-end step runs through the C++ per-projection 
 """
 from __future__ import annotations
 
+import os
+import time
+
 import numpy as np
 
 from . import capi, dropin
@@ -158,6 +161,8 @@ class MultiGpuReconstructor:
         ctx, torch = self.ctx, self._torch
         w, m = self.plan.world, self.m
         slot_floats = self.slot_bytes // 4
+        trace = os.environ.get("PARIS_B200_TRACE") and upload
+        t_begin = time.perf_counter()
         ctx.volume_clear(self.d_vol, *self.slab_dims)
         gathered = []
         for rd in range(self.rounds):
@@ -186,8 +191,13 @@ class MultiGpuReconstructor:
             if rd >= 1:
                 self._ext_stream.wait_event(gathered[rd - 1])
                 self._backproject((rd - 1) * w * m, w * m)
+        t_submitted = time.perf_counter()
         self._ext_stream.wait_event(gathered[-1])
         self._backproject((self.rounds - 1) * w * m, w * m, download=upload)
+        if trace:
+            t_end = time.perf_counter()
+            print(f"[trace rank {self.plan.rank}] rounds submitted in {(t_submitted - t_begin) * 1e3:.1f} ms, "
+                  f"last round + download {(t_end - t_submitted) * 1e3:.1f} ms, pool {ctx.stats()}", flush=True)
 
     def step_resident(self, timed: bool = False, overlap: bool = True):
         """raw projections already in HBM -> slab in HBM.  timed (sequential, for the stage breakdown):
