@@ -12,12 +12,16 @@ OBJS     := $(SRCS:.cu=.o)
 HDRS     := $(wildcard $(CSRC)/*.cuh) include/paris_b200.h
 LIB      := paris_b200/libparis_b200.so
 DROPIN   := paris_b200/libparis_b200_dropin.so
-CPPSRC   := paris_b200/cpp/b200/backend.cpp paris_b200/cpp/pipeline.cpp paris_b200/cpp/dropin_api.cpp
-CPPHDR   := paris_b200/cpp/b200/backend.h paris_b200/cpp/pipeline.h paris_b200/cpp/paris_types.h
+CPPDIR   := paris_b200/cpp
+CPPSRC   := $(CPPDIR)/b200/backend.cpp $(CPPDIR)/pipeline.cpp $(CPPDIR)/dropin_api.cpp $(CPPDIR)/io_api.cpp \
+            $(CPPDIR)/io/his.cpp $(CPPDIR)/io/ddbvf.cpp $(CPPDIR)/io/filesystem.cpp $(CPPDIR)/io/source.cpp \
+            $(CPPDIR)/io/sink.cpp $(CPPDIR)/program_options.cpp $(CPPDIR)/task.cpp
+CPPHDR   := $(wildcard $(CPPDIR)/*.h $(CPPDIR)/b200/*.h $(CPPDIR)/io/*.h)
+CLI      := paris_b200/bin/paris_b200
 
 all: lib oracle
 
-lib: $(LIB) $(DROPIN)
+lib: $(LIB) $(DROPIN) $(CLI)
 
 $(CSRC)/%.o: $(CSRC)/%.cu $(HDRS)
 	$(NVCC) $(NVFLAGS) -c $< -o $@
@@ -27,13 +31,18 @@ $(LIB): $(OBJS)
 
 # the C++ host layer (namespace paris::b200 + stage wrappers + the reference-shaped loop), over the C ABI
 $(DROPIN): $(CPPSRC) $(CPPHDR) include/paris_b200.h $(LIB)
-	$(HOSTCXX) -std=c++14 -O2 -fPIC -Wall -Wextra -shared -o $@ $(CPPSRC) -Lparis_b200 -lparis_b200 -Wl,-rpath,'$$ORIGIN'
+	$(HOSTCXX) -std=c++17 -O2 -fPIC -Wall -Wextra -shared -o $@ $(CPPSRC) -Lparis_b200 -lparis_b200 -Wl,-rpath,'$$ORIGIN'
+
+# the command-line driver (src/main.cpp of the reference on the B200 backend)
+$(CLI): $(CPPDIR)/main.cpp $(DROPIN)
+	mkdir -p paris_b200/bin
+	$(HOSTCXX) -std=c++17 -O2 -Wall -Wextra -pthread -o $@ $(CPPDIR)/main.cpp -Lparis_b200 -lparis_b200_dropin -lparis_b200 -Wl,-rpath,'$$ORIGIN/..'
 
 oracle:
 	$(MAKE) -C oracle
 
 clean:
-	rm -f $(OBJS) $(LIB) $(DROPIN)
+	rm -f $(OBJS) $(LIB) $(DROPIN) $(CLI)
 	$(MAKE) -C oracle clean
 
 .PHONY: all lib oracle clean

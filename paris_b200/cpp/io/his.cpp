@@ -1,0 +1,136 @@
+// io/his.cpp -- see his.h.
+#include "his.h"
+
+#include <cerrno>
+#include <cstdio>
+#include <cstring>
+#include <memory>
+#include <system_error>
+
+#include "log.h"
+
+namespace paris
+{
+    namespace his
+    {
+        namespace
+        {
+            constexpr std::size_t file_header_bytes = 68;   // src/his.cpp:44
+            constexpr std::uint16_t his_magic = 0x7000;     // src/his.cpp:48
+
+            template <class T>
+            auto field(const unsigned char* header, std::size_t offset) -> T
+            {
+                T v;
+                std::memcpy(&v, header + offset, sizeof(T));
+                return v;
+            }
+
+            auto sample_bytes(std::uint16_t number_type) -> std::size_t
+            {
+                switch(number_type)   // src/his.cpp:67-75
+                {
+                    case 2: return 1;     // unsigned char
+                    case 4: return 2;     // unsigned short
+                    case 32: return 4;    // dword
+                    case 64: return 8;    // double
+                    case 128: return 4;   // float
+                    default: return 0;
+                }
+            }
+
+            template <class T>
+            auto widen(const unsigned char* raw, float* dst, std::size_t n) -> void
+            {
+                // raw is not necessarily aligned for T
+                for(std::size_t i = 0; i < n; ++i)
+                {
+                    T v;
+                    std::memcpy(&v, raw + i * sizeof(T), sizeof(T));
+                    dst[i] = static_cast<float>(v);
+                }
+            }
+
+            struct file_closer { auto operator()(std::FILE* f) const noexcept -> void { if(f) std::fclose(f); } };
+        }
+
+        auto read(const std::string& path, file_info& info, const std::function<float*(std::uint32_t)>& frame_buffer)
+            -> std::uint32_t
+        {
+            info = file_info{};
+            auto file = std::unique_ptr<std::FILE, file_closer>{std::fopen(path.c_str(), "rb")};
+            if(!file)
+            {
+                log::warning() << "his::load() failed to open file at " << path;
+                throw std::system_error{errno, std::generic_category(), path};
+            }
+
+            unsigned char header[file_header_bytes] = {};
+            if(std::fread(header, 1, file_header_bytes, file.get()) != file_header_bytes
+               || field<std::uint16_t>(header, 0) != his_magic)
+            {
+                log::warning() << "his::load() could not open non-HIS file at " << path;
+                return 0;
+            }
+            if(field<std::uint16_t>(header, 2) != file_header_bytes)
+            {
+                log::warning() << "his::load() encountered a file header size mismatch at " << path;
+                return 0;
+            }
+            info.image_header_size = field<std::uint16_t>(header, 10);
+            const auto ulx = field<std::uint16_t>(header, 12), uly = field<std::uint16_t>(header, 14);
+            const auto brx = field<std::uint16_t>(header, 16), bry = field<std::uint16_t>(header, 18);
+            info.frames = field<std::uint16_t>(header, 20);
+            info.number_type = field<std::uint16_t>(header, 32);
+            const auto bytes_per_sample = sample_bytes(info.number_type);
+            if(bytes_per_sample == 0 || brx < ulx || bry < uly)
+            {
+                log::warning() << "his::load() encountered an unsupported data type at " << path;
+                return 0;
+            }
+            info.width = static_cast<std::uint32_t>(brx) - ulx + 1u;    // src/his.cpp:142-147
+            info.height = static_cast<std::uint32_t>(bry) - uly + 1u;
+            info.valid = true;
+
+            const auto samples = static_cast<std::size_t>(info.width) * info.height;
+            auto raw = std::unique_ptr<unsigned char[]>{new unsigned char[samples * bytes_per_sample]};
+            auto decoded = 0u;
+            for(auto i = 0u; i < info.frames; ++i)
+            {
+                // every frame is preceded by image_header_size bytes that are skipped (src/his.cpp:150-153)
+                if(std::fseek(file.get(), static_cast<long>(info.image_header_size), SEEK_CUR) != 0
+                   || std::fread(raw.get(), bytes_per_sample, samples, file.get()) != samples)
+                {
+                    log::warning() << "his::load() found " << path << " truncated after " << decoded << " of "
+                                   << info.frames << " frames";
+                    break;
+                }
+                auto dst = frame_buffer(i);
+                if(dst == nullptr)
+                    break;
+                switch(info.number_type)
+                {
+                    case 2: widen<std::uint8_t>(raw.get(), dst, samples); break;
+                    case 4: widen<std::uint16_t>(raw.get(), dst, samples); break;
+                    case 32: widen<std::uint32_t>(raw.get(), dst, samples); break;
+                    case 64: widen<double>(raw.get(), dst, samples); break;
+                    default: widen<float>(raw.get(), dst, samples); break;
+                }
+                ++decoded;
+            }
+            return decoded;
+        }
+
+        auto load(const std::string& path) -> std::vector<image_type>
+        {
+            auto images = std::vector<image_type>{};
+            auto info = file_info{};
+            const auto decoded = read(path, info, [&](std::uint32_t) -> float* {
+                images.push_back(b200::make_projection_host(info.width, info.height));
+                return images.back().buf.get();
+            });
+            images.resize(decoded);   // (a frame whose samples were cut short is dropped)
+            return images;
+        }
+    }
+}

@@ -1,0 +1,116 @@
+// io/source.cpp -- see source.h.
+#include "source.h"
+
+#include <algorithm>
+#include <cstdlib>
+#include <exception>
+#include <fstream>
+#include <sstream>
+#include <utility>
+
+#include "filesystem.h"
+#include "his.h"
+#include "log.h"
+
+namespace paris
+{
+    auto read_angles(const std::string& path) -> std::vector<float>
+    {
+        auto angles = std::vector<float>{};
+        auto file = std::ifstream{path.c_str()};
+        if(!file.is_open())
+        {
+            log::warning() << "Could not open angle file at " << path << ", using default values.";
+            return angles;
+        }
+        auto text = std::stringstream{};
+        text << file.rdbuf();
+        auto content = text.str();
+        const auto first_line = content.substr(0, content.find('\n'));
+        if(first_line.find(',') != std::string::npos)
+            std::replace(content.begin(), content.end(), ',', '.');   // decimal comma
+        auto tokens = std::istringstream{content};
+        auto token = std::string{};
+        while(tokens >> token)
+        {
+            char* end = nullptr;
+            const auto value = std::strtof(token.c_str(), &end);
+            if(end == token.c_str())
+                break;   // not a number: the reference's stream extraction stops here as well
+            angles.push_back(value);
+        }
+        return angles;
+    }
+
+    source::source(const std::string& proj_dir, bool enable_angles, const std::string& angle_file,
+                   std::uint16_t quality) noexcept
+    : enable_angles_{enable_angles}, quality_{quality == 0 ? std::uint16_t{1} : quality}
+    {
+        try
+        {
+            paths_ = read_directory(proj_dir);
+            if(enable_angles_)
+                angles_ = read_angles(angle_file);
+            refill();
+        }
+        catch(const std::exception& e)
+        {
+            log::error() << "source: " << e.what();
+            paths_.clear();
+        }
+        drained_ = queue_.empty();
+    }
+
+    // queue the kept frames of the next file(s) until at least one projection is waiting or the files run out
+    auto source::refill() -> void
+    {
+        while(queue_.empty() && next_path_ < paths_.size())
+        {
+            const auto& path = paths_[next_path_++];
+            auto frames = his::load(path);
+            if(frames.empty())
+            {
+                log::warning() << "Skipping invalid file at " << path;
+                continue;
+            }
+            for(auto& p : frames)
+            {
+                if(counter_ % quality_ == 0u)   // src/source.cpp:105
+                {
+                    p.idx = counter_;
+                    if(has_angle_for(counter_))
+                        p.phi = angles_[counter_];
+                    queue_.push(std::move(p));
+                }
+                ++counter_;
+            }
+        }
+    }
+
+    auto source::load_next() -> output_type
+    {
+        if(queue_.empty())
+            refill();
+        if(queue_.empty())
+        {
+            drained_ = true;
+            return output_type{};
+        }
+        auto p = std::move(queue_.front());
+        queue_.pop();
+        if(queue_.empty())
+            refill();   // look ahead so that drained() is exact even when the remaining files hold nothing
+        drained_ = queue_.empty();
+        return p;
+    }
+
+    auto source::drained() const noexcept -> bool
+    {
+        return drained_;
+    }
+
+    auto source::has_angle_for(std::uint32_t idx) const noexcept -> bool
+    {
+        return enable_angles_ && idx < angles_.size();
+    }
+}
