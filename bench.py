@@ -38,20 +38,36 @@ CONFIGS = {
     "c1": (256, 256, 128, "128^3 volume from 256 projections of 256^2 detector"),
     "c2": (1024, 720, 512, "512^3 volume from 720 projections of 1024^2 detector, full-scan FDK, float32"),
     "c3": (2048, 1440, 1024, "1024^3 volume from 1440 projections of 2048^2 detector"),
+    # ROI configurations: the PARIS-derived natural volume, reconstructed inside a region of interest
+    "c4": (2048, 2880, 1024, "ROI reconstruction (region_of_interest) 1024^3 sub-volume from 2880 projections of "
+                             "2048^2 offset detector"),
+    "c5": (2048, 2880, 2048, "2048^3 volume (32 GB float32) from 2880 projections of 2048^2, z-slabs across the GPUs"),
 }
 
 
 def geometry(cfg: str):
+    """(detector, FULL volume geometry, projections, roi or None, region (x, y, z))."""
     from paris_b200 import capi
     n, n_proj, k, _ = CONFIGS[cfg]
     l_px = 0.2 * 1024 / n  # 204.8 mm detector
-    det = capi.DetectorGeometry(n, n, l_px, l_px, 0.0, 0.0, 500.0, 500.0, 360.0 / n_proj)
+    delta_s = 100.0 if cfg == "c4" else 0.0   # offset detector (pixels)
+    det = capi.DetectorGeometry(n, n, l_px, l_px, delta_s, 0.0, 500.0, 500.0, 360.0 / n_proj)
     nat = capi.calculate_volume_geometry(det)
+    if cfg in ("c4", "c5"):
+        # a centred k^3 box of the natural volume; apply_roi: dim = x2 - x1, + 1 iff x1 == 0 (src/geometry.cpp:86-130)
+        def span(full):
+            lo = (full - k) // 2
+            return lo, (lo + k - 1) if lo == 0 else (lo + k)
+        (x1, x2), (y1, y2), (z1, z2) = span(nat.dim_x), span(nat.dim_y), span(nat.dim_z)
+        roi = capi.Roi(x1, x2, y1, y2, z1, z2)
+        reg = capi.apply_roi(nat, roi)
+        assert (reg.dim_x, reg.dim_y, reg.dim_z) == (k, k, k), (reg.dim_x, reg.dim_y, reg.dim_z)
+        return det, nat, n_proj, roi, (k, k, k)
     # "K^3 from a (2K)^2 detector": the natural full-FOV volume sampled with K^3 larger voxels
     f32 = np.float32
     vol = capi.VolumeGeometry(k, k, k, f32(nat.l_vx_x * nat.dim_x / k), f32(nat.l_vx_y * nat.dim_y / k),
                               f32(nat.l_vx_z * nat.dim_z / k))
-    return det, vol, n_proj
+    return det, vol, n_proj, None, (k, k, k)
 
 
 def ellipsoids(det):
@@ -159,17 +175,18 @@ def cpu_reconstruct_sample(cfg: str, budget_s: float, fetch=None):
     Returns (gups_total, gups_backprojection, cores, kind, description, seconds)."""
     import oracle
     from paris_b200 import phantom
-    det, vol, n_proj = geometry(cfg)
+    det, vol, n_proj, roi, region = geometry(cfg)
     odet = oracle.DetectorGeometry(det.n_row, det.n_col, det.l_px_row, det.l_px_col, det.delta_s, det.delta_t,
                                    det.d_so, det.d_od, det.delta_phi)
     ovol = oracle.VolumeGeometry(vol.dim_x, vol.dim_y, vol.dim_z, vol.l_vx_x, vol.l_vx_y, vol.l_vx_z)
+    oroi = None if roi is None else oracle.Roi(roi.x1, roi.x2, roi.y1, roi.y2, roi.z1, roi.z2)
     if oracle.have_ref():
         impl, kind = oracle.Reference(), "reference"
     else:
         impl, kind = oracle.Port(), "port"
     cores = impl.num_threads()
-    shape = (vol.dim_z, vol.dim_y, vol.dim_x)
-    voxels = vol.dim_x * vol.dim_y * vol.dim_z
+    shape = (region[2], region[1], region[0])
+    voxels = region[0] * region[1] * region[2]
 
     def raw(count, stride):
         if fetch is not None:
@@ -180,12 +197,12 @@ def cpu_reconstruct_sample(cfg: str, budget_s: float, fetch=None):
 
     # calibrate on 2 projections (the first builds FFT plans / statics and is excluded by the callee)
     stride = max(1, n_proj // 16)
-    _, t = impl.reconstruct(raw(2, stride), shape, odet, ovol, idx_stride=stride)
+    _, t = impl.reconstruct(raw(2, stride), shape, odet, ovol, roi=oroi, idx_stride=stride)
     per_proj = max(sum(t), 1e-4)
     count = int(max(2, min(64, budget_s / per_proj))) + 1
     stride = max(1, n_proj // count)
     t0 = time.perf_counter()
-    _, t = impl.reconstruct(raw(count, stride), shape, odet, ovol, idx_stride=stride)
+    _, t = impl.reconstruct(raw(count, stride), shape, odet, ovol, roi=oroi, idx_stride=stride)
     wall = time.perf_counter() - t0
     timed = count - 1
     gups_total = voxels * timed / sum(t) / 1e9
@@ -198,7 +215,7 @@ def cpu_reconstruct_sample(cfg: str, budget_s: float, fetch=None):
 def run_reference(args, rank: int):
     if rank != 0:
         return
-    det, vol, n_proj = geometry(args.config)
+    det, vol, n_proj, _roi, region = geometry(args.config)
     vals, info = [], None
     for i in range(args.warmup + args.steps):
         g_total, g_bp, cores, kind, desc, wall = cpu_reconstruct_sample(args.config, budget_s=args.cpu_budget)
@@ -206,7 +223,7 @@ def run_reference(args, rank: int):
             vals.append(g_total)
         info = (g_bp, cores, kind, desc, wall)
     value = float(np.mean(vals))
-    updates = vol.dim_x * vol.dim_y * vol.dim_z * n_proj
+    updates = region[0] * region[1] * region[2] * n_proj
     line = {
         "impl": "reference", "metric": "fdk_reconstruction_gups", "value": value, "unit": "GUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
@@ -241,17 +258,16 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
         dist = dist_mod
 
-    det, vol, n_proj = geometry(args.config)
+    det, vol, n_proj, roi, dims = geometry(args.config)
     n = det.n_row
     px = n * n
-    dims = (vol.dim_x, vol.dim_y, vol.dim_z)
     voxels = dims[0] * dims[1] * dims[2]
     updates = voxels * n_proj
 
     # one context per process, shared by the C++ loop (e2e) and the stack-level calls (value)
     from paris_b200.multi import SlabPlan, MultiGpuReconstructor
     plan = SlabPlan(dims[2], world, rank)
-    rec = MultiGpuReconstructor(local_rank, det, vol, n_proj, plan, dist)
+    rec = MultiGpuReconstructor(local_rank, det, vol, n_proj, plan, dist, roi=roi, region=dims)
     ctx = rec.ctx
 
     # synthetic raw stack: this rank's share of the projections, generated on the device, mirrored on the host

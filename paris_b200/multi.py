@@ -57,8 +57,12 @@ class SlabPlan:
 
 class MultiGpuReconstructor:
     def __init__(self, device: int, det: capi.DetectorGeometry, vol: capi.VolumeGeometry, n_proj: int,
-                 plan: SlabPlan, dist=None, batch: int = 64):
+                 plan: SlabPlan, dist=None, batch: int = 64, roi: capi.Roi | None = None, region=None):
+        """vol: the FULL volume geometry; roi/region: the reconstructed box and its (x, y, z) dimensions (default:
+        the whole volume).  plan cuts the REGION's z extent."""
         self.det, self.vol, self.n_proj, self.plan, self.dist = det, vol, n_proj, plan, dist
+        self.roi = roi
+        self.region = tuple(region) if region is not None else (vol.dim_x, vol.dim_y, vol.dim_z)
         self.device = device
         # the C++ layer's per-thread context, so the e2e loop and the stack-level calls share streams
         dropin.set_device(device)
@@ -78,7 +82,7 @@ class MultiGpuReconstructor:
         sc = np.array([angle_sin_cos(i, det) for i in range(n_proj)], dtype=np.float32).reshape(n_proj, 2)
         self.sin = np.ascontiguousarray(sc[:, 0])
         self.cos = np.ascontiguousarray(sc[:, 1])
-        self.slab_dims = (vol.dim_x, vol.dim_y, plan.slab_dz)
+        self.slab_dims = (self.region[0], self.region[1], plan.slab_dz)
         self.d_vol = self.ctx.volume_alloc(*self.slab_dims)
         self._torch_stack = None
         if dist is not None:
@@ -93,7 +97,7 @@ class MultiGpuReconstructor:
             self.d_stack = self.ctx.stack_alloc(det.n_row, det.n_col, self.slots)
         self.d_raw = None
         self.h_raw = None
-        self.h_slab = capi.PinnedArray((plan.slab_dz, vol.dim_y, vol.dim_x))
+        self.h_slab = capi.PinnedArray((plan.slab_dz, self.region[1], self.region[0]))
 
     # ---- inputs -----------------------------------------------------------------------------------------------
     def generate_inputs(self, ellipsoids_mm: np.ndarray):
@@ -150,10 +154,11 @@ class MultiGpuReconstructor:
             # last round of an end-to-end step: the slab goes to the host chunk by chunk behind the kernel
             self.ctx.backproject_stack_d2h(self.d_stack, first, count, self.sin[first:first + count],
                                            self.cos[first:first + count], self.d_vol, self.slab_dims, self.plan.offset,
-                                           self.det, self.vol, self.h_slab.ptr, layout=self.layout)
+                                           self.det, self.vol, self.h_slab.ptr, roi=self.roi, layout=self.layout)
             return
         self.ctx.backproject_stack(self.d_stack, first, count, self.sin[first:first + count], self.cos[first:first + count],
-                                   self.d_vol, self.slab_dims, self.plan.offset, self.det, self.vol, layout=self.layout)
+                                   self.d_vol, self.slab_dims, self.plan.offset, self.det, self.vol, roi=self.roi,
+                                   layout=self.layout)
 
     def _pipelined(self, upload: bool):
         """N > 1: per round, filter my m projections -> all-gather the round (comm stream) -> backproject the
@@ -233,8 +238,8 @@ class MultiGpuReconstructor:
         """pinned host raw projections -> pinned host slab, copies included."""
         if self.dist is None:
             # the reference-shaped per-projection loop in C++ (paris_b200/cpp/pipeline.cpp: reconstruct_task)
-            dropin.reconstruct(self.h_raw.ptr, self.n_proj, self.det, self.vol, self.h_slab.ptr,
-                               (self.vol.dim_x, self.vol.dim_y, self.vol.dim_z), device=self.device)
+            dropin.reconstruct(self.h_raw.ptr, self.n_proj, self.det, self.vol, self.h_slab.ptr, self.region,
+                               roi=self.roi, device=self.device)
             return
         ctx = self.ctx
         if self.m:

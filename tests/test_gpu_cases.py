@@ -187,6 +187,65 @@ def test_full_size_config2_fast_kernel_against_exact_kernel(ctx):
     assert abs(plateau / (0.2 * c) - 1.0) < 0.05
 
 
+def test_full_size_config4_roi_offset_detector(ctx):
+    """BASELINE config 4 at full size: 1024^3 region of interest of the 2248 x 2248 x 2060 natural volume from 2880
+    projections of a 2048^2 detector shifted by 100 pixels.  Properties checked (no CPU oracle finishes this size):
+    the production kernel agrees with the exact kernel -- pinned bit for bit to the reference on the small cases --
+    on bands of the ROI at its bottom, middle and top, and the ROI reconstruction is a bit-identical crop whether it
+    is computed in one piece or band by band (what z-slab tasks and the chunked download rely on)."""
+    n, n_proj, k = 2048, 2880, 1024
+    l_px = 0.1
+    det = capi.DetectorGeometry(n, n, l_px, l_px, 100.0, 0, 500, 500, 360.0 / n_proj)
+    nat = capi.calculate_volume_geometry(det)
+    assert (nat.dim_x, nat.dim_y, nat.dim_z) == (2248, 2248, 2060)
+    roi = capi.Roi(612, 1636, 612, 1636, 518, 1542)
+    reg = capi.apply_roi(nat, roi)
+    assert (reg.dim_x, reg.dim_y, reg.dim_z) == (k, k, k)
+    layout = capi.choose_stack_layout(det, nat)
+    assert layout == capi.LAYOUT_PLAIN
+    stack = ctx.stack_alloc(n, n, n_proj)                               # 48 GB
+    filt = ctx.filter_create(capi.filter_size(n), l_px)
+    ell = phantom.scaled_ellipsoids(phantom.SHEPP_LOGAN_3D, 0.9 * phantom.fov_radius(n, l_px, 100.0, 500, 500))
+    raw = ctx.dev_alloc(64 * n * n * 4)
+    for first in range(0, n_proj, 64):                                  # raw projections never exist all at once
+        ctx.phantom_project(ell, det, first, 64, raw)
+        ctx.filter_to_stack_batch(raw, n * n, 64, det, filt, stack, first, layout)
+    ctx.dev_free(raw)
+    sc = np.array([angle_sin_cos(i, det) for i in range(n_proj)], dtype=np.float32)
+
+    ctx.set_option("bp_kernel", 2)
+    v = ctx.volume_alloc(k, k, k)
+    e0 = ctx.event()
+    ctx.backproject_stack(stack, 0, n_proj, sc[:, 0], sc[:, 1], v, (k, k, k), 0, det, nat, roi=roi, layout=layout)
+    e1 = ctx.event()
+    ms = ctx.elapsed_ms(e0, e1)
+    print(f"config 4 full size: {k ** 3 * n_proj / ms / 1e6:.0f} GUPS ({ms:.0f} ms)")
+    full = np.empty((k, k, k), np.float32)
+    ctx.vol_d2h(v, full, k ** 3)
+    ctx.volume_free(v)
+
+    c = contrast(n_proj)
+    band = 4
+    for z in (0, 509, k - band):                                        # bands of `band` slices at these ROI offsets
+        got = {}
+        for kernel in (2, 1):
+            ctx.set_option("bp_kernel", kernel)
+            vb = ctx.volume_alloc(k, k, band)
+            ctx.backproject_stack(stack, 0, n_proj, sc[:, 0], sc[:, 1], vb, (k, k, band), z, det, nat, roi=roi,
+                                  layout=layout)
+            got[kernel] = np.empty((band, k, k), np.float32)
+            ctx.vol_d2h(vb, got[kernel], band * k * k)
+            ctx.volume_free(vb)
+        assert np.array_equal(got[2], full[z:z + band]), f"band at {z} is not a crop of the one-piece ROI"
+        mx, rms = errors(got[2], got[1], c)
+        print(f"config 4 band at z={z}: fast vs exact kernel max {mx:.2e} C, rmse {rms:.2e} C")
+        assert mx <= MAX_ABS_TOL and rms <= RMSE_TOL
+    ctx.set_option("bp_kernel", 0)
+    ctx.filter_destroy(filt)
+    ctx.stack_free(stack)
+    assert np.isfinite(full).all() and full.max() > 0.5 * 1.0 * c * 0.2
+
+
 @pytest.mark.parametrize("n_row,n_col", [(96, 96), (100, 37), (256, 64), (1024, 16), (2048, 8), (3000, 5)])
 @pytest.mark.parametrize("layout", [capi.LAYOUT_PLAIN, capi.LAYOUT_SPLIT2])
 def test_filter_to_stack_layouts(ctx, port, n_row, n_col, layout):
