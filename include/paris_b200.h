@@ -107,7 +107,7 @@ int paris_b200_event_record(paris_b200_ctx* ctx, paris_b200_event* ev);
 int paris_b200_event_elapsed_ms(paris_b200_event* start, paris_b200_event* stop, float* ms);
 int paris_b200_event_destroy(paris_b200_event* ev);
 
-/* Tunables.  "bp_batch": projections accumulated per backprojection launch (default 64, max 64);
+/* Tunables.  "bp_batch": projections accumulated per backprojection launch (default 256, max 256);
  * "bp_kernel": 0 = auto, 1 = generic L1-gather kernel, 2 = TMA-staged kernel.
  * "bp_tile": 0 = auto (16x8x64 voxel tiles, two CTAs per SM, when the footprint fits), 1 = 16x16x64 tiles only. */
 int paris_b200_ctx_set_option(paris_b200_ctx* ctx, const char* name, int64_t value);

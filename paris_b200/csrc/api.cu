@@ -345,7 +345,9 @@ extern "C" int paris_b200_dev_alloc(paris_b200_ctx* ctx, size_t bytes, void** d_
     size_t same_size = 0;
     for(const auto& b : ctx->pool)
         same_size += b.bytes == bytes ? 1u : 0u;
-    const size_t cap = 2u * static_cast<size_t>(ctx->bp_batch) + 2u;
+    // deep enough for one pending batch (its raw buffers are held until the fused filter launch) plus the uploads
+    // running ahead of it
+    const size_t cap = static_cast<size_t>(ctx->bp_batch) + 66u;
     for(auto it = ctx->free_fifo.begin(); it != ctx->free_fifo.end(); ++it)
     {
         pb::raw_buffer& b = ctx->pool[*it];
@@ -968,9 +970,13 @@ extern "C" int paris_b200_backproject(paris_b200_ctx* ctx, const float* d_proj, 
         // A full batch is launched when the NEXT projection arrives, not when it fills: the last batch of a
         // scan is then still pending when the volume is read back, and vol_d2h() can backproject it slab by
         // slab with the download of each finished slab running behind the next one.
-        // The first batch into a volume is kept short so that the backprojection starts while most of the scan
-        // is still being uploaded; afterwards full batches amortise the volume traffic.
-        const int threshold = ctx->flushes_for_target == 0 ? std::min(ctx->bp_batch, 16) : ctx->bp_batch;
+        // The first batches into a volume are short -- 16 projections, then half as many again each time -- so that
+        // the backprojection starts while most of the scan is still being uploaded and never waits long for the
+        // next batch to fill; full batches then amortise the volume traffic and the kernel prologue.
+        int threshold = 16;
+        for(int i = 0; i < ctx->flushes_for_target && threshold < ctx->bp_batch; ++i)
+            threshold += threshold / 2;
+        threshold = std::min(threshold, ctx->bp_batch);
         if(ctx->pending >= threshold)
             PB_TRY(paris_b200_flush(ctx));
     }

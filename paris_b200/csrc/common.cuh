@@ -31,7 +31,7 @@ namespace pb
     }
 
     // Maximum projections accumulated by one backprojection launch (sin/cos travel as kernel parameters).
-    constexpr int kMaxBatch = 64;
+    constexpr int kMaxBatch = 256;
 
     struct raw_buffer
     {
@@ -99,7 +99,7 @@ struct paris_b200_ctx
     uint64_t stat_pool_malloc = 0, stat_pool_ready = 0, stat_pool_busy = 0, stat_flush = 0;
 
     // options
-    int bp_batch = 64;
+    int bp_batch = 256;
     int bp_kernel = 0;
     int bp_tile = 0;     // 0: half tiles (two CTAs per SM) when the footprint fits, 1: full tiles only
 

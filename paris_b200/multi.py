@@ -57,7 +57,8 @@ class SlabPlan:
 
 class MultiGpuReconstructor:
     def __init__(self, device: int, det: capi.DetectorGeometry, vol: capi.VolumeGeometry, n_proj: int,
-                 plan: SlabPlan, dist=None, batch: int = 64, roi: capi.Roi | None = None, region=None):
+                 plan: SlabPlan, dist=None, batch: int = 256, roi: capi.Roi | None = None, region=None,
+                 gather_round: int = 64):
         """vol: the FULL volume geometry; roi/region: the reconstructed box and its (x, y, z) dimensions (default:
         the whole volume).  plan cuts the REGION's z extent."""
         self.det, self.vol, self.n_proj, self.plan, self.dist = det, vol, n_proj, plan, dist
@@ -73,7 +74,9 @@ class MultiGpuReconstructor:
         self.lo, self.hi, self.chunk = plan.projection_block(n_proj)
         self.my_count = self.hi - self.lo
         # pipelined exchange (N > 1): block-cyclic ownership, m projections per rank and round
-        self.m = plan.cyclic_blocks(n_proj, batch) if dist is not None else 0
+        # (rounds of at most `gather_round` projections are exchanged; up to `batch` gathered projections share one
+        # backprojection launch)
+        self.m = plan.cyclic_blocks(n_proj, min(batch, gather_round)) if dist is not None else 0
         self.rounds = (n_proj // (plan.world * self.m)) if self.m else 0
         self.slot_bytes, self.pitch = capi.stack_slot_bytes(det.n_row, det.n_col)
         self.layout = capi.choose_stack_layout(det, vol)
@@ -161,8 +164,10 @@ class MultiGpuReconstructor:
                                    layout=self.layout)
 
     def _pipelined(self, upload: bool):
-        """N > 1: per round, filter my m projections -> all-gather the round (comm stream) -> backproject the
-        PREVIOUS round, so the exchange of round c hides behind the backprojection of round c-1."""
+        """N > 1: per round, filter my m projections -> all-gather the round (comm stream) -> backproject rounds that
+        were gathered EARLIER, so the exchange of round c hides behind the backprojection of the rounds before it.
+        The first round is backprojected on its own (work starts as early as possible); afterwards as many rounds as
+        fit one batch share a launch (the volume tile traffic and the kernel prologue amortise over more projections)."""
         ctx, torch = self.ctx, self._torch
         w, m = self.plan.world, self.m
         slot_floats = self.slot_bytes // 4
@@ -170,6 +175,8 @@ class MultiGpuReconstructor:
         t_begin = time.perf_counter()
         ctx.volume_clear(self.d_vol, *self.slab_dims)
         gathered = []
+        group = max(1, self.batch // (w * m))   # rounds per backprojection launch
+        next_bp = 0                             # first round not backprojected yet
         for rd in range(self.rounds):
             first = rd * w * m
             mine_first = first + self.plan.rank * m
@@ -193,16 +200,18 @@ class MultiGpuReconstructor:
                 done = torch.cuda.Event()
                 done.record(self._comm_stream)
             gathered.append(done)
-            if rd >= 1:
+            ready = rd - next_bp                # rounds whose exchange was issued before this one
+            if ready >= (1 if next_bp == 0 else group):
                 self._ext_stream.wait_event(gathered[rd - 1])
-                self._backproject((rd - 1) * w * m, w * m)
+                self._backproject(next_bp * w * m, ready * w * m)
+                next_bp = rd
         t_submitted = time.perf_counter()
         self._ext_stream.wait_event(gathered[-1])
-        self._backproject((self.rounds - 1) * w * m, w * m, download=upload)
+        self._backproject(next_bp * w * m, (self.rounds - next_bp) * w * m, download=upload)
         if trace:
             t_end = time.perf_counter()
             print(f"[trace rank {self.plan.rank}] rounds submitted in {(t_submitted - t_begin) * 1e3:.1f} ms, "
-                  f"last round + download {(t_end - t_submitted) * 1e3:.1f} ms, pool {ctx.stats()}", flush=True)
+                  f"last rounds + download {(t_end - t_submitted) * 1e3:.1f} ms, pool {ctx.stats()}", flush=True)
 
     def step_resident(self, timed: bool = False, overlap: bool = True):
         """raw projections already in HBM -> slab in HBM.  timed (sequential, for the stage breakdown):

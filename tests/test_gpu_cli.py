@@ -75,7 +75,8 @@ def test_cli_reconstructs_his_scan_to_ddbvf(tmp_path, port):
     odet, stack, scan, geo = make_scan(tmp_path)
     out = tmp_path / "out"
     r = run_cli(["--geometry", geo, "--input", scan, "--output", str(out)])
-    assert "Created 1 task for" in r.stderr
+    n_dev = pio.capi.device_count()
+    assert (f"Created {n_dev} tasks for {n_dev} devices" if n_dev > 1 else "Created 1 task for 1 device") in r.stderr
     got = formats.read_ddbvf(str(out / "vol.ddbvf"))
     want = oracle_volume(port, odet, stack)
     assert got.shape == want.shape
