@@ -212,7 +212,7 @@ extern "C" int paris_b200_ctx_set_option(paris_b200_ctx* ctx, const char* name, 
     }
     if(std::strcmp(name, "bp_tile") == 0)
     {
-        PB_CHECK_ARG(value >= 0 && value <= 1);
+        PB_CHECK_ARG(value >= 0 && value <= 2);
         PB_TRY(paris_b200_flush(ctx));
         ctx->bp_tile = static_cast<int>(value);
         return PARIS_B200_OK;

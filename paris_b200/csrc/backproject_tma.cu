@@ -56,8 +56,8 @@ namespace pb
         static_assert(COLS % CPW == 0, "columns per warp must divide the tile");
         static_assert(CPW % TX == 0 || TX % CPW == 0, "a warp's columns must be whole or partial x-runs");
         static_assert(BV % 4 == 0, "TMA inner box extent must be a multiple of 16 bytes");
-        static_assert(BH <= 256 && BV <= 256, "TMA box extents are limited to 256");
-        static_assert(2 * BV + 32 < (1 << (32 - FRAC)), "biased rows must fit the 9 integer bits");
+        static_assert(BH <= 256 && (SPLIT ? BV / 2 : BV) <= 256, "TMA box extents are limited to 256");
+        static_assert(2 * BV + 32 < (1 << (32 - ROW_SHIFT)), "biased rows must fit the integer bits of the fixed-point word");
         static_assert(STAGE_BYTES % 128 == 0, "stages must keep the 128-byte TMA destination alignment");
         static_assert(!SPLIT || (BV % 8 == 0 && BIAS % 2 == 0), "parity planes: even bias, 16-byte plane rows");
     };
@@ -322,11 +322,11 @@ namespace pb
     // CLAMP: additionally the box may not cover the tile's rows (never the case for launches that passed the
     // host-side footprint check; kept as the safe path)
     template <class CFG, bool MIXED, bool CLAMP = false>
-    __device__ __forceinline__ void consume(uint64_t (&acc)[CFG::CPW], const float4* __restrict__ tab_a,
+    __device__ __forceinline__ void consume(uint64_t (&acc)[CFG::CPW][CFG::NZ / 2], const float4* __restrict__ tab_a,
                                             const float* __restrict__ tab_b, const uint32_t* __restrict__ tab_c,
-                                            int col0, uint32_t lane)
+                                            int col0, uint32_t lane, uint32_t lane_z)
     {
-        static_assert(CFG::NZ == 2, "the two slices of a lane are processed as one packed f32x2 pair");
+        static_assert(CFG::NZ % 2 == 0, "the slices of a lane are processed as packed f32x2 pairs (l + 64j, l + 64j + 32)");
         // kept in registers so the fraction -> float assembly is a single three-input LOP3
         uint32_t frac_mask = (1u << CFG::FRAC) - 1u, one_bits = 0x3f800000u;
         asm volatile("" : "+r"(frac_mask), "+r"(one_bits));
@@ -335,39 +335,51 @@ namespace pb
         for(int i = 0; i < CFG::CPW; ++i)
         {
             // {stage address of (column x1, row -BIAS), v_base (fixed point, biased), dv (fixed point), w*(1-fx)},
-            // w*fx, valid slices (first | count << 8; boundary tiles only)
+            // w*fx, valid slices (first | count << 8; boundary tiles only): read ONCE for the NZ slices of the lane
             const float4 ea = tab_a[col0 + i];
             const float wb = tab_b[col0 + i];
             const uint32_t base = __float_as_uint(ea.x);
             const uint32_t dv = __float_as_uint(ea.z);
-            uint32_t v0 = dv * lane + __float_as_uint(ea.y);     // slice `lane`
-            uint32_t v1 = v0 + (dv << 5);                        // slice `lane + 32`: 32 steps of dv further
-            if(CLAMP)
-            {
-                // rows may lie outside the staged box: keep the address inside, the value is discarded below
-                const uint32_t lo = static_cast<uint32_t>(CFG::BIAS) << CFG::ROW_SHIFT;
-                const uint32_t hi = static_cast<uint32_t>(CFG::BIAS + CFG::BV - 2) << CFG::ROW_SHIFT;
-                v0 = min(max(v0, lo), hi);
-                v1 = min(max(v1, lo), hi);
-            }
-            const update_samples s0 = fetch<CFG>(base, v0, frac_mask, one_bits);
-            const update_samples s1 = fetch<CFG>(base, v1, frac_mask, one_bits);
-            // both slices at once: g1 = wa*q11 + wb*q21, g2 = wa*q12 + wb*q22, d = g1 + fy*(g2 - g1)
-            // (src/openmp/backprojection.cpp:73-83 with the weight 0.5*u^2 of :147 folded into wa, wb)
             const uint64_t wa2 = pack2(ea.w, ea.w), wb2 = pack2(wb, wb);
-            const uint64_t g1 = fma2(wb2, pack2(s0.q21, s1.q21), mul2(wa2, pack2(s0.q11, s1.q11)));
-            const uint64_t g2 = fma2(wb2, pack2(s0.q22, s1.q22), mul2(wa2, pack2(s0.q12, s1.q12)));
-            uint64_t d = fma2(pack2(s0.fy, s1.fy), fma2(g1, minus_one, g2), g1);
+            uint32_t rel = 0, count = 0;
             if(MIXED)
             {
                 // the reference's "all four neighbours inside" as a slice interval (see valid_slices)
                 const uint32_t vs = tab_c[col0 + i];
-                const uint32_t rel = lane - (vs & 0xffu), count = vs >> 8;
-                float d0, d1;
-                unpack2(d, d0, d1);
-                d = pack2(rel < count ? d0 : 0.f, (rel + 32u) < count ? d1 : 0.f);
+                rel = lane - (vs & 0xffu);
+                count = vs >> 8;
             }
-            acc[i] = add2(acc[i], d);
+            uint32_t v0 = dv * lane_z + __float_as_uint(ea.y);   // slice `lane` (lane_z counts from the row anchor)
+            #pragma unroll
+            for(int j = 0; j < CFG::NZ / 2; ++j)
+            {
+                uint32_t v1 = v0 + (dv << 5);                    // slice `lane + 64j + 32`: 32 steps of dv further
+                uint32_t va = v0;
+                if(CLAMP)
+                {
+                    // rows may lie outside the staged box: keep the address inside, the value is discarded below
+                    const uint32_t lo = static_cast<uint32_t>(CFG::BIAS) << CFG::ROW_SHIFT;
+                    const uint32_t hi = static_cast<uint32_t>(CFG::BIAS + CFG::BV - 2) << CFG::ROW_SHIFT;
+                    va = min(max(va, lo), hi);
+                    v1 = min(max(v1, lo), hi);
+                }
+                const update_samples s0 = fetch<CFG>(base, va, frac_mask, one_bits);
+                const update_samples s1 = fetch<CFG>(base, v1, frac_mask, one_bits);
+                // both slices at once: g1 = wa*q11 + wb*q21, g2 = wa*q12 + wb*q22, d = g1 + fy*(g2 - g1)
+                // (src/openmp/backprojection.cpp:73-83 with the weight 0.5*u^2 of :147 folded into wa, wb)
+                const uint64_t g1 = fma2(wb2, pack2(s0.q21, s1.q21), mul2(wa2, pack2(s0.q11, s1.q11)));
+                const uint64_t g2 = fma2(wb2, pack2(s0.q22, s1.q22), mul2(wa2, pack2(s0.q12, s1.q12)));
+                uint64_t d = fma2(pack2(s0.fy, s1.fy), fma2(g1, minus_one, g2), g1);
+                if(MIXED)
+                {
+                    float d0, d1;
+                    unpack2(d, d0, d1);
+                    d = pack2((rel + 64u * j) < count ? d0 : 0.f, (rel + 64u * j + 32u) < count ? d1 : 0.f);
+                }
+                acc[i][j] = add2(acc[i][j], d);
+                if(j + 1 < CFG::NZ / 2)
+                    v0 += dv << 6;                               // next pair of slices: 64 steps of dv further
+            }
         }
     }
 
@@ -474,10 +486,15 @@ namespace pb
             scratch[zl * kPitch + c] = ok ? vol[static_cast<size_t>(z) * slice + static_cast<size_t>(y) * g.v_dim_x + x] : 0.f;
         }
         __syncthreads();
-        uint64_t acc[CFG::CPW];   // (slice lane, slice lane + 32) of column col0 + i, packed
+        uint64_t acc[CFG::CPW][CFG::NZ / 2];   // (slice lane + 64j, slice lane + 64j + 32) of column col0 + i, packed
         #pragma unroll
         for(int i = 0; i < CFG::CPW; ++i)
-            acc[i] = pack2(scratch[lane * kPitch + col0 + i], scratch[(lane + 32u) * kPitch + col0 + i]);
+        {
+            #pragma unroll
+            for(int j = 0; j < CFG::NZ / 2; ++j)
+                acc[i][j] = pack2(scratch[(lane + 64u * j) * kPitch + col0 + i],
+                                  scratch[(lane + 64u * j + 32u) * kPitch + col0 + i]);
+        }
         __syncthreads(); // scratch is dead: the stages may be filled
 
         if(tid == 0)
@@ -495,12 +512,21 @@ namespace pb
         // table builder state: thread c < COLS owns tile column c
         const bool builder = tid < CFG::COLS;
         float bx_k = 0.f, by_l = 0.f;
-        double z_m0 = 0.0;
+        double z_m0 = 0.0, z_ma = 0.0;
+        // The fixed-point rows are anchored at multiples of kRowAnchor slices in GLOBAL slice indices, not at the
+        // tile: v(z) = round(v(anchor)) + (z - anchor) * round(dv) whatever the tile height, so every tile shape
+        // (16x16x64, 16x8x64, 8x8x128) computes bit-identical voxels and slabs thinner than a tall tile remain
+        // bit-identical crops of the one-piece result.
+        constexpr uint32_t kRowAnchor = 128u;
+        static_assert(kRowAnchor % CFG::TZ == 0 || CFG::TZ % kRowAnchor == 0, "tiles must not straddle anchors unevenly");
+        const uint32_t z_anchor = (z0 / kRowAnchor) * kRowAnchor;
+        const uint32_t lane_z = lane + (z0 - z_anchor);
         if(builder)
         {
             bx_k = centered(x0 + tid % CFG::TX, g.full_x, g.l_vx_x);
             by_l = centered(y0 + tid / CFG::TX, g.full_y, g.l_vx_y);
             z_m0 = centered_d(z0, g.full_z, g.l_vx_z);
+            z_ma = centered_d(z_anchor, g.full_z, g.l_vx_z);
         }
         const uint32_t stage_base0 = smem_u32(stage_mem);
         constexpr double kOne = static_cast<double>(1u << CFG::ROW_SHIFT);
@@ -534,7 +560,11 @@ namespace pb
                 // skipped, when the host-side footprint check holds (the box then covers the tile's rows)
                 if(dv >= 0.0 && vb >= 0.0 && vend < static_cast<double>(2 * CFG::BV + 16))
                 {
-                    ea.y = __uint_as_float(static_cast<uint32_t>(__double2ll_rn(vb * kOne)));
+                    // biased row of the ANCHOR slice in fixed point (may wrap: the arithmetic is modulo 2^32 and the
+                    // rows of this tile's slices are in range), made box-relative by an exact integer shift
+                    const double va = row_of(z_ma, fd, g) + static_cast<double>(CFG::BIAS);
+                    ea.y = __uint_as_float(static_cast<uint32_t>(__double2ll_rn(va * kOne))
+                                           - (static_cast<uint32_t>(o.v0) << CFG::ROW_SHIFT));
                     ea.z = __uint_as_float(static_cast<uint32_t>(__double2ll_rn(dv * kOne)));
                     // detector rows of the first and last slice; one cell of slack against rounding
                     const double first = vb + static_cast<double>(o.v0 - CFG::BIAS), last = first + dv * (CFG::TZ - 1);
@@ -585,13 +615,13 @@ namespace pb
             const float* tb = tab_b + (p & 1) * CFG::COLS;
             const uint32_t* tc = tab_c + (p & 1) * CFG::COLS;
             if(o.all_valid == 1)
-                consume<CFG, false>(acc, ta, tb, tc, col0, lane);
+                consume<CFG, false>(acc, ta, tb, tc, col0, lane, lane_z);
             else if(o.all_valid == 0)
             {
                 if(o.fits)
-                    consume<CFG, true>(acc, ta, tb, tc, col0, lane);
+                    consume<CFG, true>(acc, ta, tb, tc, col0, lane, lane_z);
                 else
-                    consume<CFG, true, true>(acc, ta, tb, tc, col0, lane);
+                    consume<CFG, true, true>(acc, ta, tb, tc, col0, lane, lane_z);
             }
 
             __syncthreads(); // stage and table[p&1] are free again; table[(p+1)&1] is complete
@@ -610,10 +640,14 @@ namespace pb
         #pragma unroll
         for(int i = 0; i < CFG::CPW; ++i)
         {
-            float lo, hi;
-            unpack2(acc[i], lo, hi);
-            scratch[lane * kPitch + col0 + i] = lo;
-            scratch[(lane + 32u) * kPitch + col0 + i] = hi;
+            #pragma unroll
+            for(int j = 0; j < CFG::NZ / 2; ++j)
+            {
+                float lo, hi;
+                unpack2(acc[i][j], lo, hi);
+                scratch[(lane + 64u * j) * kPitch + col0 + i] = lo;
+                scratch[(lane + 64u * j + 32u) * kPitch + col0 + i] = hi;
+            }
         }
         __syncthreads();
         for(int e = tid; e < CFG::TZ * CFG::COLS; e += CFG::THREADS)
@@ -765,6 +799,11 @@ namespace pb
     // traffic are covered by the other CTA's interpolation work
     using cfg_fine_half         = tile_cfg<16, 8, 2, 16, 32, 96, 5>;
     using cfg_coarse_split_half = tile_cfg<16, 8, 2, 16, 52, 168, 3, true>;
+    // tall tiles: 8 x 8 columns x 128 slices, four slices per lane -- the per-(column, projection) table entry is
+    // read once per FOUR updates of a lane and built for half as many columns per voxel; used when the slab is
+    // at least one such tile thick
+    using cfg_fine_tall         = tile_cfg<8, 8, 4, 8, 24, 176, 4>;
+    using cfg_coarse_split_tall = tile_cfg<8, 8, 4, 8, 32, 312, 2, true>;
 
     template <class CFG>
     static bool fits_cfg(const bp_geometry& g)
@@ -789,7 +828,7 @@ namespace pb
     {
         *handled = false;
         const bool aligned = (reinterpret_cast<uintptr_t>(d_stack) % 16u) == 0u && (g.pitch % 8u) == 0u;
-        const bool half = ctx->bp_tile != 1;   // 0 = automatic (half tiles when they fit), 1 = full tiles only
+        const bool half = ctx->bp_tile != 1;   // 0 = automatic (tall, then half tiles when they fit), 1 = full tiles only, 2 = half or full
 #define PB_TRY_CFG(CFG)                                                                            \
         if(fits_cfg<CFG>(g))                                                                       \
         {                                                                                          \
@@ -797,16 +836,21 @@ namespace pb
             *handled = true;                                                                       \
             return PARIS_B200_OK;                                                                  \
         }
+        const bool tall = ctx->bp_tile == 0 && g.v_dim_z >= 128u;
         if(aligned)
         {
             if(g.layout == kLayoutSplit2)
             {
+                if(tall)
+                    PB_TRY_CFG(cfg_coarse_split_tall)
                 if(half)
                     PB_TRY_CFG(cfg_coarse_split_half)
                 PB_TRY_CFG(cfg_coarse_split)
             }
             else
             {
+                if(tall)
+                    PB_TRY_CFG(cfg_fine_tall)
                 if(half)
                     PB_TRY_CFG(cfg_fine_half)
                 PB_TRY_CFG(cfg_fine)
