@@ -159,6 +159,19 @@ def ncu_traffic(kernel: str):
     return best
 
 
+def ncu_metric(kernel: str, metric: str):
+    """One metric of `kernel` from the committed ncu summary (profiles/*_ncu_summary.json); None if absent."""
+    import glob
+    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json")), reverse=True):
+        try:
+            rec = json.load(open(path)).get(kernel)
+        except (OSError, ValueError):
+            continue
+        if rec and metric in rec:
+            return rec[metric]
+    return None
+
+
 def measured_peaks() -> dict:
     try:
         return json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
@@ -364,13 +377,20 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                          "unit": "GB/s", "frac": bp_gbs / smem_peak, "traffic": ncu_traffic("backprojection"),
                          "traffic_note": "DRAM bytes per 64-projection launch (ncu, profiles/); algorithmic smem bytes per "
                                          f"launch = {16.0 * my_updates * min(rec.batch, n_proj) / n_proj:.3e}",
+                         "pipe_busy_ncu_pct": ncu_metric("backprojection",
+                                                         "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed"),
+                         "pipe_busy_note": "ncu: share of cycles the L1/shared-memory data pipe is busy for this kernel "
+                                           "(algorithmic bytes + bank conflicts + table broadcasts), profiles/",
                          "note": "16 B of shared-memory sample fetches per voxel update; peak = 148 SMs x 128 B/clk x "
                                  f"{sm_mhz:.0f} MHz (SM clock sampled during the run); not an HBM- or tensor-bound kernel"},
             "roofline_filter": {"kernel": "filter_kernel", "bound": "hbm", "achieved": filt_gbs, "peak": hbm_peak,
                                 "unit": "GB/s", "frac": filt_gbs / hbm_peak, "traffic": ncu_traffic("fused"),
                                 "traffic_note": "DRAM bytes per 64-projection launch (ncu, profiles/); algorithmic = "
                                                 f"{8.0 * px * min(64, rec.my_count):.3e}",
-                                "note": f"8 B per detector pixel; peak {peak_src} (MEASURED_PEAKS.json hbm_gbs)"},
+                                "pipe_busy_ncu_pct": ncu_metric("fused",
+                                                                "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed"),
+                                "note": f"8 B per detector pixel; peak {peak_src} (MEASURED_PEAKS.json hbm_gbs); ~110 flop and "
+                                        "~30 shared-memory accesses per pixel keep it on the FP32/shared-memory side of the ridge"},
             "e2e": {"value": updates / (e2e_step / 1e3) / 1e9, "unit": "GUPS", "seconds": e2e_step / 1e3,
                     "h2d_bytes_per_step": 4 * px * n_proj, "d2h_bytes_per_step": 4 * voxels,
                     "ms_steps": [round(x, 2) for x in e2e_ms],
