@@ -295,7 +295,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     ctx.sync()
     barrier()
     sampler.start()
-    launches0 = ctx.launch_count()
+    launches0 = rec.launch_count()
     t_filter = t_gather = t_bp = 0.0
     t0 = time.perf_counter()
     e_start = ctx.event()
@@ -313,7 +313,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     ctx.sync()
     barrier()
     wall_resident = time.perf_counter() - t0
-    launches = ctx.launch_count() - launches0
+    launches = rec.launch_count() - launches0
     clocks = sampler.stop()
     if world > 1:
         # stage breakdown (diagnostic, outside the timed region): the same work without overlap

@@ -96,8 +96,16 @@ class MultiGpuReconstructor:
             self.d_stack = self._torch_stack.data_ptr()
             self._ext_stream = torch.cuda.ExternalStream(self.ctx.stream(), device=torch.device("cuda", device))
             self._comm_stream = torch.cuda.Stream(device=torch.device("cuda", device), priority=-1)
+            # uploads and the fused weight+filter kernel run in a context of their own (own streams, own buffer
+            # pool): a stream is in-order, so filter launches queued behind a long backprojection would hold back
+            # the exchange the NEXT backprojection waits for, and a backprojection queued behind a filter launch
+            # would wait for that filter's upload
+            self.fctx = capi.Context(device)
+            self.fctx.set_option("bp_batch", batch)   # (sizes its projection buffer pool)
+            self._filter_stream = torch.cuda.ExternalStream(self.fctx.stream(), device=torch.device("cuda", device))
         else:
             self.d_stack = self.ctx.stack_alloc(det.n_row, det.n_col, self.slots)
+            self.fctx = self.ctx
         self.d_raw = None
         self.h_raw = None
         self.h_slab = capi.PinnedArray((plan.slab_dz, self.region[1], self.region[0]))
@@ -120,6 +128,13 @@ class MultiGpuReconstructor:
                 self.ctx.proj_d2h(self.d_raw + i * self.px * 4, self.h_raw.ptr + i * self.px * 4, self.det.n_row,
                                   self.det.n_col)
         self.ctx.sync()
+
+    def launch_count(self) -> int:
+        """Kernel launches issued so far by this reconstructor's context(s)."""
+        n = self.ctx.launch_count()
+        if self.fctx is not self.ctx:
+            n += self.fctx.launch_count()
+        return n
 
     def global_index(self, local: int) -> int:
         """Scan index (= stack slot) of this rank's local projection `local`."""
@@ -164,34 +179,42 @@ class MultiGpuReconstructor:
                                    layout=self.layout)
 
     def _pipelined(self, upload: bool):
-        """N > 1: per round, filter my m projections -> all-gather the round (comm stream) -> backproject rounds that
-        were gathered EARLIER, so the exchange of round c hides behind the backprojection of the rounds before it.
-        The first round is backprojected on its own (work starts as early as possible); afterwards as many rounds as
-        fit one batch share a launch (the volume tile traffic and the kernel prologue amortise over more projections)."""
-        ctx, torch = self.ctx, self._torch
+        """N > 1: per round, upload + filter my m projections (filter context) -> all-gather the round (comm stream)
+        -> backproject groups of rounds (compute context).  Three independent streams ordered only by events, so the
+        exchange of a round hides behind the backprojection of the rounds before it and nothing waits for an upload
+        it does not need.  The first groups are short (1, 2, 4 rounds: work starts early); afterwards as many rounds
+        as fit one batch share a launch (volume tile traffic and kernel prologue amortise over more projections)."""
+        ctx, fctx, torch = self.ctx, self.fctx, self._torch
         w, m = self.plan.world, self.m
         slot_floats = self.slot_bytes // 4
         trace = os.environ.get("PARIS_B200_TRACE") and upload
         t_begin = time.perf_counter()
+        # the stack slots are rewritten: the previous step's backprojection must have read them
+        prev_done = torch.cuda.Event()
+        prev_done.record(self._ext_stream)
+        self._filter_stream.wait_event(prev_done)
         ctx.volume_clear(self.d_vol, *self.slab_dims)
-        gathered = []
-        group = max(1, self.batch // (w * m))   # rounds per backprojection launch
-        next_bp = 0                             # first round not backprojected yet
+        g_max = max(1, self.batch // (w * m))
+        bounds, size = [0], 1
+        while bounds[-1] < self.rounds:
+            bounds.append(min(self.rounds, bounds[-1] + size))
+            size = min(g_max, size * 2)
+        group_of_last_round = {bounds[i + 1] - 1: i for i in range(len(bounds) - 1)}
         for rd in range(self.rounds):
             first = rd * w * m
             mine_first = first + self.plan.rank * m
             if upload:
                 for j in range(m):
                     i = rd * m + j
-                    d = ctx.dev_alloc(self.px * 4)
-                    ctx.proj_h2d(self.h_raw.ptr + i * self.px * 4, d, self.det.n_row, self.det.n_col)
-                    ctx.filter_to_stack(d, self.det, self.filter, self.d_stack, mine_first + j, self.layout)
-                    ctx.dev_free(d)
+                    d = fctx.dev_alloc(self.px * 4)
+                    fctx.proj_h2d(self.h_raw.ptr + i * self.px * 4, d, self.det.n_row, self.det.n_col)
+                    fctx.filter_to_stack(d, self.det, self.filter, self.d_stack, mine_first + j, self.layout)
+                    fctx.dev_free(d)
             else:
-                ctx.filter_to_stack_batch(self.d_raw + rd * m * self.px * 4, self.px, m, self.det, self.filter,
-                                          self.d_stack, mine_first, self.layout)
+                fctx.filter_to_stack_batch(self.d_raw + rd * m * self.px * 4, self.px, m, self.det, self.filter,
+                                           self.d_stack, mine_first, self.layout)
             filtered = torch.cuda.Event()
-            filtered.record(self._ext_stream)
+            filtered.record(self._filter_stream)
             with torch.cuda.stream(self._comm_stream):
                 self._comm_stream.wait_event(filtered)
                 out = self._torch_stack[first * slot_floats:(first + w * m) * slot_floats]
@@ -199,15 +222,12 @@ class MultiGpuReconstructor:
                 self.dist.all_gather_into_tensor(out, mine)
                 done = torch.cuda.Event()
                 done.record(self._comm_stream)
-            gathered.append(done)
-            ready = rd - next_bp                # rounds whose exchange was issued before this one
-            if ready >= (1 if next_bp == 0 else group):
-                self._ext_stream.wait_event(gathered[rd - 1])
-                self._backproject(next_bp * w * m, ready * w * m)
-                next_bp = rd
+            if rd in group_of_last_round:
+                g = group_of_last_round[rd]
+                self._ext_stream.wait_event(done)
+                self._backproject(bounds[g] * w * m, (bounds[g + 1] - bounds[g]) * w * m,
+                                  download=upload and rd == self.rounds - 1)
         t_submitted = time.perf_counter()
-        self._ext_stream.wait_event(gathered[-1])
-        self._backproject(next_bp * w * m, (self.rounds - next_bp) * w * m, download=upload)
         if trace:
             t_end = time.perf_counter()
             print(f"[trace rank {self.plan.rank}] rounds submitted in {(t_submitted - t_begin) * 1e3:.1f} ms, "
@@ -270,6 +290,9 @@ class MultiGpuReconstructor:
 
     def close(self):
         self.ctx.sync()
+        if self.fctx is not self.ctx:
+            self.fctx.sync()
+            self.fctx.close()
         self.ctx.filter_destroy(self.filter)
         self.ctx.volume_free(self.d_vol)
         if self.dist is None:
