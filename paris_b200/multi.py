@@ -55,6 +55,24 @@ class SlabPlan:
         return best
 
 
+def round_schedule(n_proj: int, world: int, first_round: int = 64, max_round: int = 256):
+    """Projections per rank and round for the pipelined exchange: rounds of world*m consecutive projections with m
+    growing 2x from first_round/world up to max_round/world -- short rounds first so that the backprojection starts
+    early, long ones afterwards (few large all-gathers overlap with the backprojection far better than many small
+    ones).  Empty if the scan does not divide evenly among the ranks (callers fall back to one big all-gather)."""
+    if n_proj % world:
+        return []
+    remaining, cap, ms = n_proj // world, max(first_round, world), []
+    while remaining > 0:
+        m = min(remaining, max(1, cap // world))
+        if remaining - m < max(1, m // 4):   # do not leave a sliver for the last round
+            m = remaining
+        ms.append(m)
+        remaining -= m
+        cap = min(max(max_round, world), cap * 2)
+    return ms
+
+
 class MultiGpuReconstructor:
     def __init__(self, device: int, det: capi.DetectorGeometry, vol: capi.VolumeGeometry, n_proj: int,
                  plan: SlabPlan, dist=None, batch: int = 256, roi: capi.Roi | None = None, region=None,
@@ -74,10 +92,12 @@ class MultiGpuReconstructor:
         self.lo, self.hi, self.chunk = plan.projection_block(n_proj)
         self.my_count = self.hi - self.lo
         # pipelined exchange (N > 1): block-cyclic ownership, m projections per rank and round
-        # (rounds of at most `gather_round` projections are exchanged; up to `batch` gathered projections share one
-        # backprojection launch)
-        self.m = plan.cyclic_blocks(n_proj, min(batch, gather_round)) if dist is not None else 0
-        self.rounds = (n_proj // (plan.world * self.m)) if self.m else 0
+        # (the first exchanged round holds at most `gather_round` projections, later ones up to `batch`)
+        gather_round = int(os.environ.get("PARIS_B200_GATHER_ROUND", gather_round))
+        self.ms = round_schedule(n_proj, plan.world, min(batch, gather_round), batch) if dist is not None else []
+        self.rounds = len(self.ms)
+        self.m = self.ms[0] if self.ms else 0                       # (non-zero = pipelined exchange available)
+        self.local_start = [sum(self.ms[:r]) for r in range(self.rounds + 1)]   # first local projection of round r
         self.slot_bytes, self.pitch = capi.stack_slot_bytes(det.n_row, det.n_col)
         self.layout = capi.choose_stack_layout(det, vol)
         self.slots = self.chunk * plan.world
@@ -120,8 +140,8 @@ class MultiGpuReconstructor:
             if self.m:
                 # local projection i = round*m + j  <->  global index round*world*m + rank*m + j
                 for rd in range(self.rounds):
-                    self.ctx.phantom_project(ellipsoids_mm, self.det, self.global_index(rd * self.m), self.m,
-                                             self.d_raw + rd * self.m * self.px * 4)
+                    self.ctx.phantom_project(ellipsoids_mm, self.det, self.global_index(self.local_start[rd]),
+                                             self.ms[rd], self.d_raw + self.local_start[rd] * self.px * 4)
             else:
                 self.ctx.phantom_project(ellipsoids_mm, self.det, self.lo, self.my_count, self.d_raw)
             for i in range(self.my_count):
@@ -140,8 +160,9 @@ class MultiGpuReconstructor:
         """Scan index (= stack slot) of this rank's local projection `local`."""
         if not self.m:
             return self.lo + local
-        rd, j = divmod(local, self.m)
-        return rd * self.plan.world * self.m + self.plan.rank * self.m + j
+        rd = max(r for r in range(self.rounds) if self.local_start[r] <= local)
+        j = local - self.local_start[rd]
+        return self.plan.world * self.local_start[rd] + self.plan.rank * self.ms[rd] + j
 
     def host_sample(self, count: int, stride: int = 1) -> np.ndarray:
         return np.ascontiguousarray(self.h_raw.array[::stride][:count])
@@ -153,10 +174,11 @@ class MultiGpuReconstructor:
         torch = self._torch
         if self.m:
             slot_floats = self.slot_bytes // 4
-            w, m = self.plan.world, self.m
+            w = self.plan.world
             with torch.cuda.stream(self._ext_stream):
                 for rd in range(self.rounds):
-                    first = rd * w * m
+                    m = self.ms[rd]
+                    first = w * self.local_start[rd]
                     mine_first = first + self.plan.rank * m
                     self.dist.all_gather_into_tensor(self._torch_stack[first * slot_floats:(first + w * m) * slot_floats],
                                                      self._torch_stack[mine_first * slot_floats:(mine_first + m) * slot_floats])
@@ -182,10 +204,9 @@ class MultiGpuReconstructor:
         """N > 1: per round, upload + filter my m projections (filter context) -> all-gather the round (comm stream)
         -> backproject groups of rounds (compute context).  Three independent streams ordered only by events, so the
         exchange of a round hides behind the backprojection of the rounds before it and nothing waits for an upload
-        it does not need.  The first groups are short (1, 2, 4 rounds: work starts early); afterwards as many rounds
-        as fit one batch share a launch (volume tile traffic and kernel prologue amortise over more projections)."""
+        it does not need.  Rounds grow from `gather_round` to one batch of projections (round_schedule)."""
         ctx, fctx, torch = self.ctx, self.fctx, self._torch
-        w, m = self.plan.world, self.m
+        w = self.plan.world
         slot_floats = self.slot_bytes // 4
         trace = os.environ.get("PARIS_B200_TRACE") and upload
         t_begin = time.perf_counter()
@@ -194,40 +215,56 @@ class MultiGpuReconstructor:
         prev_done.record(self._ext_stream)
         self._filter_stream.wait_event(prev_done)
         ctx.volume_clear(self.d_vol, *self.slab_dims)
-        g_max = max(1, self.batch // (w * m))
-        bounds, size = [0], 1
-        while bounds[-1] < self.rounds:
-            bounds.append(min(self.rounds, bounds[-1] + size))
-            size = min(g_max, size * 2)
-        group_of_last_round = {bounds[i + 1] - 1: i for i in range(len(bounds) - 1)}
+        ev_trace = os.environ.get("PARIS_B200_TRACE_EVENTS")
+        if ev_trace:
+            t_ev0 = torch.cuda.Event(enable_timing=True)
+            t_ev0.record(self._ext_stream)
+            comm_marks = []
         for rd in range(self.rounds):
-            first = rd * w * m
+            m = self.ms[rd]
+            local0 = self.local_start[rd]
+            first = w * local0                      # the round's first stack slot = first projection of the scan
             mine_first = first + self.plan.rank * m
             if upload:
                 for j in range(m):
-                    i = rd * m + j
                     d = fctx.dev_alloc(self.px * 4)
-                    fctx.proj_h2d(self.h_raw.ptr + i * self.px * 4, d, self.det.n_row, self.det.n_col)
+                    fctx.proj_h2d(self.h_raw.ptr + (local0 + j) * self.px * 4, d, self.det.n_row, self.det.n_col)
                     fctx.filter_to_stack(d, self.det, self.filter, self.d_stack, mine_first + j, self.layout)
                     fctx.dev_free(d)
             else:
-                fctx.filter_to_stack_batch(self.d_raw + rd * m * self.px * 4, self.px, m, self.det, self.filter,
-                                           self.d_stack, mine_first, self.layout)
+                for done_m in range(0, m, 64):      # (a filter launch covers at most 256 projections)
+                    n = min(64, m - done_m)
+                    fctx.filter_to_stack_batch(self.d_raw + (local0 + done_m) * self.px * 4, self.px, n, self.det,
+                                               self.filter, self.d_stack, mine_first + done_m, self.layout)
             filtered = torch.cuda.Event()
             filtered.record(self._filter_stream)
             with torch.cuda.stream(self._comm_stream):
                 self._comm_stream.wait_event(filtered)
                 out = self._torch_stack[first * slot_floats:(first + w * m) * slot_floats]
                 mine = self._torch_stack[mine_first * slot_floats:(mine_first + m) * slot_floats]
+                if ev_trace:
+                    a = torch.cuda.Event(enable_timing=True)
+                    a.record(self._comm_stream)
                 self.dist.all_gather_into_tensor(out, mine)
-                done = torch.cuda.Event()
+                done = torch.cuda.Event(enable_timing=bool(ev_trace))
                 done.record(self._comm_stream)
-            if rd in group_of_last_round:
-                g = group_of_last_round[rd]
-                self._ext_stream.wait_event(done)
-                self._backproject(bounds[g] * w * m, (bounds[g + 1] - bounds[g]) * w * m,
-                                  download=upload and rd == self.rounds - 1)
+                if ev_trace:
+                    comm_marks.append((a, done))
+            # every round is backprojected as soon as it has arrived (backproject_stack cuts it into launches of at
+            # most one batch)
+            self._ext_stream.wait_event(done)
+            self._backproject(first, w * m, download=upload and rd == self.rounds - 1)
         t_submitted = time.perf_counter()
+        if ev_trace:
+            t_ev1 = torch.cuda.Event(enable_timing=True)
+            t_ev1.record(self._ext_stream)
+            t_ev1.synchronize()
+            busy = sum(a.elapsed_time(b) for a, b in comm_marks)
+            ends = [t_ev0.elapsed_time(b) for _, b in comm_marks]
+            if self.plan.rank == 0:
+                print(f"[events] step {t_ev0.elapsed_time(t_ev1):.1f} ms; exchange busy {busy:.1f} ms over {len(comm_marks)} "
+                      f"rounds of {[w * x for x in self.ms]}; round ends at {[round(e, 1) for e in ends[:4]]} ... {[round(e, 1) for e in ends[-3:]]}",
+                      flush=True)
         if trace:
             t_end = time.perf_counter()
             print(f"[trace rank {self.plan.rank}] rounds submitted in {(t_submitted - t_begin) * 1e3:.1f} ms, "
@@ -244,8 +281,11 @@ class MultiGpuReconstructor:
         ctx.volume_clear(self.d_vol, *self.slab_dims)
         if self.m:
             for rd in range(self.rounds):
-                ctx.filter_to_stack_batch(self.d_raw + rd * self.m * self.px * 4, self.px, self.m, self.det, self.filter,
-                                          self.d_stack, self.global_index(rd * self.m), self.layout)
+                for done_m in range(0, self.ms[rd], 64):
+                    n = min(64, self.ms[rd] - done_m)
+                    local = self.local_start[rd] + done_m
+                    ctx.filter_to_stack_batch(self.d_raw + local * self.px * 4, self.px, n, self.det, self.filter,
+                                              self.d_stack, self.global_index(local), self.layout)
         elif self.my_count:
             ctx.filter_to_stack_batch(self.d_raw, self.px, self.my_count, self.det, self.filter, self.d_stack, self.lo,
                                       self.layout)

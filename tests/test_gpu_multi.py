@@ -42,11 +42,11 @@ def _worker(rank, world, port, out_dir):
     try:
         det, vol, n_proj = _case()
         plan = SlabPlan(vol.dim_z, world, rank)
-        # rounds of 2 x 4 projections are exchanged, up to 16 gathered projections share a backprojection launch
+        # exchanged rounds grow from 2 x 4 to 2 x 8 projections (one batch)
         rec = MultiGpuReconstructor(rank, det, vol, n_proj, plan, dist, batch=16, gather_round=8)
         ell = phantom.scaled_ellipsoids(phantom.SHEPP_LOGAN_3D, 0.9 * phantom.fov_radius(det.n_row, 0.4, 0, 500, 500))
         rec.generate_inputs(ell)
-        assert rec.m == 4 and rec.rounds == 6
+        assert rec.ms == [4, 8, 8, 4]
         rec.step_e2e()                       # pipelined, from pinned host memory
         a = rec.slab().copy()
         rec.step_resident(overlap=False)     # one big all-gather, then everything

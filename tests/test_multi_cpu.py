@@ -118,3 +118,23 @@ def test_block_cyclic_rounds_keep_projection_order(n_proj, world):
 
 def test_block_cyclic_falls_back_when_uneven():
     assert SlabPlan(64, 8, 0).cyclic_blocks(721, 64) == 0
+
+
+@pytest.mark.parametrize("n_proj,world,first,large", [(720, 8, 64, 256), (720, 2, 64, 256), (1440, 8, 64, 256),
+                                                      (2880, 8, 64, 256), (48, 2, 8, 16), (12, 3, 64, 256), (720, 4, 64, 64)])
+def test_round_schedule_covers_the_scan_in_order(n_proj, world, first, large):
+    """Growing rounds: round r is world*m_r CONSECUTIVE projections, rank k owns the k-th block of m_r; together the
+    rounds cover the scan exactly once, in order; no round exceeds one batch (plus the merged sliver)."""
+    from paris_b200.multi import round_schedule
+    ms = round_schedule(n_proj, world, first, large)
+    assert sum(ms) * world == n_proj and all(m >= 1 for m in ms)
+    assert ms[0] * world <= max(first, world) or len(ms) == 1
+    assert all(m * world <= large * 1.25 + world for m in ms)
+    assert all(b >= a for a, b in zip(ms[:-2], ms[1:-1]))          # non-decreasing up to the last (remainder) round
+    start, seen = 0, []
+    for m in ms:
+        for k in range(world):
+            seen += list(range(start + k * m, start + (k + 1) * m))
+        start += world * m
+    assert seen == list(range(n_proj))
+    assert round_schedule(721, 8) == []
