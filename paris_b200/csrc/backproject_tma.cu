@@ -836,7 +836,14 @@ namespace pb
             *handled = true;                                                                       \
             return PARIS_B200_OK;                                                                  \
         }
-        const bool tall = ctx->bp_tile == 0 && g.v_dim_z >= 128u;
+        // Tiles are anchored at multiples of the tile size in GLOBAL voxel indices, so a region whose offsets are not
+        // multiples of the tile size pays for partly empty tiles; the tall tile (fastest per voxel) is used only when
+        // the voxels its tiles cover, times its relative cost per voxel, are fewer than the half tile's.
+        auto covered = [&](uint32_t tx, uint32_t ty, uint32_t tz) {
+            auto span = [](uint32_t off, uint32_t dim, uint32_t t) { return ((off + dim - 1u) / t - off / t + 1u) * static_cast<double>(t); };
+            return span(g.off_x, g.v_dim_x, tx) * span(g.off_y, g.v_dim_y, ty) * span(g.off_z, g.v_dim_z, tz);
+        };
+        const bool tall = ctx->bp_tile == 0 && covered(8, 8, 128) <= 1.035 * covered(16, 8, 64);
         if(aligned)
         {
             if(g.layout == kLayoutSplit2)

@@ -246,6 +246,61 @@ def test_full_size_config4_roi_offset_detector(ctx):
     assert np.isfinite(full).all() and full.max() > 0.5 * 1.0 * c * 0.2
 
 
+def test_full_size_config5_slabs_stream_over_one_filtered_stack(ctx):
+    """BASELINE config 5 geometry at full size: the 2048^3 region (z in [5, 2053) of the 2048 x 2048 x 2058 natural
+    volume) from 2880 projections of a 2048^2 detector, reconstructed slab by slab from ONE filtered stack (the
+    reference re-reads and re-filters the whole scan for every sub-volume, src/main.cpp:93-105).  Two adjacent
+    128-slice slabs of the 16 are computed here: streamed separately they must be bit-identical to the same 256
+    slices computed in one piece, and bands of them must agree with the exact kernel."""
+    n, n_proj, k = 2048, 2880, 2048
+    l_px = 0.1
+    det = capi.DetectorGeometry(n, n, l_px, l_px, 0, 0, 500, 500, 360.0 / n_proj)
+    nat = capi.calculate_volume_geometry(det)
+    assert (nat.dim_x, nat.dim_y, nat.dim_z) == (2048, 2048, 2058)
+    roi = capi.Roi(0, 2047, 0, 2047, 5, 2053)
+    reg = capi.apply_roi(nat, roi)
+    assert (reg.dim_x, reg.dim_y, reg.dim_z) == (k, k, k)
+    layout = capi.choose_stack_layout(det, nat)
+    stack = ctx.stack_alloc(n, n, n_proj)                               # 48 GB, filled once
+    filt = ctx.filter_create(capi.filter_size(n), l_px)
+    ell = phantom.scaled_ellipsoids(phantom.SHEPP_LOGAN_3D, 0.9 * phantom.fov_radius(n, l_px, 0, 500, 500))
+    raw = ctx.dev_alloc(64 * n * n * 4)
+    for first in range(0, n_proj, 64):
+        ctx.phantom_project(ell, det, first, 64, raw)
+        ctx.filter_to_stack_batch(raw, n * n, 64, det, filt, stack, first, layout)
+    ctx.dev_free(raw)
+    sc = np.array([angle_sin_cos(i, det) for i in range(n_proj)], dtype=np.float32)
+    slab = 128                                                          # 16 slabs of 128 slices
+
+    def reconstruct(z_first, dz, kernel):
+        ctx.set_option("bp_kernel", kernel)
+        v = ctx.volume_alloc(k, k, dz)
+        e0 = ctx.event()
+        ctx.backproject_stack(stack, 0, n_proj, sc[:, 0], sc[:, 1], v, (k, k, dz), z_first, det, nat, roi=roi, layout=layout)
+        e1 = ctx.event()
+        ms = ctx.elapsed_ms(e0, e1)
+        out = np.empty((dz, k, k), np.float32)
+        ctx.vol_d2h(v, out, dz * k * k)
+        ctx.volume_free(v)
+        return out, ms
+
+    a, ms_a = reconstruct(7 * slab, slab, 2)
+    b, _ = reconstruct(8 * slab, slab, 2)
+    print(f"config 5 slab of {slab} slices: {k * k * slab * n_proj / ms_a / 1e6:.0f} GUPS ({ms_a:.0f} ms)")
+    both, _ = reconstruct(7 * slab, 2 * slab, 2)
+    assert np.array_equal(both[:slab], a) and np.array_equal(both[slab:], b)
+    c = contrast(n_proj)
+    for z, src in ((7 * slab, a), (9 * slab - 2, b)):
+        exact, _ = reconstruct(z, 2, 1)
+        got = src[z - (7 * slab if src is a else 8 * slab):][:2]
+        mx, rms = errors(got, exact, c)
+        print(f"config 5 band at z={z}: fast vs exact kernel max {mx:.2e} C, rmse {rms:.2e} C")
+        assert mx <= MAX_ABS_TOL and rms <= RMSE_TOL
+    ctx.set_option("bp_kernel", 0)
+    ctx.filter_destroy(filt)
+    ctx.stack_free(stack)
+
+
 @pytest.mark.parametrize("n_row,n_col", [(96, 96), (100, 37), (256, 64), (1024, 16), (2048, 8), (3000, 5)])
 @pytest.mark.parametrize("layout", [capi.LAYOUT_PLAIN, capi.LAYOUT_SPLIT2])
 def test_filter_to_stack_layouts(ctx, port, n_row, n_col, layout):
