@@ -600,9 +600,11 @@ static int backproject_and_download(paris_b200_ctx* ctx, const float* d_stack, s
         c.d_vol = t.d_vol + static_cast<size_t>(z) * slice;
         c.v_dim_z = end - z;
         c.v_offset = t.v_offset + z;
+        const uint32_t launches = (count + static_cast<uint32_t>(ctx->bp_batch) - 1u) / static_cast<uint32_t>(ctx->bp_batch);
+        const uint32_t per_launch = launches > 0u ? (count + launches - 1u) / launches : 0u;
         for(uint32_t done = 0; done < count;)
         {
-            const uint32_t n = std::min<uint32_t>(count - done, static_cast<uint32_t>(ctx->bp_batch));
+            const uint32_t n = std::min<uint32_t>(count - done, per_launch);
             PB_TRY(launch_backproject(ctx, d_stack, slot_floats, pitch, first + done, n, sn + done, cs + done, c, layout));
             done += n;
         }
@@ -1119,9 +1121,12 @@ extern "C" int paris_b200_backproject_stack(paris_b200_ctx* ctx, const float* d_
     t.delta_t_mm = det->delta_t * det->l_px_col;
     const uint32_t pitch = stack_pitch_for(det->n_col);
     const size_t slot_floats = static_cast<size_t>(pitch) * det->n_row;
+    // launches of (nearly) equal size: 272 projections go as 136 + 136, not 256 + 16
+    const uint32_t launches = (count + static_cast<uint32_t>(ctx->bp_batch) - 1u) / static_cast<uint32_t>(ctx->bp_batch);
+    const uint32_t per_launch = launches > 0u ? (count + launches - 1u) / launches : 0u;
     for(uint32_t done = 0; done < count;)
     {
-        const uint32_t n = std::min<uint32_t>(count - done, static_cast<uint32_t>(ctx->bp_batch));
+        const uint32_t n = std::min<uint32_t>(count - done, per_launch);
         PB_TRY(launch_backproject(ctx, d_stack, slot_floats, pitch, first + done, n, sin_phi + done, cos_phi + done, t,
                                   layout));
         done += n;

@@ -47,7 +47,7 @@ namespace pb
         static constexpr int WARPS = COLS / CPW;          // one warp per group of CPW columns
         static constexpr int THREADS = 32 * WARPS;
         static constexpr int STAGE_BYTES = BH * BV * 4;
-        static constexpr int TAB_BYTES = COLS * (16 + 4 + 4);  // float4 + 2 floats per column
+        static constexpr int TAB_BYTES = COLS * (16 + 4 + 4 + 4);  // float4 + 3 words per column
         static constexpr size_t SMEM = size_t(STAGES) * STAGE_BYTES + 2 * TAB_BYTES + kMaxBatch * 16 + STAGES * 8 + 128;
         // fixed point: rows are carried with a bias of BV so that they stay non-negative on boundary tiles
         static constexpr int FRAC = 23;
@@ -321,9 +321,12 @@ namespace pb
     // MIXED: the tile has voxels on both sides of the detector border (per-slice validity from the table);
     // CLAMP: additionally the box may not cover the tile's rows (never the case for launches that passed the
     // host-side footprint check; kept as the safe path)
-    template <class CFG, bool MIXED, bool CLAMP = false>
+    // STRADDLE: the tile is anchored at the slab's own first slice and may cross one row anchor; slices beyond it
+    // (bit 2j / 2j+1 of `beyond` for the two slices of pair j) take the row word of the second anchor from tab_d.
+    template <class CFG, bool MIXED, bool CLAMP = false, bool STRADDLE = false>
     __device__ __forceinline__ void consume(uint64_t (&acc)[CFG::CPW][CFG::NZ / 2], const float4* __restrict__ tab_a,
                                             const float* __restrict__ tab_b, const uint32_t* __restrict__ tab_c,
+                                            const uint32_t* __restrict__ tab_d, uint32_t beyond,
                                             int col0, uint32_t lane, uint32_t lane_z)
     {
         static_assert(CFG::NZ % 2 == 0, "the slices of a lane are processed as packed f32x2 pairs (l + 64j, l + 64j + 32)");
@@ -349,12 +352,21 @@ namespace pb
                 rel = lane - (vs & 0xffu);
                 count = vs >> 8;
             }
-            uint32_t v0 = dv * lane_z + __float_as_uint(ea.y);   // slice `lane` (lane_z counts from the row anchor)
+            // slice `lane` (lane_z counts from the row anchor); with STRADDLE the anchor's row word is added per slice
+            uint32_t v0 = STRADDLE ? dv * lane_z : dv * lane_z + __float_as_uint(ea.y);
+            uint32_t vb_second = 0;
+            if(STRADDLE)
+                vb_second = tab_d[col0 + i];
             #pragma unroll
             for(int j = 0; j < CFG::NZ / 2; ++j)
             {
                 uint32_t v1 = v0 + (dv << 5);                    // slice `lane + 64j + 32`: 32 steps of dv further
                 uint32_t va = v0;
+                if(STRADDLE)
+                {
+                    va += ((beyond >> (2 * j)) & 1u) ? vb_second : __float_as_uint(ea.y);
+                    v1 += ((beyond >> (2 * j + 1)) & 1u) ? vb_second : __float_as_uint(ea.y);
+                }
                 if(CLAMP)
                 {
                     // rows may lie outside the staged box: keep the address inside, the value is discarded below
@@ -383,7 +395,7 @@ namespace pb
         }
     }
 
-    template <class CFG>
+    template <class CFG, bool STRADDLE = false>
     __global__ void __launch_bounds__(CFG::THREADS, CFG::THREADS <= 256 ? 2 : 1)
     bp_tma_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ vol, const bp_geometry g,
                   const bp_angles ang, const uint32_t first_slot)
@@ -393,7 +405,8 @@ namespace pb
         float4* tab_a = reinterpret_cast<float4*>(smem + size_t(CFG::STAGES) * CFG::STAGE_BYTES);
         float* tab_b = reinterpret_cast<float*>(tab_a + 2 * CFG::COLS);
         uint32_t* tab_c = reinterpret_cast<uint32_t*>(tab_b + 2 * CFG::COLS);
-        box_origin* origin = reinterpret_cast<box_origin*>(tab_c + 2 * CFG::COLS);
+        uint32_t* tab_d = tab_c + 2 * CFG::COLS;
+        box_origin* origin = reinterpret_cast<box_origin*>(tab_d + 2 * CFG::COLS);
         uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(origin) + kMaxBatch * 16);
 
         const int tid = threadIdx.x;
@@ -407,7 +420,10 @@ namespace pb
         // slabs and ROI blocks are bit-identical to the corresponding crop of the one-piece reconstruction.
         const uint32_t x0 = (g.off_x / CFG::TX + blockIdx.x) * CFG::TX;   // global index of the tile's first voxel
         const uint32_t y0 = (g.off_y / CFG::TY + blockIdx.y) * CFG::TY;
-        const uint32_t z0 = (g.off_z / CFG::TZ + blockIdx.z) * CFG::TZ;
+        // (z: the STRADDLE instantiation anchors its tiles at the slab's first slice instead -- no partly empty tile
+        // layers for regions whose z offset is not a multiple of the tile height; the ROW anchors below stay global,
+        // so the voxels are bit-identical either way)
+        const uint32_t z0 = STRADDLE ? g.off_z + blockIdx.z * CFG::TZ : (g.off_z / CFG::TZ + blockIdx.z) * CFG::TZ;
         // ---- prologue 1: barriers, box origins for every projection of the batch ---------------------------
         if(tid == 0)
         {
@@ -518,15 +534,27 @@ namespace pb
         // (16x16x64, 16x8x64, 8x8x128) computes bit-identical voxels and slabs thinner than a tall tile remain
         // bit-identical crops of the one-piece result.
         constexpr uint32_t kRowAnchor = 128u;
-        static_assert(kRowAnchor % CFG::TZ == 0 || CFG::TZ % kRowAnchor == 0, "tiles must not straddle anchors unevenly");
+        static_assert(kRowAnchor % CFG::TZ == 0, "a tile crosses at most one row anchor");
         const uint32_t z_anchor = (z0 / kRowAnchor) * kRowAnchor;
         const uint32_t lane_z = lane + (z0 - z_anchor);
+        // slices of this lane that lie beyond the next anchor (STRADDLE only): bit 2j for slice lane + 64j, bit 2j+1
+        // for slice lane + 64j + 32
+        uint32_t beyond = 0;
+        double z_mb = 0.0;
+        if(STRADDLE)
+        {
+            const uint32_t zb_local = z_anchor + kRowAnchor - z0;   // 1 .. 128
+            #pragma unroll
+            for(int jj = 0; jj < CFG::NZ; ++jj)
+                beyond |= (lane + 32u * jj >= zb_local ? 1u : 0u) << jj;
+        }
         if(builder)
         {
             bx_k = centered(x0 + tid % CFG::TX, g.full_x, g.l_vx_x);
             by_l = centered(y0 + tid / CFG::TX, g.full_y, g.l_vx_y);
             z_m0 = centered_d(z0, g.full_z, g.l_vx_z);
             z_ma = centered_d(z_anchor, g.full_z, g.l_vx_z);
+            z_mb = centered_d(z_anchor + kRowAnchor, g.full_z, g.l_vx_z);
         }
         const uint32_t stage_base0 = smem_u32(stage_mem);
         constexpr double kOne = static_cast<double>(1u << CFG::ROW_SHIFT);
@@ -543,6 +571,7 @@ namespace pb
                                     __uint_as_float(0u), 0.f);
             float eb = 0.f;
             uint32_t ec = static_cast<uint32_t>(CFG::TZ) << 8;   // every slice valid
+            uint32_t ed = static_cast<uint32_t>(CFG::BIAS) << CFG::ROW_SHIFT;   // (dead entry: same row as ea.y)
             int x1rel = 0;
             if(valid_x)
             {
@@ -566,6 +595,13 @@ namespace pb
                     ea.y = __uint_as_float(static_cast<uint32_t>(__double2ll_rn(va * kOne))
                                            - (static_cast<uint32_t>(o.v0) << CFG::ROW_SHIFT));
                     ea.z = __uint_as_float(static_cast<uint32_t>(__double2ll_rn(dv * kOne)));
+                    if(STRADDLE)
+                    {
+                        // the second anchor's row word, shifted so that the same dv * (z - first anchor) term applies
+                        const double vb2 = row_of(z_mb, fd, g) + static_cast<double>(CFG::BIAS);
+                        ed = static_cast<uint32_t>(__double2ll_rn(vb2 * kOne)) - (static_cast<uint32_t>(o.v0) << CFG::ROW_SHIFT)
+                           - __float_as_uint(ea.z) * kRowAnchor;
+                    }
                     // detector rows of the first and last slice; one cell of slack against rounding
                     const double first = vb + static_cast<double>(o.v0 - CFG::BIAS), last = first + dv * (CFG::TZ - 1);
                     const bool safe = fmin(first, last) >= 1.0 && fmax(first, last) + 2.0 <= static_cast<double>(g.p_dim_y) - 1.0;
@@ -594,6 +630,8 @@ namespace pb
             tab_a[(p & 1) * CFG::COLS + tid] = ea;
             tab_b[(p & 1) * CFG::COLS + tid] = eb;
             tab_c[(p & 1) * CFG::COLS + tid] = ec;
+            if(STRADDLE)
+                tab_d[(p & 1) * CFG::COLS + tid] = ed;
         };
 
         if(builder && count > 0)
@@ -614,14 +652,15 @@ namespace pb
             const float4* ta = tab_a + (p & 1) * CFG::COLS;
             const float* tb = tab_b + (p & 1) * CFG::COLS;
             const uint32_t* tc = tab_c + (p & 1) * CFG::COLS;
+            const uint32_t* td = tab_d + (p & 1) * CFG::COLS;
             if(o.all_valid == 1)
-                consume<CFG, false>(acc, ta, tb, tc, col0, lane, lane_z);
+                consume<CFG, false, false, STRADDLE>(acc, ta, tb, tc, td, beyond, col0, lane, lane_z);
             else if(o.all_valid == 0)
             {
                 if(o.fits)
-                    consume<CFG, true>(acc, ta, tb, tc, col0, lane, lane_z);
+                    consume<CFG, true, false, STRADDLE>(acc, ta, tb, tc, td, beyond, col0, lane, lane_z);
                 else
-                    consume<CFG, true, true>(acc, ta, tb, tc, col0, lane, lane_z);
+                    consume<CFG, true, true, STRADDLE>(acc, ta, tb, tc, td, beyond, col0, lane, lane_z);
             }
 
             __syncthreads(); // stage and table[p&1] are free again; table[(p+1)&1] is complete
@@ -742,7 +781,9 @@ namespace pb
         // farthest voxel column from the rotation axis, and farthest slice from the mid-plane, in millimetres
         // (tiles are anchored at global multiples of the tile size and may stick out of the region)
         auto extent = [](uint32_t off, uint32_t n, uint32_t full, float size, int tile) {
-            const uint32_t first = off / tile * tile, last = (off + n - 1u) / tile * tile + tile - 1u;
+            // (covers both anchorings: global multiples of the tile size, and tiles starting at `off`)
+            const uint32_t first = off / tile * tile;
+            const uint32_t last = std::max((off + n - 1u) / tile * tile + tile - 1u, off + (n + tile - 1u) / tile * tile - 1u);
             const double lo = (static_cast<double>(first) + 0.5 - full / 2.0) * size;
             const double hi = (static_cast<double>(last) + 0.5 - full / 2.0) * size;
             return std::max(std::fabs(lo), std::fabs(hi));
@@ -774,12 +815,15 @@ namespace pb
         // the tensor map spans the slots this launch can touch: [0, first + count)
         const uint32_t slots = first + static_cast<uint32_t>(a.count);
         PB_TRY(make_tensor_map(ctx, d_stack, g.p_dim_x, g.pitch, slots, slot_floats, CFG::BV, CFG::BH, CFG::SPLIT));
-        auto kern = bp_tma_kernel<CFG>;
+        // x, y: tiles anchored at global multiples of the tile size (first tile holds off, last holds off + dim - 1);
+        // z: the same when the slab starts on a tile boundary, else tiles anchored at the slab's first slice (the
+        // STRADDLE instantiation: no partly empty tile layers, row anchors stay global)
+        const bool straddle = (g.off_z % static_cast<uint32_t>(CFG::TZ)) != 0u;
+        auto kern = straddle ? bp_tma_kernel<CFG, true> : bp_tma_kernel<CFG, false>;
         PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(CFG::SMEM)));
-        // tiles anchored at global multiples of the tile size: first tile holds off, last holds off + dim - 1
         auto tiles = [](uint32_t off, uint32_t dim, uint32_t t) { return (off + dim - 1u) / t - off / t + 1u; };
         const dim3 grid(tiles(g.off_x, g.v_dim_x, CFG::TX), tiles(g.off_y, g.v_dim_y, CFG::TY),
-                        tiles(g.off_z, g.v_dim_z, CFG::TZ));
+                        straddle ? (g.v_dim_z + CFG::TZ - 1u) / CFG::TZ : tiles(g.off_z, g.v_dim_z, CFG::TZ));
         if(grid.y > 65535u || grid.z > 65535u)
         {
             set_error("slab too large for the backprojection grid");
@@ -836,12 +880,15 @@ namespace pb
             *handled = true;                                                                       \
             return PARIS_B200_OK;                                                                  \
         }
-        // Tiles are anchored at multiples of the tile size in GLOBAL voxel indices, so a region whose offsets are not
-        // multiples of the tile size pays for partly empty tiles; the tall tile (fastest per voxel) is used only when
-        // the voxels its tiles cover, times its relative cost per voxel, are fewer than the half tile's.
+        // Tiles are anchored at multiples of the tile size in GLOBAL voxel indices in x and y, so a region whose offsets
+        // are not multiples of the tile size pays for partly empty tiles; the tall tile (fastest per voxel) is used only
+        // when the voxels its tiles cover, times its relative cost per voxel, are fewer than the half tile's.
         auto covered = [&](uint32_t tx, uint32_t ty, uint32_t tz) {
             auto span = [](uint32_t off, uint32_t dim, uint32_t t) { return ((off + dim - 1u) / t - off / t + 1u) * static_cast<double>(t); };
-            return span(g.off_x, g.v_dim_x, tx) * span(g.off_y, g.v_dim_y, ty) * span(g.off_z, g.v_dim_z, tz);
+            // (z: a slab that does not start on a tile boundary gets tiles anchored at its first slice, at ~10 % more
+            // instructions per voxel)
+            const double z = (g.off_z % tz) ? 1.1 * ((g.v_dim_z + tz - 1u) / tz) * static_cast<double>(tz) : span(g.off_z, g.v_dim_z, tz);
+            return span(g.off_x, g.v_dim_x, tx) * span(g.off_y, g.v_dim_y, ty) * z;
         };
         const bool tall = ctx->bp_tile == 0 && covered(8, 8, 128) <= 1.035 * covered(16, 8, 64);
         if(aligned)
