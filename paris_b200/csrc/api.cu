@@ -979,7 +979,16 @@ extern "C" int paris_b200_backproject(paris_b200_ctx* ctx, const float* d_proj, 
         for(int i = 0; i < ctx->flushes_for_target && threshold < ctx->bp_batch; ++i)
             threshold += threshold / 2;
         threshold = std::min(threshold, ctx->bp_batch);
-        if(ctx->pending >= threshold)
+        bool launch = ctx->pending >= threshold;
+        if(!launch && ctx->pending >= std::min(16, ctx->bp_batch))
+        {
+            // upload-bound scans: if the GPU has nothing left to do, give it what has arrived (batches then stay
+            // small, and so does the work left when the last projection comes in); while the GPU is busy the batch
+            // keeps growing
+            launch = cudaStreamQuery(ctx->compute) == cudaSuccess;
+            (void)cudaGetLastError();   // cudaErrorNotReady is not an error
+        }
+        if(launch)
             PB_TRY(paris_b200_flush(ctx));
     }
     // (the layout is a function of the target geometry, so it is constant within a batch)

@@ -47,8 +47,16 @@ namespace pb
         static constexpr int WARPS = COLS / CPW;          // one warp per group of CPW columns
         static constexpr int THREADS = 32 * WARPS;
         static constexpr int STAGE_BYTES = BH * BV * 4;
-        static constexpr int TAB_BYTES = COLS * (16 + 4 + 4 + 4);  // float4 + 3 words per column
-        static constexpr size_t SMEM = size_t(STAGES) * STAGE_BYTES + 2 * TAB_BYTES + kMaxBatch * 16 + STAGES * 8 + 128;
+        static constexpr int TAB_BYTES = COLS * (16 + 4 + 4);  // float4 + 2 words per column (+ 1 word with STRADDLE)
+        // shared memory of an instantiation: stages, two table sets, box origins, barriers
+        static constexpr size_t smem(bool straddle)
+        {
+            return size_t(STAGES) * STAGE_BYTES + 2 * TAB_BYTES + (straddle ? 2 * COLS * 4 : 0) + kMaxBatch * 8
+                 + STAGES * 8 + 128;
+        }
+        static constexpr size_t SMEM = smem(true);   // (scratch-size checks use the larger one)
+        // 256-thread tiles rely on TWO resident CTAs per SM (228 KB of shared memory, 1 KB reserved per CTA)
+        static_assert(THREADS > 256 || 2 * (smem(true) + 1024) <= 233472, "two CTAs of this tile must fit one SM");
         // fixed point: rows are carried with a bias of BV so that they stay non-negative on boundary tiles
         static constexpr int FRAC = 23;
         static constexpr int ROW_SHIFT = SPLIT ? FRAC - 1 : FRAC;   // the split layout's word counts row pairs
@@ -62,13 +70,15 @@ namespace pb
         static_assert(!SPLIT || (BV % 8 == 0 && BIAS % 2 == 0), "parity planes: even bias, 16-byte plane rows");
     };
 
-    struct box_origin
+    struct box_origin   // 8 bytes per projection of the batch
     {
-        int h0, v0;      // detector coordinates of the box's first element
-        int all_valid;   // 1: every bilinear cell the tile touches lies inside the detector and the box;
-                         // 2: the tile's shadow misses the detector altogether (nothing to add); 0: mixed
-        int fits;        // the box covers the tile's footprint (guaranteed by the host-side check; else rows are clamped)
+        short h0, v0;             // detector coordinates of the box's first element
+        unsigned char all_valid;  // 1: every bilinear cell the tile touches lies inside the detector and the box;
+                                  // 2: the tile's shadow misses the detector altogether (nothing to add); 0: mixed
+        unsigned char fits;       // the box covers the tile's footprint (guaranteed by the host-side check; else rows are clamped)
+        unsigned short pad;
     };
+    static_assert(sizeof(box_origin) == 8, "box origins are budgeted at 8 bytes per projection");
 
     // ---- small PTX wrappers -----------------------------------------------------------------------------
     __device__ __forceinline__ uint32_t smem_u32(const void* p) { return static_cast<uint32_t>(__cvta_generic_to_shared(p)); }
@@ -405,9 +415,9 @@ namespace pb
         float4* tab_a = reinterpret_cast<float4*>(smem + size_t(CFG::STAGES) * CFG::STAGE_BYTES);
         float* tab_b = reinterpret_cast<float*>(tab_a + 2 * CFG::COLS);
         uint32_t* tab_c = reinterpret_cast<uint32_t*>(tab_b + 2 * CFG::COLS);
-        uint32_t* tab_d = tab_c + 2 * CFG::COLS;
-        box_origin* origin = reinterpret_cast<box_origin*>(tab_d + 2 * CFG::COLS);
-        uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(origin) + kMaxBatch * 16);
+        uint32_t* tab_d = tab_c + 2 * CFG::COLS;   // (present only with STRADDLE)
+        box_origin* origin = reinterpret_cast<box_origin*>(tab_d + (STRADDLE ? 2 * CFG::COLS : 0));
+        uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(origin) + kMaxBatch * 8);
 
         const int tid = threadIdx.x;
         const uint32_t lane = tid & 31;
@@ -463,11 +473,11 @@ namespace pb
             const int hlo = static_cast<int>(hlo_f), hhi = static_cast<int>(hhi_f);
             const int vlo = static_cast<int>(vlo_f), vhi = static_cast<int>(vhi_f);
             box_origin o;
-            o.h0 = hlo - 1;
+            o.h0 = static_cast<short>(hlo - 1);
             // the TMA unit wants the innermost start coordinate on a 16-byte boundary (measured on B200:
             // anything else raises an illegal-instruction fault), so round down to a multiple of 4 floats
             // (a multiple of 8 rows = 4 row pairs for the split layout)
-            o.v0 = CFG::SPLIT ? ((vlo - 1) >> 3) << 3 : ((vlo - 1) >> 2) << 2;
+            o.v0 = static_cast<short>(CFG::SPLIT ? ((vlo - 1) >> 3) << 3 : ((vlo - 1) >> 2) << 2);
             // cells used: columns hlo-1 .. hhi+2, rows vlo-1 .. vhi+2 (one cell of slack for float rounding)
             const bool fits = (hhi + 2 - o.h0) < CFG::BH && (vhi + 2 - o.v0) < CFG::BV;
             const bool inside = hlo - 1 >= 0 && hhi + 2 <= static_cast<int>(g.p_dim_x) - 1
@@ -820,7 +830,8 @@ namespace pb
         // STRADDLE instantiation: no partly empty tile layers, row anchors stay global)
         const bool straddle = (g.off_z % static_cast<uint32_t>(CFG::TZ)) != 0u;
         auto kern = straddle ? bp_tma_kernel<CFG, true> : bp_tma_kernel<CFG, false>;
-        PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(CFG::SMEM)));
+        const size_t smem = CFG::smem(straddle);
+        PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         auto tiles = [](uint32_t off, uint32_t dim, uint32_t t) { return (off + dim - 1u) / t - off / t + 1u; };
         const dim3 grid(tiles(g.off_x, g.v_dim_x, CFG::TX), tiles(g.off_y, g.v_dim_y, CFG::TY),
                         straddle ? (g.v_dim_z + CFG::TZ - 1u) / CFG::TZ : tiles(g.off_z, g.v_dim_z, CFG::TZ));
@@ -829,7 +840,7 @@ namespace pb
             set_error("slab too large for the backprojection grid");
             return PARIS_B200_EINVAL;
         }
-        kern<<<grid, CFG::THREADS, CFG::SMEM, ctx->compute>>>(ctx->tma.map, d_vol, g, a, first);
+        kern<<<grid, CFG::THREADS, smem, ctx->compute>>>(ctx->tma.map, d_vol, g, a, first);
         PB_CUDA(cudaGetLastError());
         ++ctx->launches;
         return PARIS_B200_OK;
@@ -871,7 +882,9 @@ namespace pb
                       const bp_geometry& g, const bp_angles& a, float* d_vol, bool required, bool* handled)
     {
         *handled = false;
-        const bool aligned = (reinterpret_cast<uintptr_t>(d_stack) % 16u) == 0u && (g.pitch % 8u) == 0u;
+        // (box origins are kept as 16-bit detector coordinates)
+        const bool aligned = (reinterpret_cast<uintptr_t>(d_stack) % 16u) == 0u && (g.pitch % 8u) == 0u
+                          && g.p_dim_x <= 32000u && g.p_dim_y <= 32000u;
         const bool half = ctx->bp_tile != 1;   // 0 = automatic (tall, then half tiles when they fit), 1 = full tiles only, 2 = half or full
 #define PB_TRY_CFG(CFG)                                                                            \
         if(fits_cfg<CFG>(g))                                                                       \

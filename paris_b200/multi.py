@@ -86,6 +86,7 @@ class MultiGpuReconstructor:
         # the C++ layer's per-thread context, so the e2e loop and the stack-level calls share streams
         dropin.set_device(device)
         self.ctx = capi.Context(device, handle=dropin.context_handle())
+        batch = int(os.environ.get("PARIS_B200_BATCH", batch))   # (tuning experiments)
         self.batch = batch
         self.ctx.set_option("bp_batch", batch)
         self.px = det.n_row * det.n_col
