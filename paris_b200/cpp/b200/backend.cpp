@@ -46,12 +46,14 @@ namespace paris
 
             // Pinned host buffers are pooled: the reference drops a host projection at the end of every loop
             // iteration (src/main.cpp:100-105) while its upload may still be in flight, and cudaFreeHost would
-            // synchronise the device.  A released buffer is reused only after the copy stream has drained.
+            // synchronise the device.  A released buffer is reused only after the copy stream has drained -- the copy
+            // stream of the thread that released it, so the free lists are PER THREAD (= per device, src/main.cpp:
+            // 157-169 runs one host thread per device): a buffer released by one device thread must not be handed to
+            // another whose context knows nothing about the upload still reading it.  Ownership is process-wide.
             struct host_pool
             {
                 std::mutex m;
                 std::unordered_map<float*, std::size_t> owned;          // every pooled pointer -> bytes
-                std::unordered_multimap<std::size_t, float*> free_list; // bytes -> released pointers
                 ~host_pool()
                 {
                     for(auto& kv : owned)
@@ -65,26 +67,31 @@ namespace paris
                 return p;
             }
 
+            auto free_list() -> std::unordered_multimap<std::size_t, float*>&   // bytes -> pointers this thread released
+            {
+                thread_local std::unordered_multimap<std::size_t, float*> list;
+                return list;
+            }
+
             auto host_acquire(std::size_t bytes, bool zero) -> float*
             {
-                auto& p = pool();
+                auto& mine = free_list();
+                auto it = mine.find(bytes);
+                if(it != mine.end())
                 {
-                    std::lock_guard<std::mutex> lock{p.m};
-                    auto it = p.free_list.find(bytes);
-                    if(it != p.free_list.end())
-                    {
-                        auto ptr = it->second;
-                        p.free_list.erase(it);
-                        // the previous user's upload must have left the buffer before it is overwritten
-                        if(state().ctx != nullptr)
-                            paris_b200_h2d_wait(state().ctx);
-                        if(zero)
-                            std::fill_n(ptr, bytes / sizeof(float), 0.f);
-                        return ptr;
-                    }
+                    auto ptr = it->second;
+                    mine.erase(it);
+                    // the previous upload (issued by this thread's context) must have left the buffer before it is
+                    // overwritten
+                    if(state().ctx != nullptr)
+                        paris_b200_h2d_wait(state().ctx);
+                    if(zero)
+                        std::fill_n(ptr, bytes / sizeof(float), 0.f);
+                    return ptr;
                 }
                 void* raw = nullptr;
                 must(paris_b200_host_alloc(bytes, zero ? 1 : 0, &raw), "paris_b200_host_alloc");
+                auto& p = pool();
                 std::lock_guard<std::mutex> lock{p.m};
                 p.owned.emplace(static_cast<float*>(raw), bytes);
                 return static_cast<float*>(raw);
@@ -110,10 +117,15 @@ namespace paris
             if(p == nullptr)
                 return;
             auto& hp = pool();
-            std::lock_guard<std::mutex> lock{hp.m};
-            auto it = hp.owned.find(p);
-            if(it != hp.owned.end())
-                hp.free_list.emplace(it->second, p); // borrowed pointers are simply forgotten
+            auto bytes = std::size_t{0};
+            {
+                std::lock_guard<std::mutex> lock{hp.m};
+                auto it = hp.owned.find(p);
+                if(it == hp.owned.end())
+                    return; // borrowed pointers are simply forgotten
+                bytes = it->second;
+            }
+            free_list().emplace(bytes, p);
         }
 
         auto device_deleter::operator()(float* p) const noexcept -> void
