@@ -49,7 +49,8 @@ namespace
         while(queue.pop(t))
         {
             const auto last = (t.num - t.id) <= 1u;
-            auto source = paris::source{t.input_path, t.enable_angles, t.angle_path, t.quality};
+            const auto& scan = t.scan;
+            auto source = paris::source{scan.input_path, scan.enable_angles, scan.angle_path, scan.quality};
 
             auto v = paris::make_volume(t.subvol_geo, last);
             const auto offset = t.id * t.subvol_geo.dim_z;
@@ -63,9 +64,9 @@ namespace
                     break;
                 const auto use_angle = source.has_angle_for(p.idx);
                 auto d_p = paris::load(p);
-                paris::weight(d_p, t.det_geo);
-                paris::filter(d_p, t.det_geo);
-                paris::backproject(d_p, v, offset, t.det_geo, t.vol_geo, use_angle, t.enable_roi, t.roi);
+                paris::weight(d_p, scan.det_geo);
+                paris::filter(d_p, scan.det_geo);
+                paris::backproject(d_p, v, offset, scan.det_geo, t.vol_geo, use_angle, scan.enable_roi, scan.roi);
                 ++count;
             }
             paris::log::info() << "device " << device << ": task " << t.id + 1u << "/" << t.num << ", " << count
