@@ -71,6 +71,43 @@ def test_roi_and_slabs_are_bit_identical_crops(ctx):
     ctx.set_option("bp_kernel", 0)
 
 
+@pytest.mark.parametrize("v_offset,dz", [(0, 200), (5, 150), (70, 64)])
+def test_backproject_with_overlapped_download_equals_separate_calls(ctx, v_offset, dz):
+    """paris_b200_backproject_stack_d2h cuts the slab into z-chunks at the kernel's tile anchors and downloads each
+    chunk behind the next one's backprojection; the host volume must equal backproject_stack + vol_d2h bit for bit,
+    whatever the slab's offset (chunks then start off the anchors) and for slabs of several chunks or one."""
+    n, n_proj = 128, 70
+    _, det = both_det(n, 300, l_px=0.4, n_proj=n_proj)
+    vol = capi.calculate_volume_geometry(det)
+    assert vol.dim_z >= v_offset + dz
+    raw = ctx.dev_alloc(n_proj * n * 300 * 4)
+    ell = phantom.scaled_ellipsoids(phantom.SHEPP_LOGAN_3D, 0.9 * phantom.fov_radius(n, 0.4, 0, 500, 500))
+    ctx.phantom_project(ell, det, 0, n_proj, raw)
+    stack = ctx.stack_alloc(n, 300, n_proj)
+    filt = ctx.filter_create(capi.filter_size(n), 0.4)
+    layout = capi.choose_stack_layout(det, vol)
+    ctx.filter_to_stack_batch(raw, n * 300, n_proj, det, filt, stack, 0, layout)
+    sc = np.array([angle_sin_cos(i, det) for i in range(n_proj)], dtype=np.float32)
+    dims = (vol.dim_x, vol.dim_y, dz)
+    ctx.set_option("bp_batch", 32)          # several launches per chunk as well
+    v = ctx.volume_alloc(*dims)
+    ctx.backproject_stack(stack, 0, n_proj, sc[:, 0], sc[:, 1], v, dims, v_offset, det, vol, layout=layout)
+    want = np.empty((dz, vol.dim_y, vol.dim_x), np.float32)
+    ctx.vol_d2h(v, want, want.size)
+    ctx.volume_clear(v, *dims)
+    got = capi.PinnedArray(want.shape)
+    ctx.backproject_stack_d2h(stack, 0, n_proj, sc[:, 0], sc[:, 1], v, dims, v_offset, det, vol, got.ptr, layout=layout)
+    same = np.array_equal(got.array, want)
+    nonzero = float(np.abs(want).max())
+    got.free()
+    ctx.set_option("bp_batch", 256)
+    ctx.volume_free(v)
+    ctx.filter_destroy(filt)
+    ctx.stack_free(stack)
+    ctx.dev_free(raw)
+    assert nonzero > 0 and same
+
+
 @pytest.mark.parametrize("n_row,n_col,n_proj", [(100, 37, 9), (33, 65, 3), (250, 20, 65), (64, 64, 1)])
 def test_ragged_shapes_and_batch_boundaries(ctx, port, n_row, n_col, n_proj):
     """odd detector sizes (pitch padding, partial row groups), volumes that are no multiple of the tile,
