@@ -93,7 +93,27 @@ class ClockSampler:
         self._stop = threading.Event()
         self._thread = None
 
+    def _sample(self):
+        import pynvml
+        h = self._handle
+        self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
+        self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1e3)
+        mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
+        for name, bit in self.REASONS.items():
+            if mask & bit:
+                self.reasons.add(name)
+
     def _run(self):
+        try:
+            while not self._stop.is_set():
+                self._sample()
+                self._stop.wait(self.interval)
+        except Exception as e:  # report that instead of clocks
+            self.error = repr(e)
+
+    def start(self):
+        """NVML is initialised HERE, synchronously (importing and initialising it takes longer than a short timed
+        region); the thread only samples."""
         try:
             import pynvml
             pynvml.nvmlInit()
@@ -104,21 +124,11 @@ class ClockSampler:
                     index = int(visible.split(",")[self.device])
                 except (ValueError, IndexError):
                     pass
-            h = pynvml.nvmlDeviceGetHandleByIndex(index)
-            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(h, pynvml.NVML_CLOCK_SM))
-            while not self._stop.is_set():
-                self.samples.append(float(pynvml.nvmlDeviceGetClockInfo(h, pynvml.NVML_CLOCK_SM)))
-                self.power.append(pynvml.nvmlDeviceGetPowerUsage(h) / 1e3)
-                mask = pynvml.nvmlDeviceGetCurrentClocksThrottleReasons(h)
-                for name, bit in self.REASONS.items():
-                    if mask & bit:
-                        self.reasons.add(name)
-                self._stop.wait(self.interval)
-            pynvml.nvmlShutdown()
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(index)
+            self.max_mhz = float(pynvml.nvmlDeviceGetMaxClockInfo(self._handle, pynvml.NVML_CLOCK_SM))
         except Exception as e:  # no NVML: report that instead of clocks
             self.error = repr(e)
-
-    def start(self):
+            return
         self._thread = threading.Thread(target=self._run, daemon=True)
         self._thread.start()
 
