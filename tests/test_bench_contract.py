@@ -1,0 +1,53 @@
+"""The JSON line bench.py prints must keep the driver's contract.  Checked on the committed lines under profiles/
+(produced by the real runs on B200 boxes), so a change to bench.py that drops or renames a key is caught on CPU."""
+import glob
+import json
+import os
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+LINES = sorted(glob.glob(os.path.join(ROOT, "profiles", "r*_bench_*.json")) + glob.glob(os.path.join(ROOT, "profiles", "r*_scale_*.json")))
+
+
+def last_line(path):
+    return [json.loads(l) for l in open(path) if l.startswith("{")][-1]
+
+
+def test_profiles_hold_bench_lines():
+    assert LINES, "profiles/ holds no bench line"
+
+
+@pytest.mark.parametrize("path", LINES, ids=[os.path.basename(p) for p in LINES])
+def test_bench_line_keeps_the_contract(path):
+    d = last_line(path)
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "roofline", "e2e", "gpu_launches", "clocks"):
+        assert key in d, key
+    assert d["unit"] == "GUPS" and d["higher_is_better"] is True and d["dtype"] == "f32" and d["data"] == "synthetic"
+    assert d["vs_baseline"] is None                      # BASELINE.md holds no published number
+    assert "workload" in d["config"] and "model" not in d["config"]
+    r = d["roofline"]
+    for key in ("bound", "achieved", "peak", "unit", "frac", "traffic"):
+        assert key in r, key
+    assert abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-9
+    e = d["e2e"]
+    for key in ("value", "unit", "h2d_bytes_per_step", "d2h_bytes_per_step"):
+        assert key in e, key
+    assert e["h2d_bytes_per_step"] > 0 and e["d2h_bytes_per_step"] > 0 and e["value"] < d["value"] * 1.001
+    assert d["gpu_launches"] > 0
+    assert d["steps"] >= 1 and d["warmup"] >= 3
+    # whole-job throughput = updates / time
+    assert d["value"] > 0 and d["ms_per_step"] > 0
+    if d["n_gpus"] == 1 and "cpu_baseline" in d:
+        c = d["cpu_baseline"]
+        for key in ("value", "unit", "cores", "kind", "sample"):
+            assert key in c, key
+        assert c["kind"] in ("reference", "port") and c["cores"] >= 1
+
+
+def test_final_single_gpu_line_has_clocks_and_cpu_baseline():
+    d = last_line(os.path.join(ROOT, "profiles", "r1_bench_c2_1gpu.json"))
+    assert d["clocks"]["sm_mhz"] and d["clocks"]["sm_max_mhz"] and isinstance(d["clocks"]["reasons"], list)
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] > 0
+    assert "512^3" in d["config"]["workload"]
