@@ -42,7 +42,9 @@ namespace paris
                 return s;
             }
 
-            int g_slab_count = 0;
+            // per calling thread, like every other piece of backend state: concurrent per-device callers must not
+            // plan their slabs with another call's count
+            thread_local int g_slab_count = 0;
 
             // Pinned host buffers are pooled: the reference drops a host projection at the end of every loop
             // iteration (src/main.cpp:100-105) while its upload may still be in flight, and cudaFreeHost would

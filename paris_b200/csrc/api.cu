@@ -28,6 +28,7 @@ namespace pb
 using namespace pb;
 
 static int flush_if_held(paris_b200_ctx* ctx, const void* d_ptr);
+static int run_pending_filter(paris_b200_ctx* ctx);
 
 extern "C" const char* paris_b200_last_error(void) { return pb::g_error; }
 extern "C" const char* paris_b200_version(void) { return "paris_b200 0.1 (sm_100a)"; }
@@ -61,10 +62,24 @@ extern "C" int paris_b200_ctx_create(int device, paris_b200_ctx** out)
     auto* ctx = new paris_b200_ctx{};
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
-    PB_CUDA(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
-    PB_CUDA(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
-    PB_CUDA(cudaEventCreateWithFlags(&ctx->h2d_done, cudaEventDisableTiming));
-    PB_CUDA(cudaEventCreateWithFlags(&ctx->scratch_ev, cudaEventDisableTiming));
+    // (a context whose streams or events cannot all be created is taken apart again, not leaked)
+    const auto build = [&]() -> int {
+        PB_CUDA(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
+        PB_CUDA(cudaStreamCreateWithFlags(&ctx->copy, cudaStreamNonBlocking));
+        PB_CUDA(cudaEventCreateWithFlags(&ctx->h2d_done, cudaEventDisableTiming));
+        PB_CUDA(cudaEventCreateWithFlags(&ctx->scratch_ev, cudaEventDisableTiming));
+        return PARIS_B200_OK;
+    };
+    const int rc = build();
+    if(rc != PARIS_B200_OK)
+    {
+        if(ctx->scratch_ev) cudaEventDestroy(ctx->scratch_ev);
+        if(ctx->h2d_done) cudaEventDestroy(ctx->h2d_done);
+        if(ctx->copy) cudaStreamDestroy(ctx->copy);
+        if(ctx->compute) cudaStreamDestroy(ctx->compute);
+        delete ctx;
+        return rc;
+    }
     *out = ctx;
     return PARIS_B200_OK;
 }
@@ -210,6 +225,13 @@ extern "C" int paris_b200_ctx_set_option(paris_b200_ctx* ctx, const char* name, 
         ctx->bp_kernel = static_cast<int>(value);
         return PARIS_B200_OK;
     }
+    if(std::strcmp(name, "bp_swizzle") == 0)
+    {
+        PB_CHECK_ARG(value >= 0 && value <= 64);
+        PB_TRY(paris_b200_flush(ctx));
+        ctx->bp_swizzle = static_cast<int>(value);
+        return PARIS_B200_OK;
+    }
     if(std::strcmp(name, "bp_tile") == 0)
     {
         PB_CHECK_ARG(value >= 0 && value <= 2);
@@ -288,13 +310,28 @@ extern "C" int paris_b200_make_subvolume_information(paris_b200_ctx* ctx, const 
         // 64-bit byte counts (the reference's 32-bit product overflows at >= 4 GiB)
         const size_t vol_bytes = static_cast<size_t>(vol->dim_x) * vol->dim_y * vol->dim_z * sizeof(float);
         const size_t proj_bytes = static_cast<size_t>(det->n_row) * det->n_col * sizeof(float);
-        size_t need = vol_bytes + 10u * proj_bytes;
+        // Besides the slab and the reference's ten projections, this backend holds the filtered stack of one batch
+        // and a pool of raw projection buffers (bp_batch + 66 of them, dev_alloc); neither shrinks with the slab.
+        // What the context already holds of them (and a spare slab, which volume_alloc releases) is not counted twice.
+        const size_t slot_bytes = static_cast<size_t>(stack_pitch_for(det->n_col)) * det->n_row * sizeof(float);
+        const size_t pool_stride = (proj_bytes + 255u) & ~static_cast<size_t>(255u);
+        size_t fixed = 10u * proj_bytes;
+        if(ctx->stack == nullptr)
+            fixed += static_cast<size_t>(ctx->bp_batch) * slot_bytes;
+        if(ctx->pool.empty())
+            fixed += (static_cast<size_t>(ctx->bp_batch) + 66u) * pool_stride;
         size_t mem_free = 0, mem_total = 0;
         PB_CUDA(cudaMemGetInfo(&mem_free, &mem_total));
+        mem_free += ctx->spare_vol_bytes;
+        size_t need = vol_bytes;
         slabs = 1;
-        while(need >= mem_free && slabs < vol->dim_z)
+        // (the last slab carries the remainder: dim_z / slabs + dim_z % slabs slices)
+        const size_t slice_bytes = static_cast<size_t>(vol->dim_x) * vol->dim_y * sizeof(float);
+        while(slabs < vol->dim_z)
         {
-            need /= 2;
+            need = (vol->dim_z / slabs + vol->dim_z % slabs) * slice_bytes;
+            if(need + fixed < mem_free)
+                break;
             slabs *= 2;
         }
     }
@@ -334,6 +371,13 @@ static pb::raw_buffer* find_buffer(paris_b200_ctx* ctx, const void* p)
     return nullptr;
 }
 
+// a launch queued on the compute stream reads or writes this (pooled) buffer: a later upload into it must wait
+static void touch(paris_b200_ctx* ctx, const void* p)
+{
+    if(auto* b = find_buffer(ctx, p))
+        b->touched = true;
+}
+
 extern "C" int paris_b200_dev_alloc(paris_b200_ctx* ctx, size_t bytes, void** d_ptr)
 {
     PB_CHECK_ARG(ctx != nullptr && d_ptr != nullptr && bytes > 0);
@@ -370,6 +414,7 @@ extern "C" int paris_b200_dev_alloc(paris_b200_ctx* ctx, size_t bytes, void** d_
         else
             ++ctx->stat_pool_busy;
         b.in_use = true;
+        b.touched = false;
         *d_ptr = b.ptr;
         ctx->free_fifo.erase(it);
         return PARIS_B200_OK;
@@ -452,6 +497,16 @@ extern "C" int paris_b200_volume_alloc(paris_b200_ctx* ctx, uint32_t dim_x, uint
     }
     else
     {
+        // A spare of another size (the last slab of a run carries the remainder, src/make_volume.cpp:32-34) is let go
+        // FIRST: slabs are sized to fill the device, two of them do not fit (the reference never holds two either).
+        if(ctx->spare_vol != nullptr)
+        {
+            PB_CUDA(cudaStreamSynchronize(ctx->compute));
+            PB_CUDA(cudaFree(ctx->spare_vol));
+            ctx->vol_bytes.erase(ctx->spare_vol);
+            ctx->spare_vol = nullptr;
+            ctx->spare_vol_bytes = 0;
+        }
         PB_CUDA(cudaMalloc(reinterpret_cast<void**>(d_vol), bytes));
         ctx->vol_bytes[*d_vol] = bytes;
     }
@@ -464,8 +519,15 @@ extern "C" int paris_b200_volume_clear(paris_b200_ctx* ctx, float* d_vol, uint32
 {
     PB_CHECK_ARG(ctx != nullptr && d_vol != nullptr);
     PB_TRY(bind(ctx));
-    if(ctx->pending > 0 && ctx->target.d_vol == d_vol)
-        PB_TRY(paris_b200_flush(ctx));
+    if(ctx->target.d_vol == d_vol)
+    {
+        // the pending batch would be zeroed right after being added: drop it (the deferred filter launch still runs,
+        // which is how the raw buffers it holds are let go) and start the short-first-batch ramp again
+        if(ctx->pending > 0)
+            PB_TRY(run_pending_filter(ctx));
+        ctx->pending = 0;
+        ctx->flushes_for_target = 0;
+    }
     PB_CUDA(cudaMemsetAsync(d_vol, 0, static_cast<size_t>(dim_x) * dim_y * dim_z * sizeof(float), ctx->compute));
     return PARIS_B200_OK;
 }
@@ -516,6 +578,17 @@ extern "C" int paris_b200_proj_h2d(paris_b200_ctx* ctx, const float* h_src, floa
         // pooled buffer recycled while its previous reader may still run
         PB_CUDA(cudaStreamWaitEvent(ctx->copy, b->freed, 0));
     }
+    if(b != nullptr && b->touched)
+    {
+        // a live pooled buffer that was uploaded to before, or that a kernel queued on the compute stream reads or
+        // writes (weight, apply_filter, filter_to_stack, the deferred launch flush_if_held just enqueued): the new
+        // upload must not overtake that work.  (The first upload into a freshly allocated buffer -- the
+        // reference's loop, src/main.cpp:100-101 -- does not take this path and keeps running ahead of compute.)
+        PB_CUDA(cudaEventRecord(ctx->scratch_ev, ctx->compute));
+        PB_CUDA(cudaStreamWaitEvent(ctx->copy, ctx->scratch_ev, 0));
+    }
+    if(b != nullptr)
+        b->touched = true;
     else if(b == nullptr)
     {
         // foreign destination: order after everything queued on the compute stream
@@ -786,6 +859,7 @@ extern "C" int paris_b200_weight(paris_b200_ctx* ctx, float* d_proj, uint32_t di
     PB_CHECK_ARG(ctx != nullptr && d_proj != nullptr && dim_x > 0 && dim_y > 0);
     PB_TRY(bind(ctx));
     PB_TRY(flush_if_held(ctx, d_proj));
+    touch(ctx, d_proj);
     return launch_weight(ctx, d_proj, dim_x, dim_y, h_min, v_min, d_sd, l_px_row, l_px_col);
 }
 
@@ -796,6 +870,7 @@ extern "C" int paris_b200_apply_filter(paris_b200_ctx* ctx, float* d_proj, uint3
     PB_CHECK_ARG(filter_size == filter->size && n_col == dim_y && dim_x <= filter_size);
     PB_TRY(bind(ctx));
     PB_TRY(flush_if_held(ctx, d_proj));
+    touch(ctx, d_proj);
     return launch_filter(ctx, d_proj, d_proj, dim_x, dim_y, filter, weight_params{}, false, 0);
 }
 
@@ -807,6 +882,7 @@ extern "C" int paris_b200_weight_filter(paris_b200_ctx* ctx, float* d_proj, uint
     PB_CHECK_ARG(filter_size == filter->size && dim_x <= filter_size);
     PB_TRY(bind(ctx));
     PB_TRY(flush_if_held(ctx, d_proj));
+    touch(ctx, d_proj);
     weight_params w{1, h_min, v_min, d_sd, l_px_row, l_px_col};
     return launch_filter(ctx, d_proj, d_proj, dim_x, dim_y, filter, w, false, 0);
 }
@@ -996,6 +1072,7 @@ extern "C" int paris_b200_backproject(paris_b200_ctx* ctx, const float* d_proj, 
     ctx->target = t;
 
     float* slot = ctx->stack + ctx->stack_slot_floats * static_cast<size_t>(ctx->pending);
+    touch(ctx, d_proj);
     if(fuse)
     {
         weight_params w = weighting_from_detector(det);
@@ -1098,6 +1175,7 @@ extern "C" int paris_b200_filter_to_stack(paris_b200_ctx* ctx, const float* d_ra
 {
     PB_CHECK_ARG(ctx != nullptr);
     PB_TRY(flush_if_held(ctx, d_raw));
+    touch(ctx, d_raw);
     return paris_b200_filter_to_stack_batch(ctx, d_raw, 0, 1u, det, filter, d_stack, slot, layout);
 }
 

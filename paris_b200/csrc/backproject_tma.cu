@@ -408,7 +408,8 @@ namespace pb
     template <class CFG, bool STRADDLE = false>
     __global__ void __launch_bounds__(CFG::THREADS, CFG::THREADS <= 256 ? 2 : 1)
     bp_tma_kernel(const __grid_constant__ CUtensorMap tmap, float* __restrict__ vol, const bp_geometry g,
-                  const bp_angles ang, const uint32_t first_slot)
+                  const bp_angles ang, const uint32_t first_slot, const uint32_t tiles_x, const uint32_t tiles_y,
+                  const uint32_t super)
     {
         extern __shared__ __align__(128) unsigned char smem[];
         unsigned char* stage_mem = smem;                                                   // STAGES x BH x BV floats
@@ -428,8 +429,19 @@ namespace pb
         // included), and every per-tile quantity below is derived from the full, unclipped tile.  A voxel
         // therefore sees the same arithmetic whichever ROI / z-slab decomposition it is reconstructed in:
         // slabs and ROI blocks are bit-identical to the corresponding crop of the one-piece reconstruction.
-        const uint32_t x0 = (g.off_x / CFG::TX + blockIdx.x) * CFG::TX;   // global index of the tile's first voxel
-        const uint32_t y0 = (g.off_y / CFG::TY + blockIdx.y) * CFG::TY;
+        // CTAs are numbered along grid.x in SUPER-BLOCKS of super x super tiles, so that the ~300 CTAs resident at any
+        // time cover a compact square of the slab instead of a few full-width rows of tiles.  Their boxes on a
+        // projection then cover a narrow detector strip and the boxes of a whole batch stay in L2 from one wave of
+        // tiles to the next (with row-major numbering the TMA loads of a 256-projection batch re-read ~57 GB from
+        // HBM per launch, profiles/r1_ncu_summary.md).  Which CTA computes a tile changes nothing about the tile.
+        const uint32_t sb = blockIdx.x / (super * super), within = blockIdx.x % (super * super);
+        const uint32_t sb_per_row = (tiles_x + super - 1u) / super;
+        const uint32_t bx = (sb % sb_per_row) * super + within % super;
+        const uint32_t by = (sb / sb_per_row) * super + within / super;
+        if(bx >= tiles_x || by >= tiles_y)
+            return;   // (padding of the last super-blocks; uniform for the CTA, before any barrier is initialised)
+        const uint32_t x0 = (g.off_x / CFG::TX + bx) * CFG::TX;   // global index of the tile's first voxel
+        const uint32_t y0 = (g.off_y / CFG::TY + by) * CFG::TY;
         // (z: the STRADDLE instantiation anchors its tiles at the slab's first slice instead -- no partly empty tile
         // layers for regions whose z offset is not a multiple of the tile height; the ROW anchors below stay global,
         // so the voxels are bit-identical either way)
@@ -576,11 +588,14 @@ namespace pb
             const column_terms ct = project_column(bx_k, by_l, ang.sn[p], ang.cs[p], g);
             const float x1 = floorf(ct.h);
             const bool valid_x = x1 >= 0.f && x1 + 1.f < static_cast<float>(g.p_dim_x);
-            // a dead entry reads row 0 of column 0 of the box with zero weights
+            // A dead entry (detector column off the detector, or rows the fixed-point word cannot reach) reads row 0 of
+            // column 0 of the box with zero weights AND an empty interval of valid slices: dead entries only occur in
+            // tiles that take the MIXED path, whose select then yields an exact 0 whatever was staged there (0 * NaN
+            // from a bad pixel must not reach voxels the reference leaves untouched, src/openmp/backprojection.cpp:65-71).
             float4 ea = make_float4(0.f, __uint_as_float(static_cast<uint32_t>(CFG::BIAS) << CFG::ROW_SHIFT),
                                     __uint_as_float(0u), 0.f);
             float eb = 0.f;
-            uint32_t ec = static_cast<uint32_t>(CFG::TZ) << 8;   // every slice valid
+            uint32_t ec = 0u;                                    // no slice valid
             uint32_t ed = static_cast<uint32_t>(CFG::BIAS) << CFG::ROW_SHIFT;   // (dead entry: same row as ea.y)
             int x1rel = 0;
             if(valid_x)
@@ -592,6 +607,7 @@ namespace pb
                 const double vend = vb + dv * static_cast<double>(CFG::TZ - 1);
                 const float fx = ct.h - x1;
                 const float w = 0.5f * ct.u * ct.u;
+                ec = static_cast<uint32_t>(CFG::TZ) << 8;        // every slice valid, unless found otherwise below
                 x1rel = min(max(static_cast<int>(x1) - o.h0, 0), CFG::BH - 2);
                 ea.w = w * (1.f - fx);
                 eb = w * fx;
@@ -622,6 +638,7 @@ namespace pb
                 {
                     ea.w = 0.f;         // unreachable rows: contributes nothing
                     eb = 0.f;
+                    ec = 0u;
                 }
             }
             // plain: address of (column x1, row -BIAS), the biased row index is added as is;
@@ -833,14 +850,19 @@ namespace pb
         const size_t smem = CFG::smem(straddle);
         PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
         auto tiles = [](uint32_t off, uint32_t dim, uint32_t t) { return (off + dim - 1u) / t - off / t + 1u; };
-        const dim3 grid(tiles(g.off_x, g.v_dim_x, CFG::TX), tiles(g.off_y, g.v_dim_y, CFG::TY),
+        const uint32_t tiles_x = tiles(g.off_x, g.v_dim_x, CFG::TX), tiles_y = tiles(g.off_y, g.v_dim_y, CFG::TY);
+        // (x, y) tiles are numbered in super x super blocks along grid.x (see the kernel); super = tiles_x gives the
+        // plain row-major order ("bp_swizzle" = 0)
+        const uint32_t super = ctx->bp_swizzle > 0 ? static_cast<uint32_t>(ctx->bp_swizzle) : std::max(tiles_x, tiles_y);
+        const uint32_t super_blocks = ((tiles_x + super - 1u) / super) * ((tiles_y + super - 1u) / super);
+        const dim3 grid(super_blocks * super * super, 1u,
                         straddle ? (g.v_dim_z + CFG::TZ - 1u) / CFG::TZ : tiles(g.off_z, g.v_dim_z, CFG::TZ));
         if(grid.y > 65535u || grid.z > 65535u)
         {
             set_error("slab too large for the backprojection grid");
             return PARIS_B200_EINVAL;
         }
-        kern<<<grid, CFG::THREADS, smem, ctx->compute>>>(ctx->tma.map, d_vol, g, a, first);
+        kern<<<grid, CFG::THREADS, smem, ctx->compute>>>(ctx->tma.map, d_vol, g, a, first, tiles_x, tiles_y, super);
         PB_CUDA(cudaGetLastError());
         ++ctx->launches;
         return PARIS_B200_OK;

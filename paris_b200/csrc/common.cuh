@@ -43,6 +43,7 @@ namespace pb
         bool held = false;          // read by a deferred filter launch that has not been enqueued yet
         bool free_pending = false;  // dev_free arrived while held
         bool in_slab = false;       // carved out of one of the context's pool slabs (not freed on its own)
+        bool touched = false;       // since dev_alloc: uploaded to, or named in a launch queued on the compute stream
     };
 
     // Geometry of one pending backprojection batch: everything but the angles must match for
@@ -102,6 +103,7 @@ struct paris_b200_ctx
     int bp_batch = 256;
     int bp_kernel = 0;
     int bp_tile = 0;     // 0: half tiles (two CTAs per SM) when the footprint fits, 1: full tiles only
+    int bp_swizzle = 16; // CTAs numbered in bp_swizzle x bp_swizzle super-blocks of (x, y) tiles; 0: row-major
 
     // pooled raw projection buffers (dev_alloc / dev_free)
     std::vector<pb::raw_buffer> pool;

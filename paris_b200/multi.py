@@ -25,6 +25,9 @@ class SlabPlan:
     """Equal z-slabs, remainder on the last one; contiguous, equal blocks of projections per rank."""
 
     def __init__(self, dim_z: int, world: int, rank: int):
+        if world > dim_z:
+            raise ValueError(f"{world} ranks cannot share {dim_z} slices: every rank needs at least one "
+                             "(run with at most as many ranks as the region has slices)")
         self.world, self.rank = world, rank
         self.dz = dim_z // world
         self.remainder = dim_z % world

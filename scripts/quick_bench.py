@@ -16,6 +16,7 @@ ap.add_argument("--batch", type=int, default=32)
 ap.add_argument("--reps", type=int, default=3)
 ap.add_argument("--layout", type=int, default=-1)
 ap.add_argument("--tile", type=int, default=0)
+ap.add_argument("--swizzle", type=int, default=16)
 ap.add_argument("--check", action="store_true", help="compare against the exact kernel")
 a = ap.parse_args()
 
@@ -32,6 +33,7 @@ ctx = capi.Context(0)
 ctx.set_option("bp_batch", a.batch)
 ctx.set_option("bp_kernel", a.kernel)
 ctx.set_option("bp_tile", a.tile)
+ctx.set_option("bp_swizzle", a.swizzle)
 n = a.proj
 raw = ctx.dev_alloc(n * a.det * a.det * 4)
 r = 0.9 * phantom.fov_radius(a.det, l_px, 0, 500, 500)
