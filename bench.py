@@ -1,7 +1,10 @@
 #!/usr/bin/env python
 """bench.py -- FDK hot path (weight -> ramp filter -> backprojection) on N B200s, one JSON line.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c1|c2|c3]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl b200|reference] [--config c1|c2|c3|c4|c5]
+
+Default workload: BASELINE config 3 (1024^3 from 1440 x 2048^2), the configuration north_star quotes its target on;
+it fits one GPU (24 GB raw + 24 GB filtered stack + 4 GB volume).
 
 A "step" is one full reconstruction of the workload from its raw projections:
   value   device-resident: raw stack already in HBM; per step the fused weight+filter kernel fills the
@@ -45,9 +48,21 @@ CONFIGS = {
 }
 
 
-def geometry(cfg: str):
-    """(detector, FULL volume geometry, projections, roi or None, region (x, y, z))."""
-    from paris_b200 import capi
+class _OracleApi:
+    """The reference arm's geometry types and arithmetic: oracle/ only (that arm must not load the product)."""
+
+    def __init__(self):
+        import oracle
+        self._impl = oracle.Reference() if oracle.have_ref() else oracle.Port()
+        self.DetectorGeometry, self.VolumeGeometry, self.Roi = oracle.DetectorGeometry, oracle.VolumeGeometry, oracle.Roi
+        self.calculate_volume_geometry, self.apply_roi = self._impl.calculate_volume_geometry, self._impl.apply_roi
+
+
+def geometry(cfg: str, capi=None):
+    """(detector, FULL volume geometry, projections, roi or None, region (x, y, z)).  `capi`: the module or object
+    that provides the geometry structs and calculate_volume_geometry / apply_roi (default: the product's C ABI)."""
+    if capi is None:
+        from paris_b200 import capi
     n, n_proj, k, _ = CONFIGS[cfg]
     l_px = 0.2 * 1024 / n  # 204.8 mm detector
     delta_s = 100.0 if cfg == "c4" else 0.0   # offset detector (pixels)
@@ -70,8 +85,9 @@ def geometry(cfg: str):
     return det, vol, n_proj, None, (k, k, k)
 
 
-def ellipsoids(det):
-    from paris_b200 import phantom
+def ellipsoids(det, phantom=None):
+    if phantom is None:
+        from paris_b200 import phantom
     r = 0.9 * phantom.fov_radius(det.n_row, det.l_px_row, det.delta_s, det.d_so, det.d_od)
     return phantom.scaled_ellipsoids(phantom.SHEPP_LOGAN_3D, r)
 
@@ -148,38 +164,55 @@ class ClockSampler:
         return out
 
 
-def ncu_traffic(kernel: str):
-    """dram__bytes_read.sum + dram__bytes_write.sum per launch of `kernel` from the committed ncu summary
-    (profiles/*_ncu_summary.json, one --set full capture on the same workload shape); None if absent."""
-    import glob
-    best = None
-    for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json"))):
-        try:
-            rec = json.load(open(path)).get(kernel)
-        except (OSError, ValueError):
-            continue
-        if not rec:
-            continue
-        total = 0.0
-        for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
-            unit = rec.get(key + "__unit", "byte").lower()
-            scale = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
-            total += float(rec.get(key, 0.0)) * scale
-        best = total
-    return best
-
-
-def ncu_metric(kernel: str, metric: str):
-    """One metric of `kernel` from the committed ncu summary (profiles/*_ncu_summary.json); None if absent."""
+def ncu_record(kernel: str):
+    """The newest committed ncu summary of `kernel` (profiles/*_ncu_summary.json: one --set full capture each),
+    or None.  A record may carry "capture": {"what": text, "algorithmic_bytes": B} describing the launch that was
+    captured, so that DRAM traffic is compared with the algorithmic bytes of THAT launch."""
     import glob
     for path in sorted(glob.glob(os.path.join(ROOT, "profiles", "*_ncu_summary.json")), reverse=True):
         try:
             rec = json.load(open(path)).get(kernel)
         except (OSError, ValueError):
             continue
-        if rec and metric in rec:
-            return rec[metric]
+        if rec:
+            rec = dict(rec)
+            rec["_file"] = os.path.basename(path)
+            return rec
     return None
+
+
+def ncu_traffic(rec):
+    """dram__bytes_read.sum + dram__bytes_write.sum of the captured launch, in bytes."""
+    if not rec:
+        return None
+    total = 0.0
+    for key in ("dram__bytes_read.sum", "dram__bytes_write.sum"):
+        unit = rec.get(key + "__unit", "byte").lower()
+        scale = {"byte": 1.0, "kbyte": 1e3, "mbyte": 1e6, "gbyte": 1e9}.get(unit, 1.0)
+        total += float(rec.get(key, 0.0)) * scale
+    return total
+
+
+def traffic_note(rec):
+    if not rec:
+        return "no ncu capture committed"
+    cap = rec.get("capture") or {}
+    note = f"DRAM bytes of the launch captured in profiles/{rec['_file']}"
+    if cap.get("what"):
+        note += f" ({cap['what']})"
+    if cap.get("algorithmic_bytes"):
+        note += f"; algorithmic HBM bytes of that launch = {float(cap['algorithmic_bytes']):.3e}"
+    return note
+
+
+def gather_peak():
+    """The measured ceiling of the backprojection's shared-memory gather (scripts/microbench/gather_peak.cu, committed
+    output profiles/r2_gather_peak.json): GUPS of the kernel's own LDS.32 pattern with nothing else in the way."""
+    try:
+        rec = json.load(open(os.path.join(ROOT, "profiles", "r2_gather_peak.json")))
+        return {"gups": rec["gather_gups"], "source": "profiles/r2_gather_peak.json"}
+    except (OSError, ValueError, KeyError):
+        return None
 
 
 def measured_peaks() -> dict:
@@ -193,20 +226,28 @@ def measured_peaks() -> dict:
 # CPU arm: the reference's OpenMP backend (or the plain-C port) on a bounded sample of the workload
 # ------------------------------------------------------------------------------------------------------------------
 
+def host_threads() -> int:
+    """Host cores this process may use (its affinity mask), NOT what OMP_NUM_THREADS says: torchrun exports
+    OMP_NUM_THREADS=1 to every rank, which made the round-1 reference arm single-threaded at N > 1."""
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
 def cpu_reconstruct_sample(cfg: str, budget_s: float, fetch=None):
-    """Times weight+filter+backproject of the reference on `p` projections of the workload (full region).
-    Returns (gups_total, gups_backprojection, cores, kind, description, seconds)."""
+    """Times weight+filter+backproject of the reference on `p` projections of the workload (full region), with
+    every host core.  Imports oracle/ only.  Returns (gups_total, gups_backprojection, cores, kind, description, seconds)."""
     import oracle
-    from paris_b200 import phantom
-    det, vol, n_proj, roi, region = geometry(cfg)
-    odet = oracle.DetectorGeometry(det.n_row, det.n_col, det.l_px_row, det.l_px_col, det.delta_s, det.delta_t,
-                                   det.d_so, det.d_od, det.delta_phi)
-    ovol = oracle.VolumeGeometry(vol.dim_x, vol.dim_y, vol.dim_z, vol.l_vx_x, vol.l_vx_y, vol.l_vx_z)
-    oroi = None if roi is None else oracle.Roi(roi.x1, roi.x2, roi.y1, roi.y2, roi.z1, roi.z2)
+    import oracle.phantom as ophantom
+    api = _OracleApi()
+    det, vol, n_proj, roi, region = geometry(cfg, api)
+    odet, ovol, oroi = det, vol, roi
     if oracle.have_ref():
         impl, kind = oracle.Reference(), "reference"
     else:
         impl, kind = oracle.Port(), "port"
+    impl.set_num_threads(host_threads())
     cores = impl.num_threads()
     shape = (region[2], region[1], region[0])
     voxels = region[0] * region[1] * region[2]
@@ -215,8 +256,8 @@ def cpu_reconstruct_sample(cfg: str, budget_s: float, fetch=None):
         if fetch is not None:
             return fetch(count, stride)
         ang = np.float32(det.delta_phi) * (np.arange(count, dtype=np.float32) * np.float32(stride))
-        return phantom.project(ellipsoids(det), det.n_row, det.n_col, det.l_px_row, det.l_px_col, det.delta_s,
-                               det.delta_t, det.d_so, det.d_od, ang.astype(np.float64))
+        return ophantom.project(ellipsoids(det, ophantom), det.n_row, det.n_col, det.l_px_row, det.l_px_col, det.delta_s,
+                                det.delta_t, det.d_so, det.d_od, ang.astype(np.float64))
 
     # calibrate on 2 projections (the first builds FFT plans / statics and is excluded by the callee)
     stride = max(1, n_proj // 16)
@@ -236,25 +277,29 @@ def cpu_reconstruct_sample(cfg: str, budget_s: float, fetch=None):
 
 
 def run_reference(args, rank: int):
+    """The reference's own CPU implementation (oracle/_ref = /root/reference compiled unmodified; the plain-C port
+    where that is absent) on every host core.  ONE bounded sample (a 2-projection calibration run before it is the
+    warm-up: FFT plans, function-local statics): per-update cost does not depend on the projection, so repeating
+    the sample --steps times would only burn lease time.  Loads nothing of the product."""
     if rank != 0:
         return
-    det, vol, n_proj, _roi, region = geometry(args.config)
-    vals, info = [], None
-    for i in range(args.warmup + args.steps):
-        g_total, g_bp, cores, kind, desc, wall = cpu_reconstruct_sample(args.config, budget_s=args.cpu_budget)
-        if i >= args.warmup:
-            vals.append(g_total)
-        info = (g_bp, cores, kind, desc, wall)
-    value = float(np.mean(vals))
+    assert "paris_b200" not in sys.modules, "the reference arm must not load the product"
+    api = _OracleApi()
+    det, vol, n_proj, _roi, region = geometry(args.config, api)
+    g_total, g_bp, cores, kind, desc, wall = cpu_reconstruct_sample(args.config, budget_s=args.cpu_budget)
+    assert "paris_b200" not in sys.modules
+    value = float(g_total)
     updates = region[0] * region[1] * region[2] * n_proj
     line = {
         "impl": "reference", "metric": "fdk_reconstruction_gups", "value": value, "unit": "GUPS",
         "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup,
         "ms_per_step": updates / value / 1e6, "higher_is_better": True, "scaling": "strong", "vs_baseline": None,
         "dtype": "f32", "data": "synthetic",
-        "config": {"workload": CONFIGS[args.config][3], "note": "ms_per_step extrapolated from the sample"},
-        "cpu_baseline": {"value": value, "unit": "GUPS", "cores": info[1], "kind": info[2], "sample": info[3],
-                         "backprojection_only_gups": info[0]},
+        "config": {"workload": CONFIGS[args.config][3],
+                   "note": "one bounded sample (after a 2-projection warm-up run) stands for every step; ms_per_step "
+                           "extrapolated from it"},
+        "cpu_baseline": {"value": value, "unit": "GUPS", "cores": cores, "kind": kind, "sample": desc,
+                         "backprojection_only_gups": g_bp, "sample_wall_s": wall},
         "e2e": {"value": value, "unit": "GUPS", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -372,6 +417,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         bp_gbs = 16.0 * my_updates / bp_s / 1e9
         smem_peak = 148 * 128 * sm_mhz * 1e6 / 1e9
         filt_gbs = 8.0 * px * rec.my_count / filt_s / 1e9
+        kernel_info = ctx.bp_kernel_info()
+        ncu_bp, ncu_filt = ncu_record("backprojection"), ncu_record("fused")
         line = {
             "metric": "fdk_reconstruction_gups", "value": updates / (ms_step / 1e3) / 1e9, "unit": "GUPS",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
@@ -383,22 +430,22 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "backprojection_gups": my_updates * world / bp_s / 1e9,
             "stage_ms": {"filter": filt_s * 1e3, "allgather": t_gather / args.steps, "backproject": bp_s * 1e3,
                          "note": "sequential stage times; at N>1 the timed step overlaps the all-gather with the backprojection"},
-            "roofline": {"kernel": "bp_tma_kernel", "bound": "smem", "achieved": bp_gbs, "peak": smem_peak,
-                         "unit": "GB/s", "frac": bp_gbs / smem_peak, "traffic": ncu_traffic("backprojection"),
-                         "traffic_note": "DRAM bytes per 64-projection launch (ncu, profiles/); algorithmic smem bytes per "
-                                         f"launch = {16.0 * my_updates * min(rec.batch, n_proj) / n_proj:.3e}",
-                         "pipe_busy_ncu_pct": ncu_metric("backprojection",
-                                                         "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed"),
+            "roofline": {"kernel": kernel_info["last"], "bound": "smem", "achieved": bp_gbs, "peak": smem_peak,
+                         "unit": "GB/s", "frac": bp_gbs / smem_peak, "traffic": ncu_traffic(ncu_bp),
+                         "traffic_note": traffic_note(ncu_bp),
+                         "launches_by_kernel": {"tma": kernel_info["tma_launches"], "exact": kernel_info["exact_launches"]},
+                         "measured_gather_peak": gather_peak(),
+                         "pipe_busy_ncu_pct": (ncu_bp or {}).get(
+                             "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed"),
                          "pipe_busy_note": "ncu: share of cycles the L1/shared-memory data pipe is busy for this kernel "
                                            "(algorithmic bytes + bank conflicts + table broadcasts), profiles/",
                          "note": "16 B of shared-memory sample fetches per voxel update; peak = 148 SMs x 128 B/clk x "
                                  f"{sm_mhz:.0f} MHz (SM clock sampled during the run); not an HBM- or tensor-bound kernel"},
             "roofline_filter": {"kernel": "filter_kernel", "bound": "hbm", "achieved": filt_gbs, "peak": hbm_peak,
-                                "unit": "GB/s", "frac": filt_gbs / hbm_peak, "traffic": ncu_traffic("fused"),
-                                "traffic_note": "DRAM bytes per 64-projection launch (ncu, profiles/); algorithmic = "
-                                                f"{8.0 * px * min(64, rec.my_count):.3e}",
-                                "pipe_busy_ncu_pct": ncu_metric("fused",
-                                                                "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed"),
+                                "unit": "GB/s", "frac": filt_gbs / hbm_peak, "traffic": ncu_traffic(ncu_filt),
+                                "traffic_note": traffic_note(ncu_filt),
+                                "pipe_busy_ncu_pct": (ncu_filt or {}).get(
+                                    "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed"),
                                 "note": f"8 B per detector pixel; peak {peak_src} (MEASURED_PEAKS.json hbm_gbs); ~110 flop and "
                                         "~30 shared-memory accesses per pixel keep it on the FP32/shared-memory side of the ridge"},
             "e2e": {"value": updates / (e2e_step / 1e3) / 1e9, "unit": "GUPS", "seconds": e2e_step / 1e3,
@@ -433,7 +480,7 @@ def main():
     ap.add_argument("--steps", type=int, default=5)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--config", default="c2", choices=sorted(CONFIGS))
+    ap.add_argument("--config", default="c3", choices=sorted(CONFIGS))
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work per reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--clock-interval-ms", type=int, default=100, help="NVML sampling period")

@@ -95,6 +95,12 @@ int paris_b200_ctx_stream(paris_b200_ctx* ctx, void** stream);
 /* counters since ctx_create: kernels launched by this library on this context */
 int paris_b200_ctx_launch_count(const paris_b200_ctx* ctx, uint64_t* launches);
 
+/* Which backprojection kernel ran: the instantiation of the most recent backprojection launch as text (tile, box,
+ * stages, stack layout; "bp_exact_kernel" for the reference-order fallback a geometry takes when its footprint does
+ * not fit the TMA kernel's tiles), and how many launches went to either since ctx_create.  Any pointer may be NULL. */
+int paris_b200_ctx_bp_kernel_info(const paris_b200_ctx* ctx, char* name, size_t name_len, uint64_t* tma_launches,
+                                  uint64_t* exact_launches);
+
 /* diagnostics: stats[0..5] = kernel launches, pool cudaMallocs, pool reuses of an idle buffer, pool reuses of a
  * buffer still being read (the upload waits), backprojection flushes, pool size; n >= 6 */
 int paris_b200_ctx_stats(const paris_b200_ctx* ctx, uint64_t* stats, int n);

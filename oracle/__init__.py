@@ -100,6 +100,12 @@ class _Lib:
     def num_threads(self) -> int:
         return int(self._f("num_threads")())
 
+    def set_num_threads(self, n: int) -> None:
+        """OpenMP threads of THIS library's parallel regions (torchrun exports OMP_NUM_THREADS=1)."""
+        f = self._f("set_num_threads")
+        f.argtypes, f.restype = [C.c_int], None
+        f(int(n))
+
     def calculate_volume_geometry(self, det: DetectorGeometry) -> VolumeGeometry:
         out = VolumeGeometry()
         self._f("calculate_volume_geometry")(C.byref(det), C.byref(out))
@@ -170,6 +176,39 @@ class Port(_Lib):
 
     def filter_size(self, n_row: int) -> int:
         return int(self.lib.oracle_filter_size(n_row))
+
+    def weight_filter_rows(self, proj: np.ndarray, det: DetectorGeometry, row0: int, n_rows: int) -> np.ndarray:
+        """weight -> filter of rows [row0, row0 + n_rows) of a full-size projection; returns a copy whose other rows
+        are untouched (bit-identical to the same rows of filter(weight(proj)))."""
+        out = np.ascontiguousarray(proj, dtype=np.float32).copy()
+        size = self.filter_size(det.n_row)
+        k = self.make_filter(size, det.l_px_row)
+        f = self.lib.oracle_weight_filter_rows
+        f.argtypes = [C.POINTER(C.c_float), C.POINTER(DetectorGeometry), C.POINTER(C.c_float), C.c_uint32, C.c_uint32,
+                      C.c_uint32]
+        f.restype = None
+        f(_fp(out), C.byref(det), _fp(k), size, row0, n_rows)
+        return out
+
+    def reconstruct_block(self, band_stack: np.ndarray, row0: int, det: DetectorGeometry, vol_full: VolumeGeometry,
+                          roi: Roi, first_idx: int = 0, idx_stride: int = 1, vol: np.ndarray | None = None) -> np.ndarray:
+        """The reference's loop for the box `roi` (ROI path) from the band of detector rows [row0, row0 + n_rows) of
+        every raw projection: band_stack is (n_proj, n_rows, n_row).  Returns the box (dz, dy, dx); pass the previous
+        result as `vol` to add the next chunk of projections (first_idx = scan index of its first projection)."""
+        assert band_stack.dtype == np.float32 and band_stack.flags["C_CONTIGUOUS"] and band_stack.ndim == 3
+        assert band_stack.shape[2] == det.n_row and row0 + band_stack.shape[1] <= det.n_col
+        box = self.apply_roi(vol_full, roi)
+        if vol is None:
+            vol = np.zeros((box.dim_z, box.dim_y, box.dim_x), dtype=np.float32)
+        assert vol.shape == (box.dim_z, box.dim_y, box.dim_x) and vol.dtype == np.float32 and vol.flags["C_CONTIGUOUS"]
+        f = self.lib.oracle_reconstruct_block
+        f.argtypes = [C.POINTER(C.c_float), C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32, C.c_uint32,
+                      C.POINTER(C.c_float), C.c_uint32, C.c_uint32, C.c_uint32, C.POINTER(DetectorGeometry),
+                      C.POINTER(VolumeGeometry), C.POINTER(Roi)]
+        f.restype = None
+        f(_fp(band_stack), band_stack.shape[0], first_idx, idx_stride, row0, band_stack.shape[1], _fp(vol),
+          box.dim_x, box.dim_y, box.dim_z, C.byref(det), C.byref(vol_full), C.byref(roi))
+        return vol
 
     def make_subvolume_information(self, vol: VolumeGeometry, num: int) -> SubvolumeInfo:
         out = SubvolumeInfo()

@@ -386,3 +386,75 @@ void oracle_reconstruct(const float* stack, uint32_t n_proj, uint32_t first_idx,
     free(p);
     free(k);
 }
+
+/* ---- full-size checks block by block ---------------------------------------------------- */
+
+/*
+ * Rows [row0, row0 + n_rows) of weight -> filter, in place in a FULL-SIZE projection buffer.  Not a different
+ * algorithm: the weight of a pixel depends only on its own (s, t) (src/openmp/weighting.cpp:44-52, t absolute), and
+ * the reference filters detector rows independently of each other (batched 1-D plans, howmany = n_col,
+ * src/openmp/filtering.cpp:199-204), so a band of rows goes through exactly the operations it would see inside the
+ * whole projection.  tests/test_oracle.py checks bit-identity with the crop of the full-projection result.
+ * This is what makes oracle checks at 2048^2 x 1440 affordable: a 32^3 block of voxels only ever reads a band of
+ * detector rows.
+ */
+void oracle_weight_filter_rows(float* p, const oracle_detector_geometry* det, const float* k, uint32_t filter_size,
+                               uint32_t row0, uint32_t n_rows)
+{
+    const float n_row_f = (float)det->n_row;
+    const float n_col_f = (float)det->n_col;
+    const float h_min = (det->delta_s * det->l_px_row) - ((n_row_f * det->l_px_row) / 2);
+    const float v_min = (det->delta_t * det->l_px_col) - ((n_col_f * det->l_px_col) / 2);
+    const float d_sd = fabsf(det->d_so) + fabsf(det->d_od);
+    const float l_px_row = det->l_px_row;
+    const float l_px_col = det->l_px_col;
+    const uint32_t dim_x = det->n_row;
+
+    #pragma omp parallel for collapse(2)
+    for(uint32_t t = row0; t < row0 + n_rows; ++t)
+    {
+        for(uint32_t s = 0u; s < dim_x; ++s)
+        {
+            const size_t coord = s + (size_t)t * dim_x;
+            const float s_f = (float)s;
+            const float t_f = (float)t;
+            const float h_s = (l_px_row / 2) + s_f * l_px_row + h_min;
+            const float v_t = (l_px_col / 2) + t_f * l_px_col + v_min;
+            const float w_st = d_sd / sqrtf(d_sd * d_sd + h_s * h_s + v_t * v_t);
+            p[coord] *= w_st;
+        }
+    }
+    oracle_apply_filter(p + (size_t)row0 * dim_x, dim_x, n_rows, k, filter_size);
+}
+
+/*
+ * The hot loop of src/main.cpp:98-105 for ONE box of voxels through the ROI path (src/openmp/backprojection.cpp:
+ * 105-118), fed with only the band of detector rows the box can touch.  band_stack: n_proj x n_rows x n_row raw
+ * samples (rows [row0, row0 + n_rows) of every projection).  Every other row of the scratch projection is NaN, so
+ * a band chosen too small poisons the result instead of going unnoticed.
+ */
+void oracle_reconstruct_block(const float* band_stack, uint32_t n_proj, uint32_t first_idx, uint32_t idx_stride,
+                              uint32_t row0, uint32_t n_rows, float* vol, uint32_t v_dim_x, uint32_t v_dim_y,
+                              uint32_t v_dim_z, const oracle_detector_geometry* det,
+                              const oracle_volume_geometry* vol_full, const oracle_roi* roi)
+{
+    const size_t px = (size_t)det->n_row * det->n_col;
+    const size_t band_px = (size_t)det->n_row * n_rows;
+    const uint32_t filter_size = oracle_filter_size(det->n_row);
+    float* k = (float*)malloc((filter_size / 2 + 1) * sizeof(float));
+    float* p = (float*)malloc(px * sizeof(float));
+    for(size_t i = 0; i < px; ++i)
+        p[i] = NAN;
+    oracle_make_filter(filter_size, det->l_px_row, k);
+    for(uint32_t i = 0u; i < n_proj; ++i)
+    {
+        memcpy(p + (size_t)row0 * det->n_row, band_stack + (size_t)i * band_px, band_px * sizeof(float));
+        oracle_weight_filter_rows(p, det, k, filter_size, row0, n_rows);
+        oracle_backproject(p, first_idx + i * idx_stride, 0.f, 0, vol, v_dim_x, v_dim_y, v_dim_z, 0u, det, vol_full, 1,
+                           roi);
+    }
+    free(p);
+    free(k);
+}
+
+void oracle_set_num_threads(int n) { omp_set_num_threads(n > 0 ? n : 1); }

@@ -98,6 +98,8 @@ extern "C"
     }
 
     int paris_ref_num_threads(void) { return omp_get_max_threads(); }
+    // (torchrun exports OMP_NUM_THREADS=1 to its children: the CPU arm of the bench sets the count itself)
+    void paris_ref_set_num_threads(int n) { omp_set_num_threads(n > 0 ? n : 1); }
 
     // src/geometry.cpp:71
     void paris_ref_calculate_volume_geometry(const ref_detector_geometry* det, ref_volume_geometry* out)

@@ -65,6 +65,7 @@ SIGNATURES = {
     "paris_b200_ctx_stream": (C.c_int, [_vp, _P(_vp)]),
     "paris_b200_ctx_launch_count": (C.c_int, [_vp, _P(C.c_uint64)]),
     "paris_b200_ctx_stats": (C.c_int, [_vp, _P(C.c_uint64), C.c_int]),
+    "paris_b200_ctx_bp_kernel_info": (C.c_int, [_vp, C.c_char_p, C.c_size_t, _P(C.c_uint64), _P(C.c_uint64)]),
     "paris_b200_event_create": (C.c_int, [_vp, _P(_vp)]),
     "paris_b200_event_record": (C.c_int, [_vp, _vp]),
     "paris_b200_event_elapsed_ms": (C.c_int, [_vp, _vp, _P(_f)]),
@@ -242,6 +243,13 @@ class Context:
         a = (C.c_uint64 * 6)()
         check(self._L.paris_b200_ctx_stats(self.h, a, 6))
         return dict(zip(("launches", "pool_malloc", "pool_ready", "pool_busy", "flushes", "pool_size"), list(a)))
+
+    def bp_kernel_info(self) -> dict:
+        """Instantiation of the most recent backprojection launch, launches that went to the TMA / exact kernel."""
+        name = C.create_string_buffer(96)
+        tma, exact = C.c_uint64(0), C.c_uint64(0)
+        check(self._L.paris_b200_ctx_bp_kernel_info(self.h, name, 96, C.byref(tma), C.byref(exact)))
+        return {"last": name.value.decode(), "tma_launches": tma.value, "exact_launches": exact.value}
 
     def event(self) -> int:
         """Create a CUDA event and record it on the compute stream."""

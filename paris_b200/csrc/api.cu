@@ -156,6 +156,22 @@ extern "C" int paris_b200_ctx_stats(const paris_b200_ctx* ctx, uint64_t* stats, 
     return PARIS_B200_OK;
 }
 
+extern "C" int paris_b200_ctx_bp_kernel_info(const paris_b200_ctx* ctx, char* name, size_t name_len, uint64_t* tma_launches,
+                                             uint64_t* exact_launches)
+{
+    PB_CHECK_ARG(ctx != nullptr);
+    if(name != nullptr && name_len > 0)
+    {
+        std::strncpy(name, ctx->bp_last_kernel, name_len - 1);
+        name[name_len - 1] = '\0';
+    }
+    if(tma_launches != nullptr)
+        *tma_launches = ctx->bp_launches_tma;
+    if(exact_launches != nullptr)
+        *exact_launches = ctx->bp_launches_exact;
+    return PARIS_B200_OK;
+}
+
 struct paris_b200_event
 {
     int device;

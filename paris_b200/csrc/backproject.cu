@@ -156,6 +156,8 @@ namespace pb
         bp_exact_kernel<<<grid, block, 0, ctx->compute>>>(d_first_slot, slot_floats, d_vol, g, a);
         PB_CUDA(cudaGetLastError());
         ++ctx->launches;
+        ++ctx->bp_launches_exact;
+        std::snprintf(ctx->bp_last_kernel, sizeof(ctx->bp_last_kernel), "bp_exact_kernel");
         return PARIS_B200_OK;
     }
 

@@ -865,6 +865,10 @@ namespace pb
         kern<<<grid, CFG::THREADS, smem, ctx->compute>>>(ctx->tma.map, d_vol, g, a, first, tiles_x, tiles_y, super);
         PB_CUDA(cudaGetLastError());
         ++ctx->launches;
+        ++ctx->bp_launches_tma;
+        std::snprintf(ctx->bp_last_kernel, sizeof(ctx->bp_last_kernel), "bp_tma_kernel<%dx%dx%d tile, box %dx%d, %d stages, %s%s>",
+                      CFG::TX, CFG::TY, CFG::TZ, CFG::BH, CFG::BV, CFG::STAGES, CFG::SPLIT ? "split2" : "plain",
+                      straddle ? ", straddle" : "");
         return PARIS_B200_OK;
     }
 

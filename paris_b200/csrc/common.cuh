@@ -96,6 +96,10 @@ struct paris_b200_ctx
     bool h2d_any = false;
     cudaEvent_t scratch_ev = nullptr;
     uint64_t launches = 0;
+    // which backprojection kernel the launches went to (paris_b200_ctx_bp_kernel_info): a geometry whose footprint
+    // does not fit the TMA kernel's tiles silently takes the exact kernel, 2-3x slower -- callers can see that
+    uint64_t bp_launches_tma = 0, bp_launches_exact = 0;
+    char bp_last_kernel[96] = "";
     // pool statistics (paris_b200_ctx_stats)
     uint64_t stat_pool_malloc = 0, stat_pool_ready = 0, stat_pool_busy = 0, stat_flush = 0;
 

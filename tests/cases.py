@@ -4,7 +4,8 @@ from __future__ import annotations
 import numpy as np
 
 import oracle
-from paris_b200 import capi, phantom
+import oracle.phantom as phantom
+from paris_b200 import capi
 
 
 def both_det(n_row, n_col, l_px=0.4, delta_s=0.0, delta_t=0.0, d_so=500.0, d_od=500.0, n_proj=64, l_px_col=None):
@@ -49,3 +50,39 @@ def errors(a: np.ndarray, b: np.ndarray, c: float):
 # north_star tolerance: max abs error <= 1e-4 of phantom contrast, RMSE <= 1e-5
 MAX_ABS_TOL = 1e-4
 RMSE_TOL = 1e-5
+
+
+# ---- full-size checks block by block (no CPU oracle finishes 1e12 updates) -----------------------------
+
+def box_roi(x1, nx, y1, ny, z1, nz) -> "oracle.Roi":
+    """The region_of_interest whose box is [x1, x1+nx) x [y1, y1+ny) x [z1, z1+nz) under apply_roi's rule
+    (dim = x2 - x1, + 1 iff x1 == 0; /root/reference/src/geometry.cpp:86-130)."""
+    def upper(lo, n):
+        return lo + n - 1 if lo == 0 else lo + n
+    return oracle.Roi(x1, upper(x1, nx), y1, upper(y1, ny), z1, upper(z1, nz))
+
+
+def row_band(det, vol_full, x1, nx, y1, ny, z1, nz, margin=3):
+    """[row0, row0 + n_rows): a conservative band of detector rows the voxels [x1, x1+nx) x [y1, y1+ny) x [z1, z1+nz)
+    of the FULL volume can read at any projection angle: v = (z_m * factor - min_v) / l_px - 0.5 with
+    factor = d_sd / (s + d_so), |s| <= the box's largest distance from the rotation axis
+    (/root/reference/src/openmp/backprojection.cpp:120-133).  Float64; `margin` rows either side cover float32
+    rounding of the reference's own v and the + 1 neighbour."""
+    def centred(i, dim, size):
+        return -(dim * size / 2.0) + size / 2.0 + i * size
+    xs = [centred(i, vol_full.dim_x, float(vol_full.l_vx_x)) for i in (x1, x1 + nx - 1)]
+    ys = [centred(i, vol_full.dim_y, float(vol_full.l_vx_y)) for i in (y1, y1 + ny - 1)]
+    zs = [centred(i, vol_full.dim_z, float(vol_full.l_vx_z)) for i in (z1, z1 + nz - 1)]
+    r = max(np.hypot(x, y) for x in xs for y in ys)
+    d_so, d_sd = float(det.d_so), abs(float(det.d_so)) + abs(float(det.d_od))
+    assert d_so - r > 0
+    factors = (d_sd / (d_so + r), d_sd / (d_so - r))
+    l_px = float(det.l_px_col)
+    min_v = -(det.n_col * l_px / 2.0) - float(det.delta_t) * l_px
+    vs = [(z * f - min_v) / l_px - 0.5 for z in zs for f in factors]
+    lo = int(np.floor(min(vs))) - margin
+    hi = int(np.floor(max(vs))) + 1 + margin
+    lo, hi = max(lo, 0), min(hi, det.n_col - 1)
+    if hi < lo:          # the box never sees the detector: any one row will do
+        lo = hi = min(max(lo, 0), det.n_col - 1)
+    return lo, hi - lo + 1

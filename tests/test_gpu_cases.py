@@ -172,7 +172,8 @@ def test_changing_the_target_flushes(ctx, port):
 def test_phantom_kernel_matches_numpy(ctx):
     odet, det = both_det(72, 40, l_px=0.3, delta_s=1.5, delta_t=-0.5, n_proj=12)
     ell = phantom.scaled_ellipsoids(phantom.SHEPP_LOGAN_3D, 0.9 * phantom.fov_radius(72, 0.3, 1.5, 500, 500))
-    want = phantom.shepp_logan_stack(72, 40, 0.3, 0.3, 1.5, -0.5, 500, 500, 12)
+    import oracle.phantom
+    want = oracle.phantom.shepp_logan_stack(72, 40, 0.3, 0.3, 1.5, -0.5, 500, 500, 12)
     d = ctx.dev_alloc(want.nbytes)
     ctx.phantom_project(ell, det, 0, 12, d)
     got = np.empty_like(want)
@@ -180,162 +181,6 @@ def test_phantom_kernel_matches_numpy(ctx):
         ctx.proj_d2h(d + i * 72 * 40 * 4, got[i], 72, 40)
     ctx.dev_free(d)
     assert np.abs(got - want).max() <= 1e-4 * want.max()
-
-
-def test_full_size_config2_fast_kernel_against_exact_kernel(ctx):
-    """BASELINE config 2 at full size (512^3 from 720 x 1024^2): the TMA kernel against the exact kernel
-    (which the small cases pin bit for bit to the reference), both on the same filtered stack, plus the
-    size-independent sanity property that the phantom's plateau sits at density * N / (8 pi)."""
-    n, n_proj, k = 1024, 720, 512
-    l_px = 0.2
-    det = capi.DetectorGeometry(n, n, l_px, l_px, 0, 0, 500, 500, 360.0 / n_proj)
-    nat = capi.calculate_volume_geometry(det)
-    f32 = np.float32
-    vol = capi.VolumeGeometry(k, k, k, f32(nat.l_vx_x * nat.dim_x / k), f32(nat.l_vx_y * nat.dim_y / k),
-                              f32(nat.l_vx_z * nat.dim_z / k))
-    raw = ctx.dev_alloc(n_proj * n * n * 4)
-    ell = phantom.scaled_ellipsoids(phantom.SHEPP_LOGAN_3D, 0.9 * phantom.fov_radius(n, l_px, 0, 500, 500))
-    ctx.phantom_project(ell, det, 0, n_proj, raw)
-    slot_bytes, _ = capi.stack_slot_bytes(n, n)
-    stack = ctx.stack_alloc(n, n, n_proj)
-    filt = ctx.filter_create(capi.filter_size(n), l_px)
-    layout = capi.choose_stack_layout(det, vol)
-    assert layout == capi.LAYOUT_SPLIT2
-    ctx.filter_to_stack_batch(raw, n * n, n_proj, det, filt, stack, 0, layout)
-    sc = np.array([angle_sin_cos(i, det) for i in range(n_proj)], dtype=np.float32)
-    out = {}
-    for kernel in (2, 1):
-        ctx.set_option("bp_kernel", kernel)
-        v = ctx.volume_alloc(k, k, k)
-        ctx.backproject_stack(stack, 0, n_proj, sc[:, 0], sc[:, 1], v, (k, k, k), 0, det, vol, layout=layout)
-        out[kernel] = np.empty((k, k, k), np.float32)
-        ctx.vol_d2h(v, out[kernel], k ** 3)
-        ctx.volume_free(v)
-    ctx.set_option("bp_kernel", 0)
-    ctx.filter_destroy(filt)
-    ctx.stack_free(stack)
-    ctx.dev_free(raw)
-    c = contrast(n_proj)
-    mx, rms = errors(out[2], out[1], c)
-    print(f"config 2 full size: fast vs exact kernel max {mx:.2e} C, rmse {rms:.2e} C")
-    assert mx <= MAX_ABS_TOL and rms <= RMSE_TOL
-    # brain tissue of the phantom (density 1.0 - 0.8 = 0.2) a few voxels off the centre, away from the ventricles
-    plateau = out[2][k // 2, k // 2 - 40:k // 2 - 30, k // 2 - 4:k // 2 + 4].mean()
-    assert abs(plateau / (0.2 * c) - 1.0) < 0.05
-
-
-def test_full_size_config4_roi_offset_detector(ctx):
-    """BASELINE config 4 at full size: 1024^3 region of interest of the 2248 x 2248 x 2060 natural volume from 2880
-    projections of a 2048^2 detector shifted by 100 pixels.  Properties checked (no CPU oracle finishes this size):
-    the production kernel agrees with the exact kernel -- pinned bit for bit to the reference on the small cases --
-    on bands of the ROI at its bottom, middle and top, and the ROI reconstruction is a bit-identical crop whether it
-    is computed in one piece or band by band (what z-slab tasks and the chunked download rely on)."""
-    n, n_proj, k = 2048, 2880, 1024
-    l_px = 0.1
-    det = capi.DetectorGeometry(n, n, l_px, l_px, 100.0, 0, 500, 500, 360.0 / n_proj)
-    nat = capi.calculate_volume_geometry(det)
-    assert (nat.dim_x, nat.dim_y, nat.dim_z) == (2248, 2248, 2060)
-    roi = capi.Roi(612, 1636, 612, 1636, 518, 1542)
-    reg = capi.apply_roi(nat, roi)
-    assert (reg.dim_x, reg.dim_y, reg.dim_z) == (k, k, k)
-    layout = capi.choose_stack_layout(det, nat)
-    assert layout == capi.LAYOUT_PLAIN
-    stack = ctx.stack_alloc(n, n, n_proj)                               # 48 GB
-    filt = ctx.filter_create(capi.filter_size(n), l_px)
-    ell = phantom.scaled_ellipsoids(phantom.SHEPP_LOGAN_3D, 0.9 * phantom.fov_radius(n, l_px, 100.0, 500, 500))
-    raw = ctx.dev_alloc(64 * n * n * 4)
-    for first in range(0, n_proj, 64):                                  # raw projections never exist all at once
-        ctx.phantom_project(ell, det, first, 64, raw)
-        ctx.filter_to_stack_batch(raw, n * n, 64, det, filt, stack, first, layout)
-    ctx.dev_free(raw)
-    sc = np.array([angle_sin_cos(i, det) for i in range(n_proj)], dtype=np.float32)
-
-    ctx.set_option("bp_kernel", 2)
-    v = ctx.volume_alloc(k, k, k)
-    e0 = ctx.event()
-    ctx.backproject_stack(stack, 0, n_proj, sc[:, 0], sc[:, 1], v, (k, k, k), 0, det, nat, roi=roi, layout=layout)
-    e1 = ctx.event()
-    ms = ctx.elapsed_ms(e0, e1)
-    print(f"config 4 full size: {k ** 3 * n_proj / ms / 1e6:.0f} GUPS ({ms:.0f} ms)")
-    full = np.empty((k, k, k), np.float32)
-    ctx.vol_d2h(v, full, k ** 3)
-    ctx.volume_free(v)
-
-    c = contrast(n_proj)
-    band = 4
-    for z in (0, 509, k - band):                                        # bands of `band` slices at these ROI offsets
-        got = {}
-        for kernel in (2, 1):
-            ctx.set_option("bp_kernel", kernel)
-            vb = ctx.volume_alloc(k, k, band)
-            ctx.backproject_stack(stack, 0, n_proj, sc[:, 0], sc[:, 1], vb, (k, k, band), z, det, nat, roi=roi,
-                                  layout=layout)
-            got[kernel] = np.empty((band, k, k), np.float32)
-            ctx.vol_d2h(vb, got[kernel], band * k * k)
-            ctx.volume_free(vb)
-        assert np.array_equal(got[2], full[z:z + band]), f"band at {z} is not a crop of the one-piece ROI"
-        mx, rms = errors(got[2], got[1], c)
-        print(f"config 4 band at z={z}: fast vs exact kernel max {mx:.2e} C, rmse {rms:.2e} C")
-        assert mx <= MAX_ABS_TOL and rms <= RMSE_TOL
-    ctx.set_option("bp_kernel", 0)
-    ctx.filter_destroy(filt)
-    ctx.stack_free(stack)
-    assert np.isfinite(full).all() and full.max() > 0.5 * 1.0 * c * 0.2
-
-
-def test_full_size_config5_slabs_stream_over_one_filtered_stack(ctx):
-    """BASELINE config 5 geometry at full size: the 2048^3 region (z in [5, 2053) of the 2048 x 2048 x 2058 natural
-    volume) from 2880 projections of a 2048^2 detector, reconstructed slab by slab from ONE filtered stack (the
-    reference re-reads and re-filters the whole scan for every sub-volume, src/main.cpp:93-105).  Two adjacent
-    128-slice slabs of the 16 are computed here: streamed separately they must be bit-identical to the same 256
-    slices computed in one piece, and bands of them must agree with the exact kernel."""
-    n, n_proj, k = 2048, 2880, 2048
-    l_px = 0.1
-    det = capi.DetectorGeometry(n, n, l_px, l_px, 0, 0, 500, 500, 360.0 / n_proj)
-    nat = capi.calculate_volume_geometry(det)
-    assert (nat.dim_x, nat.dim_y, nat.dim_z) == (2048, 2048, 2058)
-    roi = capi.Roi(0, 2047, 0, 2047, 5, 2053)
-    reg = capi.apply_roi(nat, roi)
-    assert (reg.dim_x, reg.dim_y, reg.dim_z) == (k, k, k)
-    layout = capi.choose_stack_layout(det, nat)
-    stack = ctx.stack_alloc(n, n, n_proj)                               # 48 GB, filled once
-    filt = ctx.filter_create(capi.filter_size(n), l_px)
-    ell = phantom.scaled_ellipsoids(phantom.SHEPP_LOGAN_3D, 0.9 * phantom.fov_radius(n, l_px, 0, 500, 500))
-    raw = ctx.dev_alloc(64 * n * n * 4)
-    for first in range(0, n_proj, 64):
-        ctx.phantom_project(ell, det, first, 64, raw)
-        ctx.filter_to_stack_batch(raw, n * n, 64, det, filt, stack, first, layout)
-    ctx.dev_free(raw)
-    sc = np.array([angle_sin_cos(i, det) for i in range(n_proj)], dtype=np.float32)
-    slab = 128                                                          # 16 slabs of 128 slices
-
-    def reconstruct(z_first, dz, kernel):
-        ctx.set_option("bp_kernel", kernel)
-        v = ctx.volume_alloc(k, k, dz)
-        e0 = ctx.event()
-        ctx.backproject_stack(stack, 0, n_proj, sc[:, 0], sc[:, 1], v, (k, k, dz), z_first, det, nat, roi=roi, layout=layout)
-        e1 = ctx.event()
-        ms = ctx.elapsed_ms(e0, e1)
-        out = np.empty((dz, k, k), np.float32)
-        ctx.vol_d2h(v, out, dz * k * k)
-        ctx.volume_free(v)
-        return out, ms
-
-    a, ms_a = reconstruct(7 * slab, slab, 2)
-    b, _ = reconstruct(8 * slab, slab, 2)
-    print(f"config 5 slab of {slab} slices: {k * k * slab * n_proj / ms_a / 1e6:.0f} GUPS ({ms_a:.0f} ms)")
-    both, _ = reconstruct(7 * slab, 2 * slab, 2)
-    assert np.array_equal(both[:slab], a) and np.array_equal(both[slab:], b)
-    c = contrast(n_proj)
-    for z, src in ((7 * slab, a), (9 * slab - 2, b)):
-        exact, _ = reconstruct(z, 2, 1)
-        got = src[z - (7 * slab if src is a else 8 * slab):][:2]
-        mx, rms = errors(got, exact, c)
-        print(f"config 5 band at z={z}: fast vs exact kernel max {mx:.2e} C, rmse {rms:.2e} C")
-        assert mx <= MAX_ABS_TOL and rms <= RMSE_TOL
-    ctx.set_option("bp_kernel", 0)
-    ctx.filter_destroy(filt)
-    ctx.stack_free(stack)
 
 
 @pytest.mark.parametrize("n_row,n_col", [(96, 96), (100, 37), (256, 64), (1024, 16), (2048, 8), (3000, 5)])

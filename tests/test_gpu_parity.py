@@ -121,3 +121,80 @@ def test_reconstruction_within_tolerance(ctx, port, kernel, fused):
     mx, rms = errors(got, ref, contrast(n_proj))
     print(f"kernel={kernel} fused={fused}: max {mx:.3e} rmse {rms:.3e}")
     assert mx <= MAX_ABS_TOL and rms <= RMSE_TOL
+
+
+def test_reupload_into_a_live_buffer_waits_for_the_kernels_queued_on_it(ctx, port):
+    """A pooled device buffer that is uploaded to AGAIN (no dev_free / dev_alloc in between) while the fused
+    weight+filter launch that reads its first content is still queued: the second upload must not overtake that
+    launch (copies run on their own stream).  Slot 0 must hold filter(A), slot 1 filter(B)."""
+    n_row, n_col = 1024, 256
+    odet, det = both_det(n_row, n_col, l_px=0.2)
+    rng = np.random.default_rng(7)
+    a = rng.standard_normal((n_col, n_row)).astype(np.float32)
+    b = rng.standard_normal((n_col, n_row)).astype(np.float32)
+    ha, hb = capi.PinnedArray(a.shape), capi.PinnedArray(b.shape)
+    ha.array[...] = a
+    hb.array[...] = b
+    f = ctx.filter_create(capi.filter_size(n_row), 0.2)
+    slot_bytes, pitch = capi.stack_slot_bytes(n_row, n_col)
+    st = ctx.stack_alloc(n_row, n_col, 2)
+    d = ctx.dev_alloc(a.nbytes)
+    for rep in range(20):   # (a race does not lose every time)
+        ctx.proj_h2d(ha.ptr, d, n_row, n_col)
+        ctx.filter_to_stack(d, det, f, st, 0, capi.LAYOUT_PLAIN)
+        ctx.proj_h2d(hb.ptr, d, n_row, n_col)
+        ctx.filter_to_stack(d, det, f, st, 1, capi.LAYOUT_PLAIN)
+        out = np.empty((2, n_row, pitch), np.float32)
+        ctx.proj_d2h(st, out[0], pitch, n_row)
+        ctx.proj_d2h(st + slot_bytes, out[1], pitch, n_row)
+        for got, src in ((out[0], a), (out[1], b)):
+            ref = port.filter(port.weight(src, odet), odet)
+            assert np.abs(got[:, :n_col].T - ref).max() <= 2e-6 * np.abs(ref).max(), rep
+    ctx.dev_free(d)
+    ctx.stack_free(st)
+    ctx.filter_destroy(f)
+    ha.free()
+    hb.free()
+
+
+def test_volume_alloc_lets_go_of_a_spare_slab_of_another_size(ctx):
+    """volume_free keeps the last slab for the next volume_alloc of the SAME size; a request of another size (the
+    last slab of a run carries the remainder) must release it first instead of holding two slabs."""
+    a = ctx.volume_alloc(64, 64, 40)
+    ctx.volume_free(a)                      # kept as the spare
+    b = ctx.volume_alloc(64, 64, 43)        # another size: the spare goes
+    c = ctx.volume_alloc(64, 64, 40)        # a fresh allocation, zero-initialised
+    got = np.ones((40, 64, 64), np.float32)
+    ctx.vol_d2h(c, got, got.size)
+    assert not got.any()
+    ctx.volume_free(b)
+    ctx.volume_free(c)
+    d = ctx.volume_alloc(64, 64, 40)        # the most recent spare (c) is reused
+    assert d == c
+    ctx.volume_free(d)
+
+
+def test_volume_clear_drops_the_pending_batch(ctx, port):
+    """volume_clear: 'pending batches targeting it are dropped' (include/paris_b200.h) -- projections enqueued before
+    the clear must not show up in the volume, and the ones after it must."""
+    n, n_proj = 48, 6
+    odet, det, ovol, vol, stack = _recon_case(n, n_proj)
+    pl = Pipeline(ctx, det)
+    v = pl.make_volume(vol.dim_x, vol.dim_y, vol.dim_z)
+    for i in range(3):
+        d = pl.load(stack[i], idx=i)
+        pl.backproject(d, v, 0, vol, fused_raw=True)
+        pl.release(d)
+    ctx.volume_clear(v.d_ptr, vol.dim_x, vol.dim_y, vol.dim_z)
+    for i in range(3, n_proj):
+        d = pl.load(stack[i], idx=i)
+        pl.backproject(d, v, 0, vol, fused_raw=True)
+        pl.release(d)
+    got = pl.save(v)
+    pl.free_volume(v)
+    pl.close()
+    ref = np.zeros((ovol.dim_z, ovol.dim_y, ovol.dim_x), np.float32)
+    for i in range(3, n_proj):
+        port.backproject(port.filter(port.weight(stack[i], odet), odet), i, ref, odet, ovol)
+    mx, rms = errors(got, ref, contrast(n_proj))
+    assert mx <= MAX_ABS_TOL and rms <= RMSE_TOL

@@ -10,7 +10,7 @@ import numpy as np
 import pytest
 
 import oracle
-from paris_b200 import phantom
+import oracle.phantom as phantom
 
 from cases import both_det, coarse_volume, shepp_logan
 
