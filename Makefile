@@ -7,7 +7,7 @@ ARCH     := -gencode arch=compute_100a,code=sm_100a
 NVFLAGS  := $(ARCH) -O3 -std=c++17 -lineinfo -ccbin $(HOSTCXX) -Xcompiler -fPIC -Xcompiler -Wall \
             -Xcompiler -ffp-contract=off $(EXTRA_NVFLAGS)
 CSRC     := paris_b200/csrc
-SRCS     := $(CSRC)/api.cu $(CSRC)/weight.cu $(CSRC)/filter.cu $(CSRC)/backproject.cu $(CSRC)/backproject_tma.cu $(CSRC)/phantom.cu
+SRCS     := $(CSRC)/api.cu $(CSRC)/weight.cu $(CSRC)/filter.cu $(CSRC)/backproject.cu $(CSRC)/backproject_tma.cu $(CSRC)/phantom.cu $(CSRC)/group.cu
 OBJS     := $(SRCS:.cu=.o)
 HDRS     := $(wildcard $(CSRC)/*.cuh) include/paris_b200.h
 LIB      := paris_b200/libparis_b200.so

@@ -13,9 +13,10 @@ A "step" is one full reconstruction of the workload from its raw projections:
   e2e     the same reconstruction through the reference-shaped per-projection loop of the C++ host layer
           (load -> weight -> filter -> backproject per projection, then copy_d2h): raw projections start
           in pinned HOST memory and the volume ends in pinned HOST memory, copies inside the timed region.
-N > 1 (torchrun): the region is cut into N z-slabs (one per rank); every rank filters 1/N of the
-projections, an NCCL all-gather distributes the filtered stack, every rank backprojects all projections
-into its own slab (no reduction).  Strong scaling: the workload is the same for every N.
+N > 1 (torchrun, one rank per GPU, process group over NCCL): the region is cut into N z-slabs; every rank uploads and
+filters 1/N of the projections round by round and copies the detector-row band each peer needs straight into that
+peer's stack over NVLink (paris_b200_group_*, csrc/group.cu); every rank backprojects all projections into its own
+slab (no reduction) and downloads it into ONE shared host volume.  Strong scaling: the workload is the same for every N.
 
 --impl reference times the reference's own OpenMP backend (oracle/_ref, built from /root/reference; the
 plain-C port if that is absent) on the host cores, on a bounded sample of the same workload.
@@ -310,8 +311,59 @@ def run_reference(args, rank: int):
 # B200 arm
 # ------------------------------------------------------------------------------------------------------------------
 
+class SharedHostVolume:
+    """The host volume every member downloads its slabs into (the sink's job, /root/reference/src/sink.cpp:76-81: the
+    volume is assembled by writing every slab at its offset).  One POSIX shared-memory segment, page-locked by every
+    process; falls back to a pinned buffer of the member's own where that is not possible (then `kind` says so)."""
+
+    def __init__(self, capi, dist, rank, world, voxels, member):
+        self.capi, self.kind, self.shm, self.registered = capi, "per-rank pinned buffers", None, False
+        self.ptr = None
+        ok = True
+        if world > 1:
+            from multiprocessing import shared_memory
+            name = f"paris_b200_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
+            try:
+                if rank == 0:
+                    try:
+                        shared_memory.SharedMemory(name=name).unlink()
+                    except FileNotFoundError:
+                        pass
+                    self.shm = shared_memory.SharedMemory(name=name, create=True, size=voxels * 4)
+            except OSError:
+                ok = False
+            dist.barrier()
+            try:
+                if rank != 0 and ok:
+                    self.shm = shared_memory.SharedMemory(name=name)
+                if self.shm is not None:
+                    self.array = np.ndarray((voxels,), np.float32, buffer=self.shm.buf)
+                    capi.check(capi.lib().paris_b200_host_register(self.array.ctypes.data, voxels * 4))
+                    self.registered = True
+            except (OSError, capi.Error):
+                ok = False
+            import torch
+            flag = torch.tensor([1.0 if (ok and self.registered) else 0.0], device="cuda")
+            dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+            if flag.item() > 0:
+                self.kind = "one shared page-locked volume (POSIX shm), slabs written at their offsets"
+                self.ptr = self.array.ctypes.data + member.info.z_first * member.slice_floats * 4
+        if self.ptr is None:
+            self.ptr = member.alloc_host_slabs().ptr
+
+    def close(self, rank):
+        if self.registered:
+            self.capi.lib().paris_b200_host_unregister(self.array.ctypes.data)
+        self.array = None
+        if self.shm is not None:
+            self.shm.close()
+            if rank == 0:
+                self.shm.unlink()
+
+
 def run_b200(args, rank: int, world: int, local_rank: int):
     from paris_b200 import capi, dropin
+    from paris_b200.multi import GroupMember
     from paris_b200.pipeline import angle_sin_cos
 
     dist = None
@@ -319,11 +371,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         import torch
         import torch.distributed as dist_mod
         torch.cuda.set_device(local_rank)
-        # NCCL's own stream gets high priority: its CTAs are placed as soon as backprojection CTAs retire, instead
-        # of waiting for the whole (28-wave) backprojection grid to be issued
-        opts = dist_mod.ProcessGroupNCCL.Options()
-        opts.is_high_priority_stream = True
-        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank), pg_options=opts)
+        # one rank per GPU over NCCL: handles, barriers and the max-over-ranks of the timings travel through it; the
+        # filtered projections themselves go through peer memory (csrc/group.cu)
+        dist_mod.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
         dist = dist_mod
 
     det, vol, n_proj, roi, dims = geometry(args.config)
@@ -331,58 +381,133 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     px = n * n
     voxels = dims[0] * dims[1] * dims[2]
     updates = voxels * n_proj
+    spm = args.slabs_per_gpu if args.slabs_per_gpu else (2 if args.config == "c5" else 1)
 
-    # one context per process, shared by the C++ loop (e2e) and the stack-level calls (value)
-    from paris_b200.multi import SlabPlan, MultiGpuReconstructor
-    plan = SlabPlan(dims[2], world, rank)
-    rec = MultiGpuReconstructor(local_rank, det, vol, n_proj, plan, dist, roi=roi, region=dims)
-    ctx = rec.ctx
+    member = GroupMember(local_rank, rank, world, det, vol, n_proj, roi=roi, slabs_per_member=spm,
+                         whole_projections=bool(args.whole_projections),
+                         exchange=capi.EXCHANGE_KERNEL if args.exchange == "kernel" else capi.EXCHANGE_COPY_ENGINE)
+    if dist is not None:
+        handles = [None] * world
+        dist.all_gather_object(handles, member.export())
+        member.connect(handles)
+    ctx, info = member.ctx, member.info
+    member.generate_inputs(ellipsoids(det))
+    sc = np.array([angle_sin_cos(i, det) for i in range(n_proj)], dtype=np.float32)
+    my_slices = info.z_count
+    slab_dims = (dims[0], dims[1], my_slices)
+    # stage kernels on their own (roofline legs): this member's share through the filter, all projections through the
+    # backprojection into this member's slices, on ONE stream with events in between
+    filt = ctx.filter_create(capi.filter_size(n), float(det.l_px_row))
+    stage_vol = info.d_first_slab if info.slabs == 1 else ctx.volume_alloc(*slab_dims)
 
-    # synthetic raw stack: this rank's share of the projections, generated on the device, mirrored on the host
-    rec.generate_inputs(ellipsoids(det))
+    def staged_step():
+        e0 = ctx.event()
+        local = 0
+        for first, count in member.runs:
+            for done in range(0, count, 64):
+                c = min(64, count - done)
+                ctx.filter_to_stack_batch(member.d_raw + (local + done) * px * 4, px, c, det, filt, info.d_stack, first + done,
+                                          info.layout)
+            local += count
+        e1 = ctx.event()
+        ctx.volume_clear(stage_vol, *slab_dims)
+        ctx.backproject_stack(info.d_stack, 0, n_proj, sc[:, 0], sc[:, 1], stage_vol, slab_dims, info.z_first, det, vol,
+                              roi=roi, layout=info.layout)
+        e2 = ctx.event()
+        tf = ctx.elapsed_ms(e0, e1, destroy=False)
+        tb = ctx.elapsed_ms(e1, e2, destroy=False)
+        for e in (e0, e1, e2):
+            capi.check(capi.lib().paris_b200_event_destroy(e))
+        return tf, tb
 
     sampler = ClockSampler(local_rank, args.clock_interval_ms)
     barrier = (lambda: dist.barrier()) if dist is not None else (lambda: None)
 
     # ---- device-resident steps -------------------------------------------------------------------------------
-    for _ in range(args.warmup):
-        rec.step_resident()
-    ctx.sync()
-    barrier()
-    sampler.start()
-    launches0 = rec.launch_count()
-    t_filter = t_gather = t_bp = 0.0
-    t0 = time.perf_counter()
-    e_start = ctx.event()
-    for _ in range(args.steps):
-        if world == 1:
-            # one GPU: the step is sequential anyway, so the stage split comes from the timed steps themselves
-            tf, tg, tb = rec.step_resident(timed=True)
-            t_filter += tf
-            t_gather += tg
-            t_bp += tb
-        else:
-            rec.step_resident()   # pipelined: all-gather of round c behind the backprojection of round c-1
-    e_stop = ctx.event()
-    ms_total = ctx.elapsed_ms(e_start, e_stop)
-    ctx.sync()
-    barrier()
-    wall_resident = time.perf_counter() - t0
-    launches = rec.launch_count() - launches0
-    clocks = sampler.stop()
-    if world > 1:
-        # stage breakdown (diagnostic, outside the timed region): the same work without overlap
+    t_filter = t_bp = 0.0
+    if world == 1:
+        # one GPU: filter, then backprojection, back to back on one stream -- the timed steps themselves give the
+        # per-kernel durations of the roofline objects
+        for _ in range(args.warmup):
+            staged_step()
+        ctx.sync()
+        sampler.start()
+        launches0 = member.launch_count()
+        t0 = time.perf_counter()
+        e_start = ctx.event()
         for _ in range(args.steps):
-            tf, tg, tb = rec.step_resident(timed=True)
+            tf, tb = staged_step()
             t_filter += tf
-            t_gather += tg
             t_bp += tb
+        e_stop = ctx.event()
+        ms_total = ctx.elapsed_ms(e_start, e_stop)
+        ctx.sync()
+    else:
+        # N GPUs: the pipelined group step (upload-free: raw projections resident) -- filter, exchange over peer
+        # memory and backprojection overlap; timed with events on the backprojection stream, max over ranks
+        for _ in range(args.warmup):
+            member.step_resident()
+        barrier()
+        sampler.start()
+        launches0 = member.launch_count()
+        t0 = time.perf_counter()
+        e_start = ctx.event()
+        for _ in range(args.steps):
+            member.step_resident()
+        e_stop = ctx.event()
+        ms_total = ctx.elapsed_ms(e_start, e_stop)
+        barrier()
+    wall_resident = time.perf_counter() - t0
+    launches = member.launch_count() - launches0
+    clocks = sampler.stop()
+    kernel_info = ctx.bp_kernel_info()   # (the instantiation the resident steps ran, before the e2e path's chunked tail)
+
+    parity = None
+    if world > 1:
+        # the volumes, not just the speed: two 4-slice bands of this member's slab recomputed from its own stack by the
+        # exact kernel (the reference's arithmetic operation for operation, tests/test_gpu_parity.py)
+        c = float(n_proj) / (8.0 * np.pi)
+        worst = [0.0, 0.0]
+        if info.slabs == 1:
+            for z in sorted({0, max(0, my_slices // 2 - 2), max(0, my_slices - 4)}):
+                dz = min(4, my_slices - z)
+                got = member.device_slab(z, dz)
+                ctx.set_option("bp_kernel", 1)
+                v = ctx.volume_alloc(dims[0], dims[1], dz)
+                ctx.backproject_stack(info.d_stack, 0, n_proj, sc[:, 0], sc[:, 1], v, (dims[0], dims[1], dz), info.z_first + z,
+                                      det, vol, roi=roi, layout=info.layout)
+                want = np.empty_like(got)
+                ctx.vol_d2h(v, want, want.size)
+                ctx.volume_free(v)
+                ctx.set_option("bp_kernel", 0)
+                d = got.astype(np.float64) - want
+                worst[0] = max(worst[0], float(np.abs(d).max() / c))
+                worst[1] = max(worst[1], float(np.sqrt(np.mean(d * d)) / c))
+                if not np.isfinite(got).all():
+                    worst = [float("inf"), float("inf")]
+        parity = worst
+        # stage breakdown (diagnostic, outside the timed region): the same kernels without overlap
+        for _ in range(min(2, args.steps)):
+            tf, tb = staged_step()
+            t_filter += tf * args.steps / min(2, args.steps)
+            t_bp += tb * args.steps / min(2, args.steps)
         ctx.sync()
         barrier()
 
-    # ---- end-to-end steps (host -> host through the reference-shaped loop) ---------------------------------------
+    # ---- end-to-end steps: pinned host projections -> the host volume --------------------------------------------------
+    host_vol = SharedHostVolume(capi, dist, rank, world, voxels, member) if world > 1 else None
+    if world == 1:
+        member.alloc_host_slabs()
+
+    def e2e_step():
+        if world == 1:
+            # the reference-shaped per-projection loop in C++ (paris_b200/cpp/pipeline.cpp: reconstruct_task)
+            dropin.reconstruct(member.h_raw.ptr, n_proj, det, vol, member.h_slabs.ptr, dims, roi=roi, device=local_rank)
+        else:
+            member.step_e2e(host_vol.ptr)
+
     for _ in range(max(1, args.warmup)):
-        rec.step_e2e()
+        e2e_step()
     barrier()
     sampler_e2e = ClockSampler(local_rank, 500)
     sampler_e2e.start()
@@ -390,20 +515,22 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     for _ in range(args.steps):
         barrier()
         t1 = time.perf_counter()
-        rec.step_e2e()
-        ctx.sync()
+        e2e_step()
+        barrier()    # (the volume is complete when every member's slabs are in it)
         e2e_ms.append((time.perf_counter() - t1) * 1e3)
     clocks_e2e = sampler_e2e.stop()
     clocks["reasons"] = sorted(set(clocks["reasons"]) | set(clocks_e2e["reasons"]))
     clocks["e2e_phase"] = {k: clocks_e2e.get(k) for k in ("sm_mhz", "samples", "power_w_max")}
+    pushed = member.group.info().bytes_pushed
+    memops = member.group.info().memops
 
     ms_step = ms_total / args.steps
-    e2e_step = float(np.mean(e2e_ms))
+    e2e_step_ms = float(np.mean(e2e_ms))
     if dist is not None:
         import torch
-        t = torch.tensor([ms_step, e2e_step, t_filter, t_gather, t_bp], dtype=torch.float64, device="cuda")
+        t = torch.tensor([ms_step, e2e_step_ms, t_filter, t_bp, parity[0], parity[1]], dtype=torch.float64, device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        ms_step, e2e_step, t_filter, t_gather, t_bp = [float(x) for x in t.tolist()]
+        ms_step, e2e_step_ms, t_filter, t_bp, parity[0], parity[1] = [float(x) for x in t.tolist()]
 
     if rank == 0:
         peaks = measured_peaks()
@@ -413,34 +540,46 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         # backprojection: 4 point-fetched float samples per voxel update from shared memory
         bp_s = t_bp / args.steps / 1e3
         filt_s = t_filter / args.steps / 1e3
-        my_updates = plan.slab_dz * dims[0] * dims[1] * n_proj
+        my_updates = my_slices * dims[0] * dims[1] * n_proj
         bp_gbs = 16.0 * my_updates / bp_s / 1e9
         smem_peak = 148 * 128 * sm_mhz * 1e6 / 1e9
-        filt_gbs = 8.0 * px * rec.my_count / filt_s / 1e9
-        kernel_info = ctx.bp_kernel_info()
+        filt_gbs = 8.0 * px * member.my_count / filt_s / 1e9
         ncu_bp, ncu_filt = ncu_record("backprojection"), ncu_record("fused")
+        gp = gather_peak()
+        bands = [(member.plan.band_lo[k], member.plan.band_hi[k]) for k in range(world)]
         line = {
             "metric": "fdk_reconstruction_gups", "value": updates / (ms_step / 1e3) / 1e9, "unit": "GUPS",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": CONFIGS[args.config][3], "parallelism": f"z-slab x{world}",
-                       "l2": "inputs larger than L2 (raw + filtered stack >= 6 GB at c2)",
-                       "bp_batch": rec.batch,
-                       "stack_layout": "transposed, v fastest, " + ("parity-split" if rec.layout else "plain")},
+            "config": {"workload": CONFIGS[args.config][3], "parallelism": f"z-slab x{world}" + (f", {spm} slabs per GPU" if spm > 1 else ""),
+                       "l2": "inputs larger than L2 (raw + filtered stack = 48 GB at config 3)",
+                       "bp_batch": 256,
+                       "stack_layout": "transposed, v fastest, " + ("parity-split" if info.layout else "plain"),
+                       "exchange": ("none" if world == 1 else
+                                    ("whole projections" if args.whole_projections else "detector-row bands") + " into peer memory, "
+                                    + ("copy kernel" if args.exchange == "kernel" else "copy engines")
+                                    + (", stream memory operations" if memops else ", one-word kernels") + " as arrival flags")},
             "backprojection_gups": my_updates * world / bp_s / 1e9,
-            "stage_ms": {"filter": filt_s * 1e3, "allgather": t_gather / args.steps, "backproject": bp_s * 1e3,
-                         "note": "sequential stage times; at N>1 the timed step overlaps the all-gather with the backprojection"},
+            "stage_ms": {"filter": filt_s * 1e3, "backproject": bp_s * 1e3,
+                         "note": "the two kernels on one stream without overlap (at N>1 measured next to the timed region, "
+                                 "whose step overlaps upload, filter, exchange and backprojection)"},
             "roofline": {"kernel": kernel_info["last"], "bound": "smem", "achieved": bp_gbs, "peak": smem_peak,
                          "unit": "GB/s", "frac": bp_gbs / smem_peak, "traffic": ncu_traffic(ncu_bp),
                          "traffic_note": traffic_note(ncu_bp),
                          "launches_by_kernel": {"tma": kernel_info["tma_launches"], "exact": kernel_info["exact_launches"]},
-                         "measured_gather_peak": gather_peak(),
+                         "measured_gather_peak": gp,
+                         "frac_of_measured_gather_peak": (my_updates / bp_s / 1e9 / gp["gups"]["dv_c2c3_distribution"]
+                                                          if gp and args.config in ("c1", "c2", "c3") else None),
                          "pipe_busy_ncu_pct": (ncu_bp or {}).get(
                              "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed"),
+                         "issue_active_ncu_pct": (ncu_bp or {}).get("smsp__issue_active.avg.pct_of_peak_sustained_active"),
                          "pipe_busy_note": "ncu: share of cycles the L1/shared-memory data pipe is busy for this kernel "
                                            "(algorithmic bytes + bank conflicts + table broadcasts), profiles/",
                          "note": "16 B of shared-memory sample fetches per voxel update; peak = 148 SMs x 128 B/clk x "
-                                 f"{sm_mhz:.0f} MHz (SM clock sampled during the run); not an HBM- or tensor-bound kernel"},
+                                 f"{sm_mhz:.0f} MHz (SM clock sampled during the run); not an HBM- or tensor-bound kernel.  "
+                                 "measured_gather_peak: the same LDS.32 pattern alone (scripts/microbench/gather_peak.cu): "
+                                 "lanes along z advance 0.87..1.17 words per lane, every load whose 32 rows span more "
+                                 "than 32 banks costs two wavefronts"},
             "roofline_filter": {"kernel": "filter_kernel", "bound": "hbm", "achieved": filt_gbs, "peak": hbm_peak,
                                 "unit": "GB/s", "frac": filt_gbs / hbm_peak, "traffic": ncu_traffic(ncu_filt),
                                 "traffic_note": traffic_note(ncu_filt),
@@ -448,19 +587,30 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                                     "l1tex__data_pipe_lsu_wavefronts.sum.pct_of_peak_sustained_elapsed"),
                                 "note": f"8 B per detector pixel; peak {peak_src} (MEASURED_PEAKS.json hbm_gbs); ~110 flop and "
                                         "~30 shared-memory accesses per pixel keep it on the FP32/shared-memory side of the ridge"},
-            "e2e": {"value": updates / (e2e_step / 1e3) / 1e9, "unit": "GUPS", "seconds": e2e_step / 1e3,
+            "e2e": {"value": updates / (e2e_step_ms / 1e3) / 1e9, "unit": "GUPS", "seconds": e2e_step_ms / 1e3,
                     "h2d_bytes_per_step": 4 * px * n_proj, "d2h_bytes_per_step": 4 * voxels,
                     "ms_steps": [round(x, 2) for x in e2e_ms],
                     "path": ("paris_b200_dropin_reconstruct: per-projection load/weight/filter/backproject + copy_d2h"
                              if world == 1 else
-                             "per rank: proj_h2d + filter_to_stack per projection, NCCL all-gather, backproject_stack, vol_d2h")},
+                             "paris_b200_group_reconstruct per rank: upload + filter of 1/N of the projections round by round, "
+                             "exchange over peer memory, backprojection of all projections into the rank's slabs, download"),
+                    "host_volume": ("one pinned buffer" if world == 1 else host_vol.kind)},
             "gpu_launches": int(launches), "clocks": clocks,
             "wall_s_resident": wall_resident,
         }
+        if world > 1:
+            group_steps = args.warmup + args.steps + max(1, args.warmup) + args.steps
+            line["exchange"] = {"bytes_pushed_per_step_rank0": int(pushed // group_steps),
+                                "all_gather_bytes_per_step_rank0": int((world - 1) * member.my_count * px * 4),
+                                "band_rows_per_rank": [hi - lo for lo, hi in bands], "detector_rows": int(det.n_col)}
+            line["parity_check"] = {"max": parity[0], "rmse": parity[1], "ok": bool(parity[0] <= 1e-4 and parity[1] <= 1e-5),
+                                    "what": "every rank: three 4-slice bands of its slab (first, middle, last slices) after "
+                                            "the timed steps against the exact kernel on the rank's own gathered stack; "
+                                            "max over ranks, in units of the phantom contrast"}
         if world == 1 and not args.no_cpu_baseline:
             try:
                 g_total, g_bp, cores, kind, desc, _ = cpu_reconstruct_sample(args.config, budget_s=args.cpu_budget,
-                                                                           fetch=rec.host_sample)
+                                                                           fetch=member.host_sample)
                 line["cpu_baseline"] = {"value": g_total, "unit": "GUPS", "cores": cores, "kind": kind, "sample": desc,
                                         "backprojection_only_gups": g_bp}
             except Exception as e:  # the CPU checker must never take the GPU number down with it
@@ -468,7 +618,14 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                                         "sample": repr(e)}
         print(json.dumps(line), flush=True)
 
-    rec.close()
+    ctx.filter_destroy(filt)
+    if info.slabs != 1:
+        ctx.volume_free(stage_vol)
+    if dist is not None:
+        dist.barrier()        # nobody tears its stack down while a peer may still push into it
+    if host_vol is not None:
+        host_vol.close(rank)
+    member.close()
     if dist is not None:
         dist.barrier()
         dist.destroy_process_group()
@@ -484,6 +641,9 @@ def main():
     ap.add_argument("--cpu-budget", type=float, default=12.0, help="seconds of CPU work per reference sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--clock-interval-ms", type=int, default=100, help="NVML sampling period")
+    ap.add_argument("--slabs-per-gpu", type=int, default=0, help="z-slabs every GPU streams (0: 2 for config 5, else 1)")
+    ap.add_argument("--exchange", default="copy-engine", choices=["copy-engine", "kernel"])
+    ap.add_argument("--whole-projections", action="store_true", help="exchange every detector row (an all-gather)")
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

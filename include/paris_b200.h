@@ -140,6 +140,10 @@ int paris_b200_make_subvolume_information(paris_b200_ctx* ctx, const paris_b200_
 /* pinned host memory (make_projection_host / make_volume_host); zero == nonzero clears it */
 int paris_b200_host_alloc(size_t bytes, int zero, void** h_ptr);
 int paris_b200_host_free(void* h_ptr);
+/* page-lock / release host memory the caller owns (e.g. a shared-memory mapping that several member processes of a
+ * group download their slabs into, so that the host volume is assembled by the downloads themselves) */
+int paris_b200_host_register(void* h_ptr, size_t bytes);
+int paris_b200_host_unregister(void* h_ptr);
 /* stream-ordered device memory (make_projection_device); freeing is ordered after queued work */
 int paris_b200_dev_alloc(paris_b200_ctx* ctx, size_t bytes, void** d_ptr);
 int paris_b200_dev_free(paris_b200_ctx* ctx, void* d_ptr);
@@ -262,6 +266,107 @@ int paris_b200_backproject_stack_d2h(paris_b200_ctx* ctx, const float* d_stack, 
                                      uint32_t v_offset, const paris_b200_detector_geometry* det,
                                      const paris_b200_volume_geometry* vol_full, int enable_roi,
                                      const paris_b200_roi* roi, uint32_t layout, float* h_dst);
+
+/* ---- one scan across the GPUs of a box (csrc/group.cu) ------------------------------------------
+ *
+ * The reference's multi-device scheme is task parallelism: every device re-reads and re-filters every projection for
+ * each slab it owns and nothing is exchanged (src/main.cpp:93-105; slabs src/cuda/subvolume_information.cpp:112-116,
+ * src/make_volume.cpp:32-34, offset src/main.cpp:96).  A GROUP replaces that loop: `world` members, one per GPU --
+ * one process each, or several host threads of one process like the reference's std::async per device
+ * (src/main.cpp:157-169).  Member r uploads and filters 1/world of the projections; after every round of projections
+ * each member copies its filtered share straight into its peers' stacks over NVLink (peer memory, copy engines, only
+ * the band of detector rows a peer's slabs can read) and announces it with a flag word the peer's stream waits on;
+ * every member backprojects all projections into its own z-slabs -- slabs_per_member of them, looping over the one
+ * gathered stack, each downloaded behind the next one's backprojection.  No reduction, no host synchronisation inside
+ * a step; the host volume is assembled by writing every slab at its z offset.
+ *
+ *   create (every member)  ->  export (64..128-byte handle)  ->  [the host side hands every member all handles]  ->
+ *   connect  ->  reconstruct / begin + end, any number of times  ->  destroy
+ */
+#define PARIS_B200_SAMPLES_F32 0u
+#define PARIS_B200_EXCHANGE_COPY_ENGINE 0u   /* cudaMemcpy2DAsync into peer memory on a stream of its own (default) */
+#define PARIS_B200_EXCHANGE_KERNEL 1u        /* a small copy kernel on a high-priority stream */
+#define PARIS_B200_GROUP_HANDLE_BYTES 256
+
+typedef struct paris_b200_group paris_b200_group;
+
+typedef struct paris_b200_group_config
+{
+    int32_t rank, world;
+    paris_b200_detector_geometry det;
+    paris_b200_volume_geometry vol_full;  /* the FULL volume geometry */
+    int32_t enable_roi;                   /* the reconstructed region: the ROI box if set, else the full volume */
+    paris_b200_roi roi;
+    uint32_t n_proj;                      /* projections of the scan; projection i is slot i of every member's stack */
+    const float* angles_deg;              /* n_proj angles, or NULL: angle i = float(i) * det.delta_phi (src/backprojection.cpp:53-57) */
+    uint32_t slabs_per_member;            /* >= 1: the region is cut into world * slabs_per_member equal z-slabs (remainder on
+                                             the last), member r owns slabs [r * spm, (r + 1) * spm) */
+    uint32_t stream_slabs;                /* 1: at most two slab buffers on the device, slabs go to the host one by one (a host
+                                             destination is then required); 0: every slab stays resident */
+    uint32_t sample_type;                 /* PARIS_B200_SAMPLES_F32 */
+    uint32_t first_round, max_round;      /* projections per exchanged round: first one, upper bound (0 = 64 / 256) */
+    uint32_t whole_projections;           /* 1: exchange every detector row (an all-gather); 0: only the band of rows the
+                                             receiving member's slabs can read */
+    uint32_t exchange;                    /* PARIS_B200_EXCHANGE_* */
+} paris_b200_group_config;
+
+typedef struct paris_b200_group_info_t
+{
+    uint32_t my_projections;              /* how many projections this member uploads and filters */
+    uint32_t rounds, slabs;
+    uint32_t z_first, z_count;            /* this member's slices of the region */
+    uint32_t region_x, region_y, region_z;
+    uint32_t band_lo, band_hi;            /* detector rows [lo, hi) this member receives from its peers */
+    uint32_t layout, pitch;               /* stack layout (PARIS_B200_LAYOUT_*) and line pitch in floats */
+    float* d_stack;                       /* the member's filtered stack: n_proj slots (rows outside the band are only
+                                             valid for the member's own projections) */
+    uint32_t slab_buffers;                /* device slab buffers (== slabs unless stream_slabs) */
+    float* d_first_slab;                  /* device buffer of the member's first slab */
+    uint64_t bytes_pushed;                /* bytes this member has copied into peer memory since create */
+    paris_b200_ctx* ctx;                  /* the context whose compute stream runs the backprojection (events, options) */
+    paris_b200_ctx* filter_ctx;           /* the context that uploads and filters */
+    uint32_t memops;                      /* 1: arrival flags are written by stream memory operations, 0: by one-word kernels */
+} paris_b200_group_info_t;
+
+/* The decomposition a configuration leads to -- who filters what, who owns which slices, which detector rows travel
+ * to whom.  Pure host arithmetic: no device is touched (checked on CPU-only machines, tests/test_multi_cpu.py). */
+#define PARIS_B200_GROUP_MAX_MEMBERS 64
+#define PARIS_B200_GROUP_MAX_ROUNDS 256
+typedef struct paris_b200_group_plan_t
+{
+    uint32_t region_x, region_y, region_z;   /* the reconstructed region */
+    uint32_t region_z0;                       /* its first slice in the full volume */
+    uint32_t layout, pitch;                   /* stack layout and line pitch (floats) */
+    uint32_t slabs_total, slab_dz, slab_remainder;   /* world * slabs_per_member slabs of slab_dz slices, remainder on the last */
+    uint32_t rounds;
+    uint32_t round_first[PARIS_B200_GROUP_MAX_ROUNDS], round_count[PARIS_B200_GROUP_MAX_ROUNDS];
+    uint32_t band_lo[PARIS_B200_GROUP_MAX_MEMBERS], band_hi[PARIS_B200_GROUP_MAX_MEMBERS];   /* rows [lo, hi) member k receives */
+} paris_b200_group_plan_t;
+int paris_b200_group_plan(const paris_b200_group_config* cfg, paris_b200_group_plan_t* plan);
+/* member `member`'s share of round `round`: projections [first, first + count) of the scan */
+int paris_b200_group_share(const paris_b200_group_plan_t* plan, uint32_t world, uint32_t round, uint32_t member,
+                           uint32_t* first, uint32_t* count);
+
+size_t paris_b200_group_handle_bytes(void);
+int paris_b200_group_create(int device, const paris_b200_group_config* cfg, paris_b200_group** group);
+int paris_b200_group_destroy(paris_b200_group* group);
+/* what a peer needs to reach this member's stack and flags (handle_bytes >= PARIS_B200_GROUP_HANDLE_BYTES) */
+int paris_b200_group_export(paris_b200_group* group, unsigned char* handle, size_t handle_bytes);
+/* handles: world blobs of handle_bytes each, blob k = member k's export.  Members of the same process are reached through
+ * their pointers (peer access is enabled), members of other processes through CUDA IPC. */
+int paris_b200_group_connect(paris_b200_group* group, const unsigned char* handles, size_t handle_bytes);
+int paris_b200_group_info(const paris_b200_group* group, paris_b200_group_info_t* info);
+/* scan index of this member's local projection `local` (0 <= local < my_projections): the order in which its raw
+ * projections are handed to group_begin */
+int paris_b200_group_projection_index(const paris_b200_group* group, uint32_t local, uint32_t* index);
+/* One reconstruction.  Exactly one of h_raw / d_raw: h_raw[j] = (pinned) host address of this member's local raw
+ * projection j (n_col x n_row floats), uploaded inside the step; d_raw = the same projections already on the device,
+ * contiguous in local order.  h_slabs: where this member's first slab goes on the host (z_count slices of region_x x
+ * region_y floats, pinned), or NULL to leave the slabs on the device.  begin() only enqueues -- members that share a
+ * host thread begin one after the other and then end; end() returns when this member's slabs are complete. */
+int paris_b200_group_begin(paris_b200_group* group, const float* const* h_raw, const float* d_raw, float* h_slabs);
+int paris_b200_group_end(paris_b200_group* group);
+int paris_b200_group_reconstruct(paris_b200_group* group, const float* const* h_raw, const float* d_raw, float* h_slabs);
 
 /* ---- synthetic input (bench / tests): analytic cone-beam line integrals of ellipsoids ------ */
 

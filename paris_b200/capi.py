@@ -11,6 +11,11 @@ import os
 
 import numpy as np
 
+# One hardware queue per stream (the default is 8): a group member keeps five streams busy next to whatever the host
+# program runs, and a stream blocked on a peer's arrival flag must never hold back another stream that shares its queue.
+# Read by the driver when the process creates its first CUDA context, hence set at import.
+os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PARIS_B200_LIB") or os.path.join(_HERE, "libparis_b200.so")   # (override: kernel A/B experiments)
 
@@ -38,6 +43,35 @@ class Roi(C.Structure):
 class SubvolumeInfo(C.Structure):
     _fields_ = [("dim_x", C.c_uint32), ("dim_y", C.c_uint32), ("dim_z", C.c_uint32),
                 ("remainder", C.c_uint32), ("num", C.c_int32)]
+
+
+GROUP_HANDLE_BYTES, GROUP_MAX_MEMBERS, GROUP_MAX_ROUNDS = 256, 64, 256
+SAMPLES_F32 = 0
+EXCHANGE_COPY_ENGINE, EXCHANGE_KERNEL = 0, 1
+
+
+class GroupConfig(C.Structure):
+    _fields_ = [("rank", C.c_int32), ("world", C.c_int32), ("det", DetectorGeometry), ("vol_full", VolumeGeometry),
+                ("enable_roi", C.c_int32), ("roi", Roi), ("n_proj", C.c_uint32), ("angles_deg", C.POINTER(C.c_float)),
+                ("slabs_per_member", C.c_uint32), ("stream_slabs", C.c_uint32), ("sample_type", C.c_uint32),
+                ("first_round", C.c_uint32), ("max_round", C.c_uint32), ("whole_projections", C.c_uint32),
+                ("exchange", C.c_uint32)]
+
+
+class GroupPlan(C.Structure):
+    _fields_ = [("region_x", C.c_uint32), ("region_y", C.c_uint32), ("region_z", C.c_uint32), ("region_z0", C.c_uint32),
+                ("layout", C.c_uint32), ("pitch", C.c_uint32), ("slabs_total", C.c_uint32), ("slab_dz", C.c_uint32),
+                ("slab_remainder", C.c_uint32), ("rounds", C.c_uint32),
+                ("round_first", C.c_uint32 * GROUP_MAX_ROUNDS), ("round_count", C.c_uint32 * GROUP_MAX_ROUNDS),
+                ("band_lo", C.c_uint32 * GROUP_MAX_MEMBERS), ("band_hi", C.c_uint32 * GROUP_MAX_MEMBERS)]
+
+
+class GroupInfo(C.Structure):
+    _fields_ = [("my_projections", C.c_uint32), ("rounds", C.c_uint32), ("slabs", C.c_uint32), ("z_first", C.c_uint32),
+                ("z_count", C.c_uint32), ("region_x", C.c_uint32), ("region_y", C.c_uint32), ("region_z", C.c_uint32),
+                ("band_lo", C.c_uint32), ("band_hi", C.c_uint32), ("layout", C.c_uint32), ("pitch", C.c_uint32),
+                ("d_stack", C.c_void_p), ("slab_buffers", C.c_uint32), ("d_first_slab", C.c_void_p),
+                ("bytes_pushed", C.c_uint64), ("ctx", C.c_void_p), ("filter_ctx", C.c_void_p), ("memops", C.c_uint32)]
 
 
 class Error(RuntimeError):
@@ -78,6 +112,8 @@ SIGNATURES = {
                                                         _P(SubvolumeInfo)]),
     "paris_b200_host_alloc": (C.c_int, [C.c_size_t, C.c_int, _P(_vp)]),
     "paris_b200_host_free": (C.c_int, [_vp]),
+    "paris_b200_host_register": (C.c_int, [_vp, C.c_size_t]),
+    "paris_b200_host_unregister": (C.c_int, [_vp]),
     "paris_b200_dev_alloc": (C.c_int, [_vp, C.c_size_t, _P(_vp)]),
     "paris_b200_dev_free": (C.c_int, [_vp, _vp]),
     "paris_b200_volume_alloc": (C.c_int, [_vp, _u32, _u32, _u32, _P(_vp)]),
@@ -110,6 +146,18 @@ SIGNATURES = {
     "paris_b200_backproject_stack_d2h": (C.c_int, [_vp, _fp, _u32, _u32, _P(_f), _P(_f), _fp, _u32, _u32, _u32, _u32,
                                                    _P(DetectorGeometry), _P(VolumeGeometry), C.c_int, _P(Roi), _u32,
                                                    _fp]),
+    "paris_b200_group_plan": (C.c_int, [_P(GroupConfig), _P(GroupPlan)]),
+    "paris_b200_group_share": (C.c_int, [_P(GroupPlan), _u32, _u32, _u32, _P(_u32), _P(_u32)]),
+    "paris_b200_group_handle_bytes": (C.c_size_t, []),
+    "paris_b200_group_create": (C.c_int, [C.c_int, _P(GroupConfig), _P(_vp)]),
+    "paris_b200_group_destroy": (C.c_int, [_vp]),
+    "paris_b200_group_export": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
+    "paris_b200_group_connect": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
+    "paris_b200_group_info": (C.c_int, [_vp, _P(GroupInfo)]),
+    "paris_b200_group_projection_index": (C.c_int, [_vp, _u32, _P(_u32)]),
+    "paris_b200_group_begin": (C.c_int, [_vp, _P(_vp), _vp, _vp]),
+    "paris_b200_group_end": (C.c_int, [_vp]),
+    "paris_b200_group_reconstruct": (C.c_int, [_vp, _P(_vp), _vp, _vp]),
     "paris_b200_phantom_project": (C.c_int, [_vp, _P(C.c_double), _u32, _P(DetectorGeometry), _u32, _u32, _fp]),
 }
 
@@ -395,3 +443,95 @@ class Context:
         e = np.ascontiguousarray(ellipsoids_mm, dtype=np.float64)
         check(self._L.paris_b200_phantom_project(self.h, e.ctypes.data_as(_P(C.c_double)), e.shape[0], C.byref(det),
                                                  first_idx, n_proj, d_stack_raw))
+
+
+# ---- one scan across the GPUs of a box (csrc/group.cu) -----------------------------------------------------------
+
+def group_config(rank: int, world: int, det: DetectorGeometry, vol_full: VolumeGeometry, n_proj: int, roi: Roi | None = None,
+                 slabs_per_member: int = 1, stream_slabs: bool = False, first_round: int = 0, max_round: int = 0,
+                 whole_projections: bool = False, exchange: int = EXCHANGE_COPY_ENGINE, angles_deg=None) -> GroupConfig:
+    cfg = GroupConfig()
+    cfg.rank, cfg.world, cfg.det, cfg.vol_full, cfg.n_proj = rank, world, det, vol_full, n_proj
+    cfg.enable_roi = int(roi is not None)
+    if roi is not None:
+        cfg.roi = roi
+    cfg.slabs_per_member, cfg.stream_slabs, cfg.sample_type = slabs_per_member, int(stream_slabs), SAMPLES_F32
+    cfg.first_round, cfg.max_round = first_round, max_round
+    cfg.whole_projections, cfg.exchange = int(whole_projections), exchange
+    if angles_deg is not None:
+        a = np.ascontiguousarray(angles_deg, dtype=np.float32)
+        assert a.size == n_proj
+        cfg._angles = a                     # (keeps the array alive as long as the struct)
+        cfg.angles_deg = a.ctypes.data_as(C.POINTER(C.c_float))
+    return cfg
+
+
+def group_plan(cfg: GroupConfig) -> GroupPlan:
+    """Rounds, slabs and bands of a configuration: host arithmetic only, works without a GPU."""
+    plan = GroupPlan()
+    check(lib().paris_b200_group_plan(C.byref(cfg), C.byref(plan)))
+    return plan
+
+
+def group_share(plan: GroupPlan, world: int, rnd: int, member: int):
+    first, count = _u32(0), _u32(0)
+    check(lib().paris_b200_group_share(C.byref(plan), world, rnd, member, C.byref(first), C.byref(count)))
+    return first.value, count.value
+
+
+class Group:
+    """One member of a reconstruction group (paris_b200_group_*)."""
+
+    def __init__(self, device: int, cfg: GroupConfig):
+        self._L = lib()
+        self.cfg = cfg
+        h = _vp()
+        check(self._L.paris_b200_group_create(device, C.byref(cfg), C.byref(h)))
+        self.h = h
+        self.device = device
+
+    def export(self) -> bytes:
+        buf = C.create_string_buffer(GROUP_HANDLE_BYTES)
+        check(self._L.paris_b200_group_export(self.h, buf, GROUP_HANDLE_BYTES))
+        return buf.raw
+
+    def connect(self, handles):
+        """handles: one export per member, in rank order"""
+        blob = b"".join(handles)
+        assert len(blob) == GROUP_HANDLE_BYTES * self.cfg.world
+        check(self._L.paris_b200_group_connect(self.h, blob, GROUP_HANDLE_BYTES))
+
+    def info(self) -> GroupInfo:
+        out = GroupInfo()
+        check(self._L.paris_b200_group_info(self.h, C.byref(out)))
+        return out
+
+    def projection_index(self, local: int) -> int:
+        out = _u32(0)
+        check(self._L.paris_b200_group_projection_index(self.h, local, C.byref(out)))
+        return out.value
+
+    def _args(self, h_raw, d_raw, h_slabs):
+        ptrs = None
+        if h_raw is not None:
+            ptrs = (_vp * len(h_raw))(*[int(p) for p in h_raw])
+        return ptrs, (None if d_raw is None else int(d_raw)), (None if h_slabs is None else int(h_slabs))
+
+    def begin(self, h_raw=None, d_raw=None, h_slabs=None):
+        """h_raw: host addresses of this member's raw projections in local order (pinned), or d_raw: device address
+        of the same, contiguous; h_slabs: host address for the member's slabs (pinned) or None."""
+        ptrs, d, h = self._args(h_raw, d_raw, h_slabs)
+        self._keep = ptrs
+        check(self._L.paris_b200_group_begin(self.h, ptrs, d, h))
+
+    def end(self):
+        check(self._L.paris_b200_group_end(self.h))
+
+    def reconstruct(self, h_raw=None, d_raw=None, h_slabs=None):
+        self.begin(h_raw, d_raw, h_slabs)
+        self.end()
+
+    def close(self):
+        if self.h:
+            check(self._L.paris_b200_group_destroy(self.h))
+            self.h = None

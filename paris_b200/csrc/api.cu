@@ -372,6 +372,22 @@ extern "C" int paris_b200_host_alloc(size_t bytes, int zero, void** h_ptr)
     return PARIS_B200_OK;
 }
 
+// page-lock memory the caller owns (e.g. a POSIX shared-memory mapping several member processes write their slabs
+// into: the host volume is then assembled by the downloads themselves)
+extern "C" int paris_b200_host_register(void* h_ptr, size_t bytes)
+{
+    PB_CHECK_ARG(h_ptr != nullptr && bytes > 0);
+    PB_CUDA(cudaHostRegister(h_ptr, bytes, cudaHostRegisterPortable));
+    return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_host_unregister(void* h_ptr)
+{
+    if(h_ptr != nullptr)
+        PB_CUDA(cudaHostUnregister(h_ptr));
+    return PARIS_B200_OK;
+}
+
 extern "C" int paris_b200_host_free(void* h_ptr)
 {
     if(h_ptr != nullptr)
@@ -673,9 +689,11 @@ static int run_pending_filter(paris_b200_ctx* ctx);
 // download of chunk c (copy stream) runs behind the backprojection of chunk c+1 (compute stream).  Chunks end
 // at multiples of 64 slices in GLOBAL slice indices -- the kernel's tile anchors -- so no tile is computed twice
 // and the result is bit-identical to the one-piece launch.  Returns with the host copy complete.
-static int backproject_and_download(paris_b200_ctx* ctx, const float* d_stack, size_t slot_floats, uint32_t pitch,
-                                    uint32_t first, uint32_t count, const float* sn, const float* cs, const bp_target& t,
-                                    uint32_t layout, float* h_dst)
+// wait == false: returns with the last chunk's copy still in flight on the copy stream (group.cu overlaps it with the
+// next slab's backprojection).
+int pb::backproject_and_download(paris_b200_ctx* ctx, const float* d_stack, size_t slot_floats, uint32_t pitch,
+                                 uint32_t first, uint32_t count, const float* sn, const float* cs, const bp_target& t,
+                                 uint32_t layout, float* h_dst, bool wait)
 {
     const uint32_t off0 = (t.enable_roi ? t.roi.z1 : 0u) + t.v_offset;
     const size_t slice = static_cast<size_t>(t.v_dim_x) * t.v_dim_y;
@@ -703,7 +721,8 @@ static int backproject_and_download(paris_b200_ctx* ctx, const float* d_stack, s
                                 cudaMemcpyDeviceToHost, ctx->copy));
         z = end;
     }
-    PB_CUDA(cudaStreamSynchronize(ctx->copy));
+    if(wait)
+        PB_CUDA(cudaStreamSynchronize(ctx->copy));
     return PARIS_B200_OK;
 }
 
@@ -722,7 +741,7 @@ extern "C" int paris_b200_vol_d2h(paris_b200_ctx* ctx, const float* d_src, float
         const uint32_t n = static_cast<uint32_t>(ctx->pending);
         ctx->pending = 0;
         return backproject_and_download(ctx, ctx->stack, ctx->stack_slot_floats, ctx->stack_pitch, 0u, n, ctx->pend_sin,
-                                        ctx->pend_cos, t, ctx->stack_layout, h_dst);
+                                        ctx->pend_cos, t, ctx->stack_layout, h_dst, true);
     }
     PB_TRY(paris_b200_flush(ctx));
     PB_CUDA(cudaMemcpyAsync(h_dst, d_src, n_voxels * sizeof(float), cudaMemcpyDeviceToHost, ctx->compute));
@@ -1265,7 +1284,7 @@ extern "C" int paris_b200_backproject_stack_d2h(paris_b200_ctx* ctx, const float
     t.delta_t_mm = det->delta_t * det->l_px_col;
     const uint32_t pitch = stack_pitch_for(det->n_col);
     const size_t slot_floats = static_cast<size_t>(pitch) * det->n_row;
-    return backproject_and_download(ctx, d_stack, slot_floats, pitch, first, count, sin_phi, cos_phi, t, layout, h_dst);
+    return backproject_and_download(ctx, d_stack, slot_floats, pitch, first, count, sin_phi, cos_phi, t, layout, h_dst, true);
 }
 
 extern "C" int paris_b200_phantom_project(paris_b200_ctx* ctx, const double* ellipsoids, uint32_t n_ellipsoids,

@@ -206,4 +206,9 @@ namespace pb
                        uint32_t first_idx, uint32_t n_proj, float* d_out);
 
     inline uint32_t stack_pitch_for(uint32_t n_col) { return (n_col + 31u) & ~31u; }
+
+    // Backproject `count` stack slots into the target and bring the volume to the host, z-chunk by z-chunk (api.cu)
+    int backproject_and_download(paris_b200_ctx* ctx, const float* d_stack, size_t slot_floats, uint32_t pitch, uint32_t first,
+                                 uint32_t count, const float* sn, const float* cs, const bp_target& t, uint32_t layout,
+                                 float* h_dst, bool wait);
 }
