@@ -366,6 +366,10 @@ int paris_b200_group_projection_index(const paris_b200_group* group, uint32_t lo
  * host thread begin one after the other and then end; end() returns when this member's slabs are complete. */
 int paris_b200_group_begin(paris_b200_group* group, const float* const* h_raw, const float* d_raw, float* h_slabs);
 int paris_b200_group_end(paris_b200_group* group);
+/* diagnostics: out[0..4] = 1 while the member's backprojection / download / filter / upload / exchange stream still
+ * has work; out[5 .. 5 + world) = arrival flags (last round each member delivered), the next `world` words = how
+ * many steps each member has consumed.  n >= 5 + 2 * world.  Touches none of those streams. */
+int paris_b200_group_debug_state(paris_b200_group* group, uint32_t* out, uint32_t n);
 int paris_b200_group_reconstruct(paris_b200_group* group, const float* const* h_raw, const float* d_raw, float* h_slabs);
 
 /* ---- synthetic input (bench / tests): analytic cone-beam line integrals of ellipsoids ------ */

@@ -15,6 +15,10 @@ import numpy as np
 # program runs, and a stream blocked on a peer's arrival flag must never hold back another stream that shares its queue.
 # Read by the driver when the process creates its first CUDA context, hence set at import.
 os.environ.setdefault("CUDA_DEVICE_MAX_CONNECTIONS", "32")
+# Kernels are loaded with their module, not lazily at first launch: a lazy load synchronises the context, which never
+# returns inside a group step (streams waiting for flags that work not yet enqueued will set).  The library sets both
+# defaults itself when it is loaded; here as well because torch may initialise CUDA before that.
+os.environ.setdefault("CUDA_MODULE_LOADING", "EAGER")
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.environ.get("PARIS_B200_LIB") or os.path.join(_HERE, "libparis_b200.so")   # (override: kernel A/B experiments)
@@ -158,6 +162,7 @@ SIGNATURES = {
     "paris_b200_group_begin": (C.c_int, [_vp, _P(_vp), _vp, _vp]),
     "paris_b200_group_end": (C.c_int, [_vp]),
     "paris_b200_group_reconstruct": (C.c_int, [_vp, _P(_vp), _vp, _vp]),
+    "paris_b200_group_debug_state": (C.c_int, [_vp, _P(_u32), _u32]),
     "paris_b200_phantom_project": (C.c_int, [_vp, _P(C.c_double), _u32, _P(DetectorGeometry), _u32, _u32, _fp]),
 }
 
@@ -530,6 +535,14 @@ class Group:
     def reconstruct(self, h_raw=None, d_raw=None, h_slabs=None):
         self.begin(h_raw, d_raw, h_slabs)
         self.end()
+
+    def debug_state(self) -> dict:
+        n = 5 + 2 * self.cfg.world
+        out = (_u32 * n)()
+        check(self._L.paris_b200_group_debug_state(self.h, out, n))
+        v = list(out)
+        return {"busy": dict(zip(("backprojection", "download", "filter", "upload", "exchange"), v[:5])),
+                "arrived": v[5:5 + self.cfg.world], "consumed": v[5 + self.cfg.world:]}
 
     def close(self):
         if self.h:

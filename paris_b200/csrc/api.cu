@@ -4,7 +4,22 @@
 
 #include <cmath>
 #include <cstdarg>
+#include <cstdlib>
 #include <complex>
+
+namespace
+{
+    // Runs when the library is loaded, before it makes its first CUDA call: kernels are loaded with their module instead of
+    // lazily at their first launch (a lazy load synchronises the context, see common.cuh), and every stream gets a
+    // hardware queue of its own (the default of 8 makes unrelated streams wait for each other).  Both are defaults only:
+    // whoever set the variables keeps their values, and a process that initialised CUDA earlier is not affected --
+    // group_create loads its kernels explicitly for that case.
+    __attribute__((constructor)) void paris_b200_library_defaults()
+    {
+        setenv("CUDA_MODULE_LOADING", "EAGER", 0);
+        setenv("CUDA_DEVICE_MAX_CONNECTIONS", "32", 0);
+    }
+}
 
 namespace pb
 {

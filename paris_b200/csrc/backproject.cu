@@ -161,6 +161,16 @@ namespace pb
         return PARIS_B200_OK;
     }
 
+    void preload_bp_tma_kernels();
+
+    void preload_backprojection_kernels()
+    {
+        cudaFuncAttributes a{};
+        (void)cudaFuncGetAttributes(&a, bp_exact_kernel);
+        preload_bp_tma_kernels();
+        (void)cudaGetLastError();
+    }
+
     int launch_backproject(paris_b200_ctx* ctx, const float* d_stack, size_t slot_floats, uint32_t pitch,
                            uint32_t first, uint32_t count, const float* sn, const float* cs, const bp_target& t,
                            uint32_t layout)

@@ -904,6 +904,28 @@ namespace pb
     }
 #endif
 
+    // Load every instantiation now (CUDA loads kernels lazily, on first launch, and that load synchronises the
+    // context: inside a group step, where streams wait for flags other work has yet to set, it deadlocks).
+    template <class CFG>
+    static void preload_cfg()
+    {
+        cudaFuncAttributes a{};
+        (void)cudaFuncGetAttributes(&a, bp_tma_kernel<CFG, false>);
+        (void)cudaFuncGetAttributes(&a, bp_tma_kernel<CFG, true>);
+    }
+
+    void preload_bp_tma_kernels()
+    {
+        preload_cfg<cfg_fine>();
+        preload_cfg<cfg_coarse>();
+        preload_cfg<cfg_coarse_split>();
+        preload_cfg<cfg_fine_half>();
+        preload_cfg<cfg_coarse_split_half>();
+        preload_cfg<cfg_fine_tall>();
+        preload_cfg<cfg_coarse_split_tall>();
+        (void)cudaGetLastError();
+    }
+
     int launch_bp_tma(paris_b200_ctx* ctx, const float* d_stack, size_t slot_floats, uint32_t first,
                       const bp_geometry& g, const bp_angles& a, float* d_vol, bool required, bool* handled)
     {

@@ -205,6 +205,13 @@ namespace pb
     int launch_phantom(paris_b200_ctx* ctx, const double* h_ellipsoids, uint32_t n, const paris_b200_detector_geometry* det,
                        uint32_t first_idx, uint32_t n_proj, float* d_out);
 
+    // CUDA loads kernels lazily, on their first launch, and that load synchronises the context.  Inside a group step
+    // -- streams waiting for flags that other, not yet enqueued work sets -- such a load never returns (measured: a
+    // slab shape that needed a not yet used tile instantiation hung the whole group).  Everything a step can launch
+    // is therefore loaded before the first step.
+    void preload_backprojection_kernels();
+    void preload_filter_kernels(uint32_t size);
+
     inline uint32_t stack_pitch_for(uint32_t n_col) { return (n_col + 31u) & ~31u; }
 
     // Backproject `count` stack slots into the target and bring the volume to the host, z-chunk by z-chunk (api.cu)

@@ -552,6 +552,30 @@ namespace pb
         return PARIS_B200_OK;
     }
 
+    template <int LOG2N>
+    static void preload_grouped()
+    {
+        cudaFuncAttributes a{};
+        (void)cudaFuncGetAttributes(&a, filter_kernel<LOG2N, true>);
+        (void)cudaFuncGetAttributes(&a, filter_kernel<LOG2N, false>);
+    }
+
+    // the transposed-output kernel of this filter size (what a group step launches), loaded before the step
+    void preload_filter_kernels(uint32_t size)
+    {
+        switch(size)
+        {
+            case 256: preload_grouped<8>(); break;
+            case 512: preload_grouped<9>(); break;
+            case 1024: preload_grouped<10>(); break;
+            case 2048: preload_grouped<11>(); break;
+            case 4096: preload_grouped<12>(); break;
+            case 8192: preload_grouped<13>(); break;
+            default: preload_filter_small_kernels(size); break;
+        }
+        (void)cudaGetLastError();
+    }
+
     // `count` projections in one launch.  Transposed: src[i] -> slot first_slot + i of d_stack.
     // Row-major: src[i] -> dst[i] (may alias).
     int launch_filter_batch(paris_b200_ctx* ctx, const float* const* d_src, float* const* d_dst, uint32_t count,

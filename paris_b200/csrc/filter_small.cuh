@@ -248,4 +248,16 @@ namespace pb
         ++ctx->launches;
         return PARIS_B200_OK;
     }
+
+    inline void preload_filter_small_kernels(uint32_t size)
+    {
+        cudaFuncAttributes a{};
+        switch(size)
+        {
+            case 32: (void)cudaFuncGetAttributes(&a, filter_small_kernel<5, true>); (void)cudaFuncGetAttributes(&a, filter_small_kernel<5, false>); break;
+            case 64: (void)cudaFuncGetAttributes(&a, filter_small_kernel<6, true>); (void)cudaFuncGetAttributes(&a, filter_small_kernel<6, false>); break;
+            case 128: (void)cudaFuncGetAttributes(&a, filter_small_kernel<7, true>); (void)cudaFuncGetAttributes(&a, filter_small_kernel<7, false>); break;
+            default: break;
+        }
+    }
 }

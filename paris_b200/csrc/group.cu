@@ -28,6 +28,7 @@
 
 #include <algorithm>
 #include <cmath>
+#include <cstdlib>
 
 namespace pb
 {
@@ -65,6 +66,7 @@ namespace pb
     };
     static_assert(sizeof(group_handle) <= PARIS_B200_GROUP_HANDLE_BYTES, "handle blob too small");
     constexpr uint32_t kHandleMagic = 0x50423247u;  // "PB2G"
+    constexpr uint32_t kErrorWord = 1024u;          // flags[kErrorWord]: 0, or 1 + the member a wait gave up on
 
     using stream_value32_fn = CUresult (*)(CUstream, CUdeviceptr, cuuint32_t, unsigned int);
 
@@ -82,6 +84,33 @@ namespace pb
     {
         __threadfence_system();
         *reinterpret_cast<volatile uint32_t*>(flag) = value;
+        __threadfence_system();
+    }
+
+    // The consumer's side of an arrival flag: ONE thread polls the word (flags only grow: cyclic comparison) and the
+    // stream continues when it has reached `value`.  A kernel rather than a stream memory operation for the wait: a
+    // cuStreamWaitValue32 blocks the hardware queue its stream is mapped to, and whatever other stream shares that
+    // queue -- the exchange stream whose signal a peer is waiting for, say -- stalls behind it (measured: members
+    // that share one GPU deadlocked that way).  A polling thread holds nothing but one warp slot.  It also cannot
+    // wait for ever: after `timeout_ns` it records the failure in *error and lets the stream go on, so a member that
+    // died takes the step down with an error instead of hanging the GPU.
+    __global__ void wait_flag_kernel(const uint32_t* flag, uint32_t value, unsigned long long timeout_ns, uint32_t* error,
+                                     uint32_t code)
+    {
+        const volatile uint32_t* f = flag;
+        unsigned long long t0 = 0;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t0));
+        while(static_cast<int32_t>(*f - value) < 0)
+        {
+            __nanosleep(256);
+            unsigned long long t = 0;
+            asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+            if(t - t0 > timeout_ns)
+            {
+                atomicMax(error, code);
+                break;
+            }
+        }
         __threadfence_system();
     }
 
@@ -139,7 +168,11 @@ struct paris_b200_group
     std::vector<bool> slab_down_valid;
     uint32_t steps = 0;                         // completed + begun steps (sequence numbers derive from it)
     bool in_step = false;
+    cudaStream_t side = nullptr;                // diagnostics only
+    uint32_t* h_debug = nullptr;
     bool memops_ok = true;
+    bool wait_memops = false;                   // waits as stream memory operations instead of polling kernels (A/B only)
+    unsigned long long wait_timeout_ns = 30ull * 1000ull * 1000ull * 1000ull;
     uint64_t bytes_pushed = 0;
 };
 
@@ -218,8 +251,15 @@ namespace
         return PARIS_B200_OK;
     }
 
-    int wait32(cudaStream_t s, const uint32_t* d_flag, uint32_t value)
+    // the stream continues once *d_flag >= value (see wait_flag_kernel); who = the member waited for (error report)
+    int wait32(paris_b200_group* g, cudaStream_t s, const uint32_t* d_flag, uint32_t value, uint32_t who)
     {
+        if(!g->wait_memops)
+        {
+            wait_flag_kernel<<<1, 1, 0, s>>>(d_flag, value, g->wait_timeout_ns, g->flags + kErrorWord, who + 1u);
+            PB_CUDA(cudaGetLastError());
+            return PARIS_B200_OK;
+        }
         static stream_value32_fn wait32_fn = driver_entry("cuStreamWaitValue32");
         if(wait32_fn == nullptr)
         {
@@ -427,12 +467,19 @@ extern "C" int paris_b200_group_create(int device, const paris_b200_group_config
         }                                                                                                    \
     } while(0)
 
+    if(const char* e = std::getenv("PARIS_B200_GROUP_WAIT"))
+        g->wait_memops = std::strcmp(e, "memop") == 0;
+    if(const char* e = std::getenv("PARIS_B200_GROUP_TIMEOUT_S"))
+        g->wait_timeout_ns = static_cast<unsigned long long>(std::max(1.0, std::atof(e)) * 1e9);
     PB_GTRY(paris_b200_ctx_create(device, &g->ctx));
     PB_GTRY(paris_b200_ctx_create(device, &g->fctx));
     // the exchange outranks everything else on the device (its SM-driven form must not queue behind a backprojection)
     int prio_lo = 0, prio_hi = 0;
     PB_GCUDA(cudaDeviceGetStreamPriorityRange(&prio_lo, &prio_hi));
     PB_GCUDA(cudaStreamCreateWithPriority(&g->push, cudaStreamNonBlocking, prio_hi));
+    PB_GCUDA(cudaStreamCreateWithFlags(&g->side, cudaStreamNonBlocking));
+    PB_GCUDA(cudaHostAlloc(reinterpret_cast<void**>(&g->h_debug), 2u * PARIS_B200_GROUP_MAX_MEMBERS * sizeof(uint32_t),
+                           cudaHostAllocPortable));
 
     // region, slabs, rounds, bands: pure host arithmetic, shared with paris_b200_group_plan
     paris_b200_group_plan_t plan{};
@@ -511,6 +558,17 @@ extern "C" int paris_b200_group_create(int device, const paris_b200_group_config
     }
     PB_GCUDA(cudaStreamSynchronize(g->ctx->compute));
 
+    // every kernel a step can launch is loaded NOW (see common.cuh: a lazy load inside a step deadlocks the group)
+    preload_backprojection_kernels();
+    preload_filter_kernels(g->filter->size);
+    {
+        cudaFuncAttributes a{};
+        (void)cudaFuncGetAttributes(&a, flag_store_kernel);
+        (void)cudaFuncGetAttributes(&a, wait_flag_kernel);
+        (void)cudaFuncGetAttributes(&a, push_band_kernel);
+        (void)cudaGetLastError();
+    }
+
     g->peer_stack.assign(world, nullptr);
     g->peer_flags.assign(world, nullptr);
     g->peer_ipc.assign(world, false);
@@ -557,6 +615,8 @@ extern "C" int paris_b200_group_destroy(paris_b200_group* g)
     if(g->flags) cudaFree(g->flags);
     if(g->filter) paris_b200_filter_destroy(g->filter);
     if(g->push) cudaStreamDestroy(g->push);
+    if(g->side) cudaStreamDestroy(g->side);
+    if(g->h_debug) cudaFreeHost(g->h_debug);
     if(g->fctx) paris_b200_ctx_destroy(g->fctx);
     if(g->ctx) paris_b200_ctx_destroy(g->ctx);
     delete g;
@@ -742,7 +802,7 @@ extern "C" int paris_b200_group_begin(paris_b200_group* g, const float* const* h
         PB_CUDA(cudaStreamWaitEvent(fctx->compute, g->pushed, 0));   // (the exchange reads my slots as well)
         for(uint32_t k = 0; k < world; ++k)
             if(k != me)
-                PB_TRY(wait32(g->push, g->flags + world + k, step));
+                PB_TRY(wait32(g, g->push, g->flags + world + k, step, k));
     }
 
     // ---- slab 0 (of this member): rounds pipelined against upload, filter and exchange --------------------------
@@ -795,7 +855,7 @@ extern "C" int paris_b200_group_begin(paris_b200_group* g, const float* const* h
         PB_CUDA(cudaStreamWaitEvent(ctx->compute, g->filtered[rd], 0));
         for(uint32_t k = 0; k < world; ++k)
             if(k != me)
-                PB_TRY(wait32(ctx->compute, g->flags + k, seq));
+                PB_TRY(wait32(g, ctx->compute, g->flags + k, seq, k));
         const bool last_round = rd + 1u == n_rounds;
         if(last_round && h_slabs != nullptr)
         {
@@ -859,6 +919,41 @@ extern "C" int paris_b200_group_end(paris_b200_group* g)
     PB_CUDA(cudaStreamSynchronize(g->push));
     std::fill(g->slab_down_valid.begin(), g->slab_down_valid.end(), false);
     g->in_step = false;
+    uint32_t gave_up = 0;
+    PB_CUDA(cudaMemcpy(&gave_up, g->flags + kErrorWord, sizeof(gave_up), cudaMemcpyDeviceToHost));
+    if(gave_up != 0u)
+    {
+        set_error("member %d gave up waiting for member %u after %.0f s: the step's result is incomplete", g->cfg.rank,
+                  gave_up - 1u, static_cast<double>(g->wait_timeout_ns) * 1e-9);
+        PB_CUDA(cudaMemset(g->flags + kErrorWord, 0, sizeof(uint32_t)));
+        return PARIS_B200_ESTATE;
+    }
+    return PARIS_B200_OK;
+}
+
+// diagnostics: which of the member's streams still have work (1) and the current flag words, without touching any
+// of those streams.  out: [0..4] compute, download, filter, upload, exchange; [5 .. 5 + 2 world) arrived[], consumed[]
+extern "C" int paris_b200_group_debug_state(paris_b200_group* g, uint32_t* out, uint32_t n)
+{
+    PB_CHECK_ARG(g != nullptr && out != nullptr);
+    const uint32_t world = static_cast<uint32_t>(g->cfg.world);
+    PB_CHECK_ARG(n >= 5u + 2u * world);
+    PB_TRY(bind(g));
+    cudaStream_t streams[5] = {g->ctx->compute, g->ctx->copy, g->fctx->compute, g->fctx->copy, g->push};
+    for(int i = 0; i < 5; ++i)
+    {
+        out[i] = cudaStreamQuery(streams[i]) == cudaSuccess ? 0u : 1u;
+        (void)cudaGetLastError();
+    }
+    // (a stream and a pinned landing zone made at create time: nothing here can queue behind the member's own work)
+    PB_CUDA(cudaMemcpyAsync(g->h_debug, g->flags, 2u * world * sizeof(uint32_t), cudaMemcpyDeviceToHost, g->side));
+    for(int spin = 0; spin < 2000 && cudaStreamQuery(g->side) != cudaSuccess; ++spin)
+        usleep(1000);
+    (void)cudaGetLastError();
+    const bool landed = cudaStreamQuery(g->side) == cudaSuccess;
+    (void)cudaGetLastError();
+    for(uint32_t i = 0; i < 2u * world; ++i)
+        out[5 + i] = landed ? g->h_debug[i] : 0xffffffffu;
     return PARIS_B200_OK;
 }
 
