@@ -365,6 +365,14 @@ int paris_b200_group_projection_index(const paris_b200_group* group, uint32_t lo
  * region_y floats, pinned), or NULL to leave the slabs on the device.  begin() only enqueues -- members that share a
  * host thread begin one after the other and then end; end() returns when this member's slabs are complete. */
 int paris_b200_group_begin(paris_b200_group* group, const float* const* h_raw, const float* d_raw, float* h_slabs);
+/* The same step piece by piece, for callers that produce their projections while the device works (the command-line
+ * driver reads the next round's frames from disk meanwhile): open, then every round in order -- h_raw[j] / d_raw now
+ * address only the member's share of THAT round (paris_b200_group_share tells which projections those are) -- then
+ * finish, then group_end.  group_uploaded reports when a round's host buffers may be reused. */
+int paris_b200_group_step_open(paris_b200_group* group, float* h_slabs);
+int paris_b200_group_step_round(paris_b200_group* group, uint32_t round, const float* const* h_raw, const float* d_raw);
+int paris_b200_group_uploaded(paris_b200_group* group, uint32_t round, int* done);
+int paris_b200_group_step_finish(paris_b200_group* group);
 int paris_b200_group_end(paris_b200_group* group);
 /* diagnostics: out[0..4] = 1 while the member's backprojection / download / filter / upload / exchange stream still
  * has work; out[5 .. 5 + world) = arrival flags (last round each member delivered), the next `world` words = how

@@ -160,6 +160,10 @@ SIGNATURES = {
     "paris_b200_group_info": (C.c_int, [_vp, _P(GroupInfo)]),
     "paris_b200_group_projection_index": (C.c_int, [_vp, _u32, _P(_u32)]),
     "paris_b200_group_begin": (C.c_int, [_vp, _P(_vp), _vp, _vp]),
+    "paris_b200_group_step_open": (C.c_int, [_vp, _vp]),
+    "paris_b200_group_step_round": (C.c_int, [_vp, _u32, _P(_vp), _vp]),
+    "paris_b200_group_uploaded": (C.c_int, [_vp, _u32, _P(C.c_int)]),
+    "paris_b200_group_step_finish": (C.c_int, [_vp]),
     "paris_b200_group_end": (C.c_int, [_vp]),
     "paris_b200_group_reconstruct": (C.c_int, [_vp, _P(_vp), _vp, _vp]),
     "paris_b200_group_debug_state": (C.c_int, [_vp, _P(_u32), _u32]),

@@ -42,5 +42,12 @@ namespace paris
         // Used by load() and, with plain memory, by the CPU-side format tests.
         auto read(const std::string& path, file_info& info, const std::function<float*(std::uint32_t)>& frame_buffer)
             -> std::uint32_t;
+
+        // Header only: what read() would find (info.frames = the COMPLETE frames the file really holds; a truncated
+        // file counts fewer than its header says).  info.valid is false for anything read() would reject.
+        auto probe(const std::string& path) -> file_info;
+        // Frame `frame` of a file probe() accepted, widened to float into dst (width*height floats).  False if the
+        // frame cannot be read.  Lets several readers share one scan without decoding each other's frames.
+        auto read_frame(const std::string& path, const file_info& info, std::uint32_t frame, float* dst) -> bool;
     }
 }

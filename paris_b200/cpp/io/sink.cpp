@@ -62,6 +62,24 @@ namespace paris
         save(v, v.off);
     }
 
+    namespace
+    {
+        auto file_mutex() -> std::mutex&
+        {
+            static std::mutex m;
+            return m;
+        }
+    }
+
+    auto sink::save(const float* h_slab, std::uint32_t dim_x, std::uint32_t dim_y, std::uint32_t dim_z,
+                    std::uint32_t first_slice) -> void
+    {
+        translating<stage_runtime_error>("sink::save()", "sink::save() failed", [&] {
+            const std::lock_guard<std::mutex> lock{file_mutex()};
+            ddbvf::write(handle_, h_slab, dim_x, dim_y, dim_z, first_slice);
+        });
+    }
+
     auto sink::save(const b200::volume_device_type& v, std::uint32_t first_slice) -> void
     {
         translating<stage_runtime_error>("sink::save()", "sink::save() failed", [&] {
@@ -70,8 +88,7 @@ namespace paris
             auto staged = b200::make_volume_host(v.dim_x, v.dim_y, v.dim_z);
             b200::copy_d2h(v, staged);
 
-            static std::mutex file_mutex;
-            const std::lock_guard<std::mutex> lock{file_mutex};
+            const std::lock_guard<std::mutex> lock{file_mutex()};
             ddbvf::write(handle_, staged, first_slice);
         });
     }

@@ -20,6 +20,9 @@ namespace paris
             // slab -> host (the pending backprojection batch is flushed behind the download) -> file at v.off
             auto save(const b200::volume_device_type& v) -> void;
             auto save(const b200::volume_device_type& v, std::uint32_t first_slice) -> void;
+            // a slab that is already on the host (a group member downloads its slabs itself, behind its kernels)
+            auto save(const float* h_slab, std::uint32_t dim_x, std::uint32_t dim_y, std::uint32_t dim_z,
+                      std::uint32_t first_slice) -> void;
             auto file_path() const -> std::string { return path_ + ".ddbvf"; }
 
         private:

@@ -42,6 +42,62 @@ namespace paris
         return angles;
     }
 
+    auto make_scan_index(const std::string& proj_dir, bool enable_angles, const std::string& angle_file, std::uint16_t quality)
+        -> scan_index
+    {
+        auto index = scan_index{};
+        const auto q = quality == 0 ? std::uint16_t{1} : quality;
+        auto angles = std::vector<float>{};
+        if(enable_angles)
+            angles = read_angles(angle_file);
+        auto counter = 0u;
+        for(const auto& path : read_directory(proj_dir))
+        {
+            auto info = his::file_info{};
+            try
+            {
+                info = his::probe(path);
+            }
+            catch(const std::exception&)
+            {
+                info.valid = false;
+            }
+            if(!info.valid || info.frames == 0)
+            {
+                log::warning() << "Skipping invalid file at " << path;
+                continue;
+            }
+            index.paths.push_back(path);
+            index.infos.push_back(info);
+            if(index.dim_x == 0)
+            {
+                index.dim_x = info.width;
+                index.dim_y = info.height;
+            }
+            for(auto f = 0u; f < info.frames; ++f)
+            {
+                if(counter % q == 0u)
+                {
+                    const auto has = enable_angles && counter < angles.size();
+                    index.frames.push_back(scan_frame{index.paths.size() - 1u, f, counter, has, has ? angles[counter] : 0.f});
+                }
+                ++counter;
+            }
+        }
+        return index;
+    }
+
+    auto load_scan_frame(const scan_index& index, std::size_t i, float* dst) -> bool
+    {
+        if(i >= index.frames.size())
+            return false;
+        const auto& fr = index.frames[i];
+        const auto& info = index.infos[fr.file];
+        if(info.width != index.dim_x || info.height != index.dim_y)
+            return false;   // (a scan is one detector: frames of another size cannot share the stack)
+        return his::read_frame(index.paths[fr.file], info, fr.frame, dst);
+    }
+
     source::source(const std::string& proj_dir, bool enable_angles, const std::string& angle_file,
                    std::uint16_t quality) noexcept
     : enable_angles_{enable_angles}, quality_{quality == 0 ? std::uint16_t{1} : quality}

@@ -17,12 +17,39 @@
 #include <vector>
 
 #include "../b200/backend.h"
+#include "his.h"
 
 namespace paris
 {
     // one float per whitespace-separated token; a decimal comma is accepted when the first line contains a comma
     // (the reference switches to the de_DE locale in that case, src/source.cpp:57-62)
     auto read_angles(const std::string& path) -> std::vector<float>;
+
+    // The kept frames of a scan without decoding any: which file and frame holds projection i of the scan, its
+    // frame counter idx (src/source.cpp:105: every quality-th frame is kept, idx is the counter of ALL frames) and
+    // its angle.  What several readers of one scan -- the members of a reconstruction group -- agree on.
+    struct scan_frame
+    {
+        std::size_t file;          // index into scan_index::paths
+        std::uint32_t frame;       // frame inside that file
+        std::uint32_t idx;         // frame counter of the scan (drives idx * delta_phi)
+        bool has_angle;
+        float phi;                 // from the angle file, if has_angle
+    };
+
+    struct scan_index
+    {
+        std::vector<std::string> paths;
+        std::vector<his::file_info> infos;          // per file
+        std::vector<scan_frame> frames;             // the projections of the scan, in order
+        std::uint32_t dim_x = 0, dim_y = 0;          // of the first valid file
+    };
+
+    // walks the directory exactly like source does (sorted files, invalid ones skipped, frame counter, quality, angles)
+    auto make_scan_index(const std::string& proj_dir, bool enable_angles, const std::string& angle_file, std::uint16_t quality)
+        -> scan_index;
+    // decodes projection i of the index into dst (dim_x * dim_y floats); false if the frame cannot be read
+    auto load_scan_frame(const scan_index& index, std::size_t i, float* dst) -> bool;
 
     class source
     {

@@ -162,7 +162,11 @@ struct paris_b200_group
     cudaEvent_t raw_free[2] = {nullptr, nullptr};      // the filter launch that read raw[i] has run
     bool raw_free_valid[2] = {false, false};
     std::vector<cudaEvent_t> filtered;          // per round: this member's share is in the stack
-    cudaEvent_t uploaded = nullptr, step_done = nullptr, pushed = nullptr;
+    std::vector<cudaEvent_t> uploaded;          // per round: this member's uploads have left their host buffers
+    cudaEvent_t step_done = nullptr, pushed = nullptr;
+    bool step_open = false;                     // between step_open and step_finish
+    uint32_t next_round = 0;
+    float* step_h_slabs = nullptr;
     std::vector<float*> vol;                    // slab buffers on the device
     std::vector<cudaEvent_t> slab_down;         // per slab buffer: its slab has reached the host
     std::vector<bool> slab_down_valid;
@@ -536,10 +540,12 @@ extern "C" int paris_b200_group_create(int device, const paris_b200_group_config
         PB_GCUDA(cudaEventCreateWithFlags(&g->raw_free[i], cudaEventDisableTiming));
     }
     PB_GCUDA(cudaEventCreateWithFlags(&g->pushed, cudaEventDisableTiming));
-    PB_GCUDA(cudaEventCreateWithFlags(&g->uploaded, cudaEventDisableTiming));
     PB_GCUDA(cudaEventCreateWithFlags(&g->step_done, cudaEventDisableTiming));
     g->filtered.resize(g->rounds.size());
     for(auto& e : g->filtered)
+        PB_GCUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    g->uploaded.resize(g->rounds.size());
+    for(auto& e : g->uploaded)
         PB_GCUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
     const uint32_t n_buf = cfg->stream_slabs ? std::min(spr, 2u) : spr;
     for(uint32_t b = 0; b < n_buf; ++b)
@@ -609,7 +615,8 @@ extern "C" int paris_b200_group_destroy(paris_b200_group* g)
     if(g->pushed) cudaEventDestroy(g->pushed);
     for(auto e : g->filtered)
         if(e) cudaEventDestroy(e);
-    if(g->uploaded) cudaEventDestroy(g->uploaded);
+    for(auto e : g->uploaded)
+        if(e) cudaEventDestroy(e);
     if(g->step_done) cudaEventDestroy(g->step_done);
     if(g->stack) cudaFree(g->stack);
     if(g->flags) cudaFree(g->flags);
@@ -754,21 +761,24 @@ extern "C" int paris_b200_group_projection_index(const paris_b200_group* g, uint
     return PARIS_B200_EINVAL;
 }
 
-extern "C" int paris_b200_group_begin(paris_b200_group* g, const float* const* h_raw, const float* d_raw, float* h_slabs)
+// ---- one step, piece by piece: open -> round 0 .. rounds-1 -> finish -> end -----------------------------------
+// (callers that have all their projections at hand use group_begin; the command-line driver reads the next round's
+// frames from disk while the device works on the previous one)
+
+extern "C" int paris_b200_group_step_open(paris_b200_group* g, float* h_slabs)
 {
     PB_CHECK_ARG(g != nullptr);
-    PB_CHECK_ARG((h_raw != nullptr) != (d_raw != nullptr) || g->my_count == 0);
     if(!g->connected)
     {
-        set_error("group_begin before group_connect");
+        set_error("group step before group_connect");
         return PARIS_B200_ESTATE;
     }
-    if(g->in_step)
+    if(g->in_step || g->step_open)
     {
-        set_error("group_begin while a step is in flight (call group_end first)");
+        set_error("group step opened while another one is in flight (call group_end first)");
         return PARIS_B200_ESTATE;
     }
-    if(g->cfg.stream_slabs && g->slabs.size() > g->vol.size() && h_slabs == nullptr)
+    if(g->slabs.size() > g->vol.size() && h_slabs == nullptr)
     {
         set_error("slabs are streamed through %zu buffers: a host destination is required", g->vol.size());
         return PARIS_B200_EINVAL;
@@ -777,9 +787,49 @@ extern "C" int paris_b200_group_begin(paris_b200_group* g, const float* const* h
     paris_b200_ctx* ctx = g->ctx;
     paris_b200_ctx* fctx = g->fctx;
     const uint32_t world = static_cast<uint32_t>(g->cfg.world), me = static_cast<uint32_t>(g->cfg.rank);
-    const uint32_t n_rounds = static_cast<uint32_t>(g->rounds.size());
     const uint32_t step = g->steps;            // steps completed before this one
     const size_t slice = static_cast<size_t>(g->region_x) * g->region_y;
+
+    // ---- write-after-read guards: the stack slots are rewritten ------------------------------------------------
+    // my own previous backprojections have read my slots; every peer's must have read what I am about to push
+    if(step > 0)
+    {
+        PB_CUDA(cudaStreamWaitEvent(fctx->compute, g->step_done, 0));
+        PB_CUDA(cudaStreamWaitEvent(fctx->compute, g->pushed, 0));   // (the exchange reads my slots as well)
+        for(uint32_t k = 0; k < world; ++k)
+            if(k != me)
+                PB_TRY(wait32(g, g->push, g->flags + world + k, step, k));
+    }
+    // (first use of buffer 0 in this step: the previous step's download of it finished in group_end)
+    PB_CUDA(cudaMemsetAsync(g->vol[0], 0, slice * g->slabs[0].dz * sizeof(float), ctx->compute));
+    g->step_h_slabs = h_slabs;
+    g->next_round = 0;
+    g->step_open = true;
+    return PARIS_B200_OK;
+}
+
+// Round `rd` of the open step (rounds go in order).  Exactly one of h_raw / d_raw unless this member has no share of
+// the round: h_raw[j] = pinned host address of the j-th projection of this member's share, d_raw = the share on the
+// device, contiguous.  Everything is only enqueued: the host buffers must stay untouched until group_end (or until
+// paris_b200_group_uploaded reports the round).
+extern "C" int paris_b200_group_step_round(paris_b200_group* g, uint32_t rd, const float* const* h_raw, const float* d_raw)
+{
+    PB_CHECK_ARG(g != nullptr);
+    if(!g->step_open || rd != g->next_round || rd >= g->rounds.size())
+    {
+        set_error("group_step_round(%u): rounds of an open step go in order (next: %u of %zu)", rd, g->next_round, g->rounds.size());
+        return PARIS_B200_ESTATE;
+    }
+    PB_TRY(bind(g));
+    paris_b200_ctx* ctx = g->ctx;
+    paris_b200_ctx* fctx = g->fctx;
+    const uint32_t world = static_cast<uint32_t>(g->cfg.world), me = static_cast<uint32_t>(g->cfg.rank);
+    const uint32_t n_rounds = static_cast<uint32_t>(g->rounds.size());
+    const uint32_t step = g->steps;
+    uint32_t first = 0, count = 0;
+    share_of(g->rounds[rd], world, me, &first, &count);
+    PB_CHECK_ARG(count == 0 || (h_raw != nullptr) != (d_raw != nullptr));
+    const uint32_t seq = step * n_rounds + rd + 1u;
     const weight_params w = [&] {
         // src/weighting.cpp:37-42
         const auto& det = g->cfg.det;
@@ -794,84 +844,93 @@ extern "C" int paris_b200_group_begin(paris_b200_group* g, const float* const* h
         return p;
     }();
 
-    // ---- write-after-read guards: the stack slots are rewritten ------------------------------------------------
-    // my own previous backprojections have read my slots; every peer's must have read what I am about to push
-    if(step > 0)
+    if(count > 0)
     {
-        PB_CUDA(cudaStreamWaitEvent(fctx->compute, g->step_done, 0));
-        PB_CUDA(cudaStreamWaitEvent(fctx->compute, g->pushed, 0));   // (the exchange reads my slots as well)
-        for(uint32_t k = 0; k < world; ++k)
-            if(k != me)
-                PB_TRY(wait32(g, g->push, g->flags + world + k, step, k));
+        const float* src = d_raw;
+        if(h_raw != nullptr)
+        {
+            // upload this round's share into one of the two upload buffers (copy stream of the filter context)
+            const int b = static_cast<int>(rd & 1u);
+            if(g->raw_free_valid[b])
+                PB_CUDA(cudaStreamWaitEvent(fctx->copy, g->raw_free[b], 0));
+            for(uint32_t j = 0; j < count; ++j)
+                PB_CUDA(cudaMemcpyAsync(g->raw[b] + g->px * j, h_raw[j], g->px * sizeof(float), cudaMemcpyHostToDevice,
+                                        fctx->copy));
+            PB_CUDA(cudaEventRecord(g->uploaded[rd], fctx->copy));
+            PB_CUDA(cudaStreamWaitEvent(fctx->compute, g->uploaded[rd], 0));
+            src = g->raw[b];
+        }
+        const float* ptrs[kMaxBatch];
+        for(uint32_t done = 0; done < count;)
+        {
+            const uint32_t n = std::min<uint32_t>(count - done, 64u);   // (persistent CTAs: 64 projections fill the GPU)
+            for(uint32_t i = 0; i < n; ++i)
+                ptrs[i] = src + g->px * (done + i);
+            PB_TRY(launch_filter_batch(fctx, ptrs, nullptr, n, g->stack, first + done, g->slot_floats, g->cfg.det.n_row,
+                                       g->cfg.det.n_col, g->filter, w, true, g->pitch, g->layout));
+            done += n;
+        }
+        if(h_raw != nullptr)
+        {
+            PB_CUDA(cudaEventRecord(g->raw_free[rd & 1u], fctx->compute));
+            g->raw_free_valid[rd & 1u] = true;
+        }
     }
-
-    // ---- slab 0 (of this member): rounds pipelined against upload, filter and exchange --------------------------
-    // (first use of buffer 0 in this step: the previous step's download of it finished in group_end)
+    if(count == 0 || h_raw == nullptr)
+        PB_CUDA(cudaEventRecord(g->uploaded[rd], fctx->copy));   // (nothing to wait for)
+    PB_CUDA(cudaEventRecord(g->filtered[rd], fctx->compute));
+    if(world > 1u)
+        PB_TRY(push_round(g, rd, seq));
+    // the round is complete here once my own share is filtered and every peer's has arrived
+    PB_CUDA(cudaStreamWaitEvent(ctx->compute, g->filtered[rd], 0));
+    for(uint32_t k = 0; k < world; ++k)
+        if(k != me)
+            PB_TRY(wait32(g, ctx->compute, g->flags + k, seq, k));
     const slab_t s0 = g->slabs[0];
-    PB_CUDA(cudaMemsetAsync(g->vol[0], 0, slice * s0.dz * sizeof(float), ctx->compute));
-    for(uint32_t rd = 0; rd < n_rounds; ++rd)
+    const bool last_round = rd + 1u == n_rounds;
+    if(last_round && g->step_h_slabs != nullptr)
     {
-        uint32_t first = 0, count = 0;
-        share_of(g->rounds[rd], world, me, &first, &count);
-        const uint32_t seq = step * n_rounds + rd + 1u;
-        if(count > 0)
-        {
-            const float* src = nullptr;
-            if(h_raw != nullptr)
-            {
-                // upload this round's share into one of the two upload buffers (copy stream of the filter context)
-                const int b = static_cast<int>(rd & 1u);
-                if(g->raw_free_valid[b])
-                    PB_CUDA(cudaStreamWaitEvent(fctx->copy, g->raw_free[b], 0));
-                for(uint32_t j = 0; j < count; ++j)
-                    PB_CUDA(cudaMemcpyAsync(g->raw[b] + g->px * j, h_raw[g->local_first[rd] + j], g->px * sizeof(float),
-                                            cudaMemcpyHostToDevice, fctx->copy));
-                PB_CUDA(cudaEventRecord(g->uploaded, fctx->copy));
-                PB_CUDA(cudaStreamWaitEvent(fctx->compute, g->uploaded, 0));
-                src = g->raw[b];
-            }
-            else
-                src = d_raw + g->px * g->local_first[rd];
-            const float* ptrs[kMaxBatch];
-            for(uint32_t done = 0; done < count;)
-            {
-                const uint32_t n = std::min<uint32_t>(count - done, 64u);   // (persistent CTAs: 64 projections fill the GPU)
-                for(uint32_t i = 0; i < n; ++i)
-                    ptrs[i] = src + g->px * (done + i);
-                PB_TRY(launch_filter_batch(fctx, ptrs, nullptr, n, g->stack, first + done, g->slot_floats, g->cfg.det.n_row,
-                                           g->cfg.det.n_col, g->filter, w, true, g->pitch, g->layout));
-                done += n;
-            }
-            if(h_raw != nullptr)
-            {
-                PB_CUDA(cudaEventRecord(g->raw_free[rd & 1u], fctx->compute));
-                g->raw_free_valid[rd & 1u] = true;
-            }
-        }
-        PB_CUDA(cudaEventRecord(g->filtered[rd], fctx->compute));
-        if(world > 1u)
-            PB_TRY(push_round(g, rd, seq));
-        // the round is complete here once my own share is filtered and every peer's has arrived
-        PB_CUDA(cudaStreamWaitEvent(ctx->compute, g->filtered[rd], 0));
-        for(uint32_t k = 0; k < world; ++k)
-            if(k != me)
-                PB_TRY(wait32(g, ctx->compute, g->flags + k, seq, k));
-        const bool last_round = rd + 1u == n_rounds;
-        if(last_round && h_slabs != nullptr)
-        {
-            // the last launch into the slab is cut into z-chunks whose download runs behind the next chunk's kernel
-            const bp_target t = target_of(g, s0, g->vol[0]);
-            PB_TRY(backproject_and_download(ctx, g->stack, g->slot_floats, g->pitch, g->rounds[rd].first, g->rounds[rd].count,
-                                            g->sn.data() + g->rounds[rd].first, g->cs.data() + g->rounds[rd].first, t,
-                                            g->layout, h_slabs, false));
-            PB_CUDA(cudaEventRecord(g->slab_down[0], ctx->copy));
-            g->slab_down_valid[0] = true;
-        }
-        else
-            PB_TRY(backproject_range(g, g->rounds[rd].first, g->rounds[rd].count, s0, g->vol[0]));
+        // the last launch into the slab is cut into z-chunks whose download runs behind the next chunk's kernel
+        const bp_target t = target_of(g, s0, g->vol[0]);
+        PB_TRY(backproject_and_download(ctx, g->stack, g->slot_floats, g->pitch, g->rounds[rd].first, g->rounds[rd].count,
+                                        g->sn.data() + g->rounds[rd].first, g->cs.data() + g->rounds[rd].first, t,
+                                        g->layout, g->step_h_slabs, false));
+        PB_CUDA(cudaEventRecord(g->slab_down[0], ctx->copy));
+        g->slab_down_valid[0] = true;
     }
+    else
+        PB_TRY(backproject_range(g, g->rounds[rd].first, g->rounds[rd].count, s0, g->vol[0]));
+    g->next_round = rd + 1u;
+    return PARIS_B200_OK;
+}
 
-    // ---- further slabs: loop over the ONE gathered stack, download of slab k behind the backprojection of k + 1 ------
+// 1 once the uploads of round `rd` have left their host buffers (those may then be reused)
+extern "C" int paris_b200_group_uploaded(paris_b200_group* g, uint32_t rd, int* done)
+{
+    PB_CHECK_ARG(g != nullptr && done != nullptr && rd < g->rounds.size());
+    PB_TRY(bind(g));
+    const cudaError_t e = cudaEventQuery(g->uploaded[rd]);
+    (void)cudaGetLastError();
+    *done = e == cudaSuccess ? 1 : 0;
+    return PARIS_B200_OK;
+}
+
+// After the last round: the member's further slabs loop over the ONE gathered stack, the download of slab k behind
+// the backprojection of slab k + 1; then every peer learns that its pushes into this member's stack have been consumed.
+extern "C" int paris_b200_group_step_finish(paris_b200_group* g)
+{
+    PB_CHECK_ARG(g != nullptr);
+    if(!g->step_open || g->next_round != g->rounds.size())
+    {
+        set_error("group_step_finish before every round of the step was given");
+        return PARIS_B200_ESTATE;
+    }
+    PB_TRY(bind(g));
+    paris_b200_ctx* ctx = g->ctx;
+    const uint32_t world = static_cast<uint32_t>(g->cfg.world), me = static_cast<uint32_t>(g->cfg.rank);
+    const uint32_t step = g->steps;
+    const size_t slice = static_cast<size_t>(g->region_x) * g->region_y;
+    float* h_slabs = g->step_h_slabs;
     for(uint32_t s = 1; s < g->slabs.size(); ++s)
     {
         const slab_t sl = g->slabs[s];
@@ -896,16 +955,29 @@ extern "C" int paris_b200_group_begin(paris_b200_group* g, const float* const* h
         else
             PB_TRY(backproject_range(g, 0u, n_proj, sl, g->vol[b]));
     }
-
-    // ---- end of step: tell every peer that its pushes into my stack have been consumed ------------------------------------
     PB_CUDA(cudaEventRecord(g->step_done, ctx->compute));
     PB_CUDA(cudaEventRecord(g->pushed, g->push));
     for(uint32_t k = 0; k < world; ++k)
         if(k != me)
             PB_TRY(signal32(g, ctx->compute, g->peer_flags[k] + world + me, step + 1u));
     g->steps = step + 1u;
+    g->step_open = false;
     g->in_step = true;
     return PARIS_B200_OK;
+}
+
+extern "C" int paris_b200_group_begin(paris_b200_group* g, const float* const* h_raw, const float* d_raw, float* h_slabs)
+{
+    PB_CHECK_ARG(g != nullptr);
+    PB_CHECK_ARG((h_raw != nullptr) != (d_raw != nullptr) || g->my_count == 0);
+    PB_TRY(paris_b200_group_step_open(g, h_slabs));
+    for(uint32_t rd = 0; rd < g->rounds.size(); ++rd)
+    {
+        const uint32_t local = g->local_first[rd];
+        PB_TRY(paris_b200_group_step_round(g, rd, h_raw != nullptr ? h_raw + local : nullptr,
+                                           d_raw != nullptr ? d_raw + g->px * local : nullptr));
+    }
+    return paris_b200_group_step_finish(g);
 }
 
 extern "C" int paris_b200_group_end(paris_b200_group* g)

@@ -140,3 +140,42 @@ def test_source_angles_and_second_walk_restarts_counting(tmp_path):
     assert not from_file[30:].any()                                   # callers fall back to idx*delta_phi there
     idx2, _, _, _ = pio.source_walk(scan, None, 1)                    # (the reference would continue at N_PROJ: F9)
     assert list(idx2) == list(range(N_PROJ))
+
+
+# ---- the group driver (several members; on a one-GPU box they share the device) -------------------------------------
+
+@pytest.mark.parametrize("members,slabs", [(1, 1), (3, 3), (2, 4)])
+def test_cli_group_equals_the_task_model_bit_for_bit(tmp_path, members, slabs):
+    """PARIS_B200_GROUP: every member reads and filters 1/N of the frames, detector-row bands travel between the
+    members, every member backprojects everything into its own slabs -- the same file as the reference's task model
+    (every device reads and filters everything) writes."""
+    _, _, scan, geo = make_scan(tmp_path)
+    run_cli(["--geometry", geo, "--input", scan, "--output", str(tmp_path / "tasks")], env={"PARIS_B200_TASKS": "1"})
+    r = run_cli(["--geometry", geo, "--input", scan, "--output", str(tmp_path / "group")],
+                env={"PARIS_B200_GROUP": "1", "PARIS_B200_GROUP_MEMBERS": str(members), "PARIS_B200_SLABS": str(slabs),
+                     "PARIS_B200_GROUP_TIMEOUT_S": "20"})
+    assert f"Group of {members} member" in r.stderr
+    assert r.stderr.count("projections filtered here") == members
+    a = formats.read_ddbvf(str(tmp_path / "tasks" / "vol.ddbvf"))
+    b = formats.read_ddbvf(str(tmp_path / "group" / "vol.ddbvf"))
+    assert np.array_equal(a, b)
+
+
+def test_cli_group_u16_roi_angles_quality_against_the_oracle(tmp_path, port):
+    odet, stack, scan, geo = make_scan(tmp_path, number_type=4, delta_s=2.0)
+    rng = np.random.default_rng(6)
+    angles = (np.arange(N_PROJ) * odet.delta_phi + rng.uniform(-1.0, 1.0, N_PROJ)).astype(np.float32)
+    af = tmp_path / "angles.txt"
+    af.write_text("\n".join(repr(float(a)) for a in angles[:31]) + "\n")     # shorter than the scan: idx*delta_phi after it
+    roi = oracle.Roi(5, 40, 8, 50, 3, 30)
+    out = tmp_path / "out"
+    run_cli(["--geometry", geo, "--input", scan, "--output", str(out), "--angles", str(af), "--quality", "2", "--roi",
+             "--roi-x1", "5", "--roi-x2", "40", "--roi-y1", "8", "--roi-y2", "50", "--roi-z1", "3", "--roi-z2", "30"],
+            env={"PARIS_B200_GROUP": "1", "PARIS_B200_GROUP_MEMBERS": "3", "PARIS_B200_GROUP_TIMEOUT_S": "20"})
+    got = formats.read_ddbvf(str(out / "vol.ddbvf"))
+    used = list(range(0, N_PROJ, 2))
+    full_angles = np.array([angles[i] if i < 31 else np.float32(i) * np.float32(odet.delta_phi) for i in range(N_PROJ)],
+                           np.float32)
+    want = oracle_volume(port, odet, stack, indices=used, angles=full_angles, roi=roi)
+    assert got.shape == want.shape
+    check(got, want, len(used))
