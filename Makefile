@@ -46,3 +46,4 @@ clean:
 	$(MAKE) -C oracle clean
 
 .PHONY: all lib oracle clean
+

@@ -336,6 +336,11 @@ class SharedHostVolume:
             try:
                 if rank != 0 and ok:
                     self.shm = shared_memory.SharedMemory(name=name)
+                    try:   # (rank 0 owns the segment: the other ranks' resource trackers must not unlink it again)
+                        from multiprocessing import resource_tracker
+                        resource_tracker.unregister(self.shm._name, "shared_memory")
+                    except Exception:
+                        pass
                 if self.shm is not None:
                     self.array = np.ndarray((voxels,), np.float32, buffer=self.shm.buf)
                     capi.check(capi.lib().paris_b200_host_register(self.array.ctypes.data, voxels * 4))

@@ -48,11 +48,13 @@ namespace pb
         static constexpr int THREADS = 32 * WARPS;
         static constexpr int STAGE_BYTES = BH * BV * 4;
         static constexpr int TAB_BYTES = COLS * (16 + 4 + 4);  // float4 + 2 words per column (+ 1 word with STRADDLE)
+        // table sets: two (the table of projection p + 1 is built while projection p is consumed)
+        static constexpr int TABLE_SLOTS = 2;
         // shared memory of an instantiation: stages, two table sets, box origins, barriers
         static constexpr size_t smem(bool straddle)
         {
-            return size_t(STAGES) * STAGE_BYTES + 2 * TAB_BYTES + (straddle ? 2 * COLS * 4 : 0) + kMaxBatch * 8
-                 + STAGES * 8 + 128;
+            return size_t(STAGES) * STAGE_BYTES + TABLE_SLOTS * TAB_BYTES + (straddle ? TABLE_SLOTS * COLS * 4 : 0)
+                 + kMaxBatch * 8 + STAGES * 8 + 128;
         }
         static constexpr size_t SMEM = smem(true);   // (scratch-size checks use the larger one)
         // 256-thread tiles rely on TWO resident CTAs per SM (228 KB of shared memory, 1 KB reserved per CTA)
@@ -414,10 +416,11 @@ namespace pb
         extern __shared__ __align__(128) unsigned char smem[];
         unsigned char* stage_mem = smem;                                                   // STAGES x BH x BV floats
         float4* tab_a = reinterpret_cast<float4*>(smem + size_t(CFG::STAGES) * CFG::STAGE_BYTES);
-        float* tab_b = reinterpret_cast<float*>(tab_a + 2 * CFG::COLS);
-        uint32_t* tab_c = reinterpret_cast<uint32_t*>(tab_b + 2 * CFG::COLS);
-        uint32_t* tab_d = tab_c + 2 * CFG::COLS;   // (present only with STRADDLE)
-        box_origin* origin = reinterpret_cast<box_origin*>(tab_d + (STRADDLE ? 2 * CFG::COLS : 0));
+        constexpr int TS = CFG::TABLE_SLOTS;
+        float* tab_b = reinterpret_cast<float*>(tab_a + TS * CFG::COLS);
+        uint32_t* tab_c = reinterpret_cast<uint32_t*>(tab_b + TS * CFG::COLS);
+        uint32_t* tab_d = tab_c + TS * CFG::COLS;   // (present only with STRADDLE)
+        box_origin* origin = reinterpret_cast<box_origin*>(tab_d + (STRADDLE ? TS * CFG::COLS : 0));
         uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(origin) + kMaxBatch * 8);
 
         const int tid = threadIdx.x;
@@ -451,7 +454,9 @@ namespace pb
         {
             #pragma unroll
             for(int s = 0; s < CFG::STAGES; ++s)
-                mbar_init(smem_u32(&bars[s]), 1);
+            {
+                mbar_init(smem_u32(&bars[s]), 1);                                  // the stage's box has landed
+            }
             asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
         }
         if(tid < count)
@@ -581,7 +586,8 @@ namespace pb
         const uint32_t stage_base0 = smem_u32(stage_mem);
         constexpr double kOne = static_cast<double>(1u << CFG::ROW_SHIFT);
 
-        auto build = [&](int p) {
+        // entry of tile column `col` for projection p, into table set `slot`
+        auto build = [&](int p, int col, int slot, float bx_k, float by_l) {
             const box_origin o = origin[p];
             if(o.all_valid == 2)
                 return; // the projection is skipped for this tile
@@ -654,15 +660,15 @@ namespace pb
             if(ea.w == 0.f && eb == 0.f) atomicAdd(&g_bp_stats[5], 1ull);              // dead columns
             if(o.all_valid == 0) atomicAdd(&g_bp_stats[6], 1ull);                      // entries in mixed tiles
 #endif
-            tab_a[(p & 1) * CFG::COLS + tid] = ea;
-            tab_b[(p & 1) * CFG::COLS + tid] = eb;
-            tab_c[(p & 1) * CFG::COLS + tid] = ec;
+            tab_a[slot * CFG::COLS + col] = ea;
+            tab_b[slot * CFG::COLS + col] = eb;
+            tab_c[slot * CFG::COLS + col] = ec;
             if(STRADDLE)
-                tab_d[(p & 1) * CFG::COLS + tid] = ed;
+                tab_d[slot * CFG::COLS + col] = ed;
         };
 
         if(builder && count > 0)
-            build(0);
+            build(0, tid, 0, bx_k, by_l);
         __syncthreads();
 
         // ---- main loop over the projections of the batch -----------------------------------------------------------
@@ -670,7 +676,7 @@ namespace pb
         for(int p = 0; p < count; ++p)
         {
             if(builder && p + 1 < count)
-                build(p + 1);
+                build(p + 1, tid, (p + 1) & 1, bx_k, by_l);
 
             const int stage = p % CFG::STAGES;
             mbar_wait(smem_u32(&bars[stage]), static_cast<uint32_t>((p / CFG::STAGES) & 1));

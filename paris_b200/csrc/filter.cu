@@ -122,28 +122,73 @@ namespace pb
         }
     }
 
+    // radix-4 pass with the three twiddles given (see pass4)
+    template <bool INVERSE>
+    __device__ __forceinline__ void pass4w(float2& e0, float2& e1, float2& e2, float2& e3, float2 w1, float2 w2, float2 w3)
+    {
+        if(!INVERSE)
+        {
+            dif4(e0, e1, e2, e3);
+            e1 = cmul(e1, w1);
+            e2 = cmul(e2, w2);
+            e3 = cmul(e3, w3);
+        }
+        else
+        {
+            e1 = cmul_conj(e1, w1);
+            e2 = cmul_conj(e2, w2);
+            e3 = cmul_conj(e3, w3);
+            dit4(e0, e1, e2, e3);
+        }
+    }
+
+    // exp(-2 pi i k / 16)
+    __device__ __forceinline__ constexpr float2 root16(int k)
+    {
+        constexpr float c[16] = {1.f, 0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f, 0.f,
+                                 -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f, -1.f,
+                                 -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f, 0.f,
+                                 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f};
+        constexpr float sn[16] = {0.f, 0.38268343236508977f, 0.70710678118654752f, 0.92387953251128674f, 1.f,
+                                  0.92387953251128674f, 0.70710678118654752f, 0.38268343236508977f, 0.f,
+                                  -0.38268343236508977f, -0.70710678118654752f, -0.92387953251128674f, -1.f,
+                                  -0.92387953251128674f, -0.70710678118654752f, -0.38268343236508977f};
+        return float2{c[k & 15], -sn[k & 15]};
+    }
+
     // Two consecutive passes (spans 2^M and 2^(M-2)) on the 16 points e[k] = x[block*2^M + j + k*2^(M-4)].
+    // Twiddles: butterfly r of the first pass sits at position j + r*Q2 of its quarter, Q2 = 2^(M-4), so
+    //   W_(2^M)^(q (j + r Q2)) = W_(2^M)^(q j) * exp(-2 pi i q r / 16):
+    // ONE loaded triple W^j, W^2j, W^3j times compile-time 16th roots gives all twelve twiddles of the pass, and the
+    // second pass uses one triple for its four butterflies -- 6 shared-memory loads per group instead of 15 (the kernel
+    // is bound by its shared-memory pipe: the multiplications by constants are cheaper than the loads they replace).
     template <int LOG2N, int M, bool INVERSE>
     __device__ __forceinline__ void group16(float2 (&e)[16], int j, const float2* __restrict__ tw)
     {
-        constexpr int Q2 = 1 << (M - 4);
+        static_assert(M >= 7, "both passes of a double group carry twiddles");
+        const float2* const t1 = tw + 3 * ((1 << M) - 8) / 4;
+        const float2* const t2 = tw + 3 * ((1 << (M - 2)) - 8) / 4;
+        const float2 a = t1[j], b = t1[2 * j], c = t1[3 * j];
+        const float2 a2 = t2[j], b2 = t2[2 * j], c2 = t2[3 * j];
         if(!INVERSE)
         {
             #pragma unroll
             for(int r = 0; r < 4; ++r)
-                pass4<LOG2N, M, false>(e[r], e[r + 4], e[r + 8], e[r + 12], j + r * Q2, tw);
+                pass4w<false>(e[r], e[r + 4], e[r + 8], e[r + 12], r == 0 ? a : cmul(a, root16(r)),
+                              r == 0 ? b : cmul(b, root16(2 * r)), r == 0 ? c : cmul(c, root16(3 * r)));
             #pragma unroll
             for(int q = 0; q < 4; ++q)
-                pass4<LOG2N, M - 2, false>(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3], j, tw);
+                pass4w<false>(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3], a2, b2, c2);
         }
         else
         {
             #pragma unroll
             for(int q = 0; q < 4; ++q)
-                pass4<LOG2N, M - 2, true>(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3], j, tw);
+                pass4w<true>(e[4 * q], e[4 * q + 1], e[4 * q + 2], e[4 * q + 3], a2, b2, c2);
             #pragma unroll
             for(int r = 0; r < 4; ++r)
-                pass4<LOG2N, M, true>(e[r], e[r + 4], e[r + 8], e[r + 12], j + r * Q2, tw);
+                pass4w<true>(e[r], e[r + 4], e[r + 8], e[r + 12], r == 0 ? a : cmul(a, root16(r)),
+                             r == 0 ? b : cmul(b, root16(2 * r)), r == 0 ? c : cmul(c, root16(3 * r)));
         }
     }
 

@@ -164,6 +164,11 @@ struct paris_b200_group
     std::vector<cudaEvent_t> filtered;          // per round: this member's share is in the stack
     std::vector<cudaEvent_t> uploaded;          // per round: this member's uploads have left their host buffers
     cudaEvent_t step_done = nullptr, pushed = nullptr;
+    // PARIS_B200_GROUP_TRACE=1: per round, when the member's share was filtered, when it had been pushed to every
+    // peer, when the round's backprojection finished -- milliseconds from the step's start, printed by group_end
+    bool trace = false;
+    cudaEvent_t trace_t0 = nullptr;
+    std::vector<cudaEvent_t> trace_filtered, trace_pushed, trace_bp;
     bool step_open = false;                     // between step_open and step_finish
     uint32_t next_round = 0;
     float* step_h_slabs = nullptr;
@@ -473,6 +478,8 @@ extern "C" int paris_b200_group_create(int device, const paris_b200_group_config
 
     if(const char* e = std::getenv("PARIS_B200_GROUP_WAIT"))
         g->wait_memops = std::strcmp(e, "memop") == 0;
+    if(const char* e = std::getenv("PARIS_B200_GROUP_TRACE"))
+        g->trace = std::atoi(e) != 0;
     if(const char* e = std::getenv("PARIS_B200_GROUP_TIMEOUT_S"))
         g->wait_timeout_ns = static_cast<unsigned long long>(std::max(1.0, std::atof(e)) * 1e9);
     PB_GTRY(paris_b200_ctx_create(device, &g->ctx));
@@ -547,6 +554,16 @@ extern "C" int paris_b200_group_create(int device, const paris_b200_group_config
     g->uploaded.resize(g->rounds.size());
     for(auto& e : g->uploaded)
         PB_GCUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+    if(g->trace)
+    {
+        PB_GCUDA(cudaEventCreate(&g->trace_t0));
+        for(auto* v : {&g->trace_filtered, &g->trace_pushed, &g->trace_bp})
+        {
+            v->resize(g->rounds.size());
+            for(auto& e : *v)
+                PB_GCUDA(cudaEventCreate(&e));
+        }
+    }
     const uint32_t n_buf = cfg->stream_slabs ? std::min(spr, 2u) : spr;
     for(uint32_t b = 0; b < n_buf; ++b)
     {
@@ -617,6 +634,10 @@ extern "C" int paris_b200_group_destroy(paris_b200_group* g)
         if(e) cudaEventDestroy(e);
     for(auto e : g->uploaded)
         if(e) cudaEventDestroy(e);
+    if(g->trace_t0) cudaEventDestroy(g->trace_t0);
+    for(auto* v : {&g->trace_filtered, &g->trace_pushed, &g->trace_bp})
+        for(auto e : *v)
+            if(e) cudaEventDestroy(e);
     if(g->step_done) cudaEventDestroy(g->step_done);
     if(g->stack) cudaFree(g->stack);
     if(g->flags) cudaFree(g->flags);
@@ -801,6 +822,8 @@ extern "C" int paris_b200_group_step_open(paris_b200_group* g, float* h_slabs)
                 PB_TRY(wait32(g, g->push, g->flags + world + k, step, k));
     }
     // (first use of buffer 0 in this step: the previous step's download of it finished in group_end)
+    if(g->trace)
+        PB_CUDA(cudaEventRecord(g->trace_t0, ctx->compute));
     PB_CUDA(cudaMemsetAsync(g->vol[0], 0, slice * g->slabs[0].dz * sizeof(float), ctx->compute));
     g->step_h_slabs = h_slabs;
     g->next_round = 0;
@@ -879,8 +902,12 @@ extern "C" int paris_b200_group_step_round(paris_b200_group* g, uint32_t rd, con
     if(count == 0 || h_raw == nullptr)
         PB_CUDA(cudaEventRecord(g->uploaded[rd], fctx->copy));   // (nothing to wait for)
     PB_CUDA(cudaEventRecord(g->filtered[rd], fctx->compute));
+    if(g->trace)
+        PB_CUDA(cudaEventRecord(g->trace_filtered[rd], fctx->compute));
     if(world > 1u)
         PB_TRY(push_round(g, rd, seq));
+    if(g->trace)
+        PB_CUDA(cudaEventRecord(g->trace_pushed[rd], g->push));
     // the round is complete here once my own share is filtered and every peer's has arrived
     PB_CUDA(cudaStreamWaitEvent(ctx->compute, g->filtered[rd], 0));
     for(uint32_t k = 0; k < world; ++k)
@@ -900,6 +927,8 @@ extern "C" int paris_b200_group_step_round(paris_b200_group* g, uint32_t rd, con
     }
     else
         PB_TRY(backproject_range(g, g->rounds[rd].first, g->rounds[rd].count, s0, g->vol[0]));
+    if(g->trace)
+        PB_CUDA(cudaEventRecord(g->trace_bp[rd], ctx->compute));
     g->next_round = rd + 1u;
     return PARIS_B200_OK;
 }
@@ -991,6 +1020,23 @@ extern "C" int paris_b200_group_end(paris_b200_group* g)
     PB_CUDA(cudaStreamSynchronize(g->push));
     std::fill(g->slab_down_valid.begin(), g->slab_down_valid.end(), false);
     g->in_step = false;
+    if(g->trace)
+    {
+        std::string line = "[group trace] member " + std::to_string(g->cfg.rank) + " step " + std::to_string(g->steps)
+                         + ": round(projections) filtered / pushed / backprojected at ms:";
+        for(size_t rd = 0; rd < g->rounds.size(); ++rd)
+        {
+            float f = 0.f, p = 0.f, b = 0.f;
+            cudaEventElapsedTime(&f, g->trace_t0, g->trace_filtered[rd]);
+            cudaEventElapsedTime(&p, g->trace_t0, g->trace_pushed[rd]);
+            cudaEventElapsedTime(&b, g->trace_t0, g->trace_bp[rd]);
+            char buf[96];
+            std::snprintf(buf, sizeof(buf), " %zu(%u) %.1f/%.1f/%.1f", rd, g->rounds[rd].count, f, p, b);
+            line += buf;
+        }
+        (void)cudaGetLastError();
+        std::fprintf(stderr, "%s\n", line.c_str());
+    }
     uint32_t gave_up = 0;
     PB_CUDA(cudaMemcpy(&gave_up, g->flags + kErrorWord, sizeof(gave_up), cudaMemcpyDeviceToHost));
     if(gave_up != 0u)
