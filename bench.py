@@ -320,7 +320,7 @@ class SharedHostVolume:
         self.capi, self.kind, self.shm, self.registered = capi, "per-rank pinned buffers", None, False
         self.ptr = None
         ok = True
-        if world > 1:
+        if world > 1 and voxels * 4 <= (8 << 30):   # (larger volumes: every member keeps its slabs in a buffer of its own)
             from multiprocessing import shared_memory
             name = f"paris_b200_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
             try:
@@ -353,6 +353,8 @@ class SharedHostVolume:
             if flag.item() > 0:
                 self.kind = "one shared page-locked volume (POSIX shm), slabs written at their offsets"
                 self.ptr = self.array.ctypes.data + member.info.z_first * member.slice_floats * 4
+        elif world > 1:
+            self.kind = "per-rank pinned buffers (volume larger than 8 GB)"
         if self.ptr is None:
             self.ptr = member.alloc_host_slabs().ptr
 
@@ -473,9 +475,10 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         # exact kernel (the reference's arithmetic operation for operation, tests/test_gpu_parity.py)
         c = float(n_proj) / (8.0 * np.pi)
         worst = [0.0, 0.0]
-        if info.slabs == 1:
-            for z in sorted({0, max(0, my_slices // 2 - 2), max(0, my_slices - 4)}):
-                dz = min(4, my_slices - z)
+        first_dz = member.plan.slab_dz if info.slabs > 1 else my_slices   # (bands of the member's FIRST slab)
+        if True:
+            for z in sorted({0, max(0, first_dz // 2 - 2), max(0, first_dz - 4)}):
+                dz = min(4, first_dz - z)
                 got = member.device_slab(z, dz)
                 ctx.set_option("bp_kernel", 1)
                 v = ctx.volume_alloc(dims[0], dims[1], dz)
@@ -609,7 +612,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                                 "all_gather_bytes_per_step_rank0": int((world - 1) * member.my_count * px * 4),
                                 "band_rows_per_rank": [hi - lo for lo, hi in bands], "detector_rows": int(det.n_col)}
             line["parity_check"] = {"max": parity[0], "rmse": parity[1], "ok": bool(parity[0] <= 1e-4 and parity[1] <= 1e-5),
-                                    "what": "every rank: three 4-slice bands of its slab (first, middle, last slices) after "
+                                    "what": "every rank: three 4-slice bands of its (first) slab (first, middle, last slices) after "
                                             "the timed steps against the exact kernel on the rank's own gathered stack; "
                                             "max over ranks, in units of the phantom contrast"}
         if world == 1 and not args.no_cpu_baseline:
