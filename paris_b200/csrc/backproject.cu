@@ -130,6 +130,7 @@ namespace pb
         g.min_v_d = -(static_cast<double>(g.p_dim_y) * (static_cast<double>(g.l_px_y) / 2.0)) - static_cast<double>(g.delta_t);
         g.inv_l_px_y_d = 1.0 / static_cast<double>(g.l_px_y);
         g.dv_scale_d = static_cast<double>(g.l_vx_z) / static_cast<double>(g.l_px_y);
+        g.zero = 0.f;
         return g;
     }
 

@@ -20,6 +20,7 @@ namespace pb
         double min_v_d;                       // -(dim_y * l_px_y / 2) - delta_t
         double inv_l_px_y_d;                  // 1 / l_px_y
         double dv_scale_d;                    // l_vx_z / l_px_y
+        float zero;                           // 0.f that the assembler cannot see (keeps z_m * factor a rounded product)
     };
 
     struct bp_angles

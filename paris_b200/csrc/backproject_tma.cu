@@ -9,10 +9,15 @@
 //     /root/reference/src/openmp/backprojection.cpp:120-133, including the one IEEE division -- are
 //     therefore computed ONCE per column and projection by one thread, put in a shared-memory table and
 //     read back as a warp-wide broadcast, once for the NZ slices of a lane.
-//   * v(z) is evaluated in 9.23 unsigned fixed point relative to the staged box (one IMAD); its integer
-//     part is the shared-memory row, its fraction the bilinear y-weight (bit-assembled into a float, no
-//     conversion instructions).  Resolution 2^-23 detector rows -- finer than the reference's own float
-//     rounding of v at |v| ~ 1000 (ulp 6e-5).
+//   * v(z) is evaluated with the REFERENCE'S OWN FLOAT OPERATIONS (:130-133 -> :45-50: multiply by the
+//     magnification, subtract the detector's lower edge, divide by the pixel size, subtract 1/2), two slices
+//     at a time in packed f32x2 arithmetic, the IEEE division as a reciprocal multiply plus one exact-residual
+//     correction (bit-identical to the division on every value checked, scripts/check_division.py).  floor and
+//     fraction come from one round-down addition of 1.5 * 2^23: the sum's low mantissa bits ARE the row index
+//     (no conversion instruction), the y-weight is v minus the rounded value.  The kernel therefore interpolates at
+//     exactly the reference's coordinates -- round 1 carried rows in fixed point, more accurately than the
+//     reference, and was up to 1.05e-4 of the phantom contrast away from it on single voxels for that very reason
+//     (the reference rounds v to float32 after every operation: ulp 1.2e-4 rows at |v| ~ 2000).
 //   * the filtered stack is stored transposed (detector-row index v fastest), so the 32 lanes of an
 //     update read 32 nearly consecutive floats of one stack line; the tile's footprint on projection p,
 //     a BH x BV box, is fetched by ONE 3-D TMA load (cp.async.bulk.tensor) into a ring of shared-memory
@@ -47,29 +52,24 @@ namespace pb
         static constexpr int WARPS = COLS / CPW;          // one warp per group of CPW columns
         static constexpr int THREADS = 32 * WARPS;
         static constexpr int STAGE_BYTES = BH * BV * 4;
-        static constexpr int TAB_BYTES = COLS * (16 + 4 + 4);  // float4 + 2 words per column (+ 1 word with STRADDLE)
+        static constexpr int TAB_BYTES = COLS * (16 + 4);      // float4 + the valid-slice interval per column
         // table sets: two (the table of projection p + 1 is built while projection p is consumed)
         static constexpr int TABLE_SLOTS = 2;
         // shared memory of an instantiation: stages, two table sets, box origins, barriers
         static constexpr size_t smem(bool straddle)
         {
-            return size_t(STAGES) * STAGE_BYTES + TABLE_SLOTS * TAB_BYTES + (straddle ? TABLE_SLOTS * COLS * 4 : 0)
-                 + kMaxBatch * 8 + STAGES * 8 + 128;
+            (void)straddle;   // (tiles anchored at the slab's first slice need nothing extra)
+            return size_t(STAGES) * STAGE_BYTES + TABLE_SLOTS * TAB_BYTES + kMaxBatch * 8 + STAGES * 8 + 128;
         }
         static constexpr size_t SMEM = smem(true);   // (scratch-size checks use the larger one)
         // 256-thread tiles rely on TWO resident CTAs per SM (228 KB of shared memory, 1 KB reserved per CTA)
         static_assert(THREADS > 256 || 2 * (smem(true) + 1024) <= 233472, "two CTAs of this tile must fit one SM");
-        // fixed point: rows are carried with a bias of BV so that they stay non-negative on boundary tiles
-        static constexpr int FRAC = 23;
-        static constexpr int ROW_SHIFT = SPLIT ? FRAC - 1 : FRAC;   // the split layout's word counts row pairs
-        static constexpr int BIAS = BV;
         static_assert(COLS % CPW == 0, "columns per warp must divide the tile");
         static_assert(CPW % TX == 0 || TX % CPW == 0, "a warp's columns must be whole or partial x-runs");
         static_assert(BV % 4 == 0, "TMA inner box extent must be a multiple of 16 bytes");
         static_assert(BH <= 256 && (SPLIT ? BV / 2 : BV) <= 256, "TMA box extents are limited to 256");
-        static_assert(2 * BV + 32 < (1 << (32 - ROW_SHIFT)), "biased rows must fit the integer bits of the fixed-point word");
         static_assert(STAGE_BYTES % 128 == 0, "stages must keep the 128-byte TMA destination alignment");
-        static_assert(!SPLIT || (BV % 8 == 0 && BIAS % 2 == 0), "parity planes: even bias, 16-byte plane rows");
+        static_assert(!SPLIT || BV % 8 == 0, "parity planes: 16-byte plane rows");
     };
 
     struct box_origin   // 8 bytes per projection of the batch
@@ -172,6 +172,21 @@ namespace pb
     {
         uint64_t d;
         asm("add.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+        return d;
+    }
+
+    // round towards minus infinity (FADD2.RM)
+    __device__ __forceinline__ uint64_t add2_rm(uint64_t a, uint64_t b)
+    {
+        uint64_t d;
+        asm("add.rm.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b));
+        return d;
+    }
+
+    __device__ __forceinline__ uint64_t fma2_rm(uint64_t a, uint64_t b, uint64_t c)
+    {
+        uint64_t d;
+        asm("fma.rm.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c));
         return d;
     }
 
@@ -287,75 +302,80 @@ namespace pb
         return static_cast<uint32_t>(min(lo, 255)) | (static_cast<uint32_t>(count) << 8);
     }
 
-    // The four samples of one voxel update and its y-weight (weight of q?2 against q?1).
-    struct update_samples
+    // 1.5 * 2^23: adding it (rounding down) to a row -2^22 < v < 2^22 leaves floor(v) in the low mantissa bits
+    constexpr uint32_t kMagicBits = 0x4B400000u;
+
+    // per-launch constants of the row arithmetic, packed for the two slices of a pair
+    struct row_consts
     {
-        float q11, q12, q21, q22, fy;   // fy = weight of q?2 against q?1
+        uint64_t neg_min_v2;   // -(min_v): (coord - min) of src/openmp/backprojection.cpp:49 as an addition
+        uint64_t inv_px2;      // RN(1 / l_px_y)
+        uint64_t neg_px2;      // -l_px_y
+        uint64_t neg_half2, half2, magic2, neg_magic2, neg_one2, neg_two2;
+        uint64_t zero2;        // a zero the assembler cannot see: z_m * factor + zero stays a ROUNDED product (ptxas fuses
+                               // mul.rn.f32x2 + add.rn.f32x2 into one FFMA2, which would skip the reference's rounding)
     };
 
+    // The four samples of one voxel update.  `tb` = bits of magic + floor(v); `base` = the staged column's address
+    // minus the box origin's share (see the table builder), so that the row index needs no subtraction here.
+    struct update_samples
+    {
+        float q11, q12, q21, q22;   // q?1: first row of the pair the layout fetches first, q?2: the other one
+    };
+
+    // plain layout: rows r, r + 1 are neighbours in the staged column; q?1 = row r, q?2 = row r + 1
     template <class CFG>
-    __device__ __forceinline__ update_samples fetch(uint32_t base, uint32_t vrow, uint32_t frac_mask, uint32_t one_bits)
+    __device__ __forceinline__ update_samples fetch_plain(uint32_t base, uint32_t tb)
     {
         update_samples u;
-        if(!CFG::SPLIT)
-        {
-            const uint32_t row = vrow >> CFG::FRAC;                               // biased row inside the box
-            u.fy = __uint_as_float(and_or(vrow, frac_mask, one_bits)) - 1.0f;
-            const uint32_t addr = base + 4u * row;
-            u.q11 = lds_f32(addr);
-            u.q12 = lds_f32(addr + 4);
-            u.q21 = lds_f32(addr + 4 * CFG::BV);
-            u.q22 = lds_f32(addr + 4 * CFG::BV + 4);
-        }
-        else
-        {
-            // Rows r and r+1 are one even and one odd row.  With r = 2k + p (p = parity):
-            //   odd  row sits in the odd plane at pair index k,
-            //   even row sits in the even plane at pair index k + p,
-            // and the odd row's weight is fy for p = 0 (it is row r+1), 1 - fy for p = 1 (it is row r), i.e.
-            // 1 - |t - 1| with t = p + fy the position inside the pair.  The fixed-point word counts ROW PAIRS
-            // here (k.t/2), so that t/2 is its fraction.  Across a warp both planes are read with (nearly)
-            // unit stride.  Here q?1 = even row, q?2 = odd row.
-            const uint32_t par4 = (vrow >> (CFG::FRAC - 3)) & 4u;                 // 4 * p
-            // base + 4 * k: shift-and-add (one LEA.HI), then the two fraction bits that came along are cleared
-            const uint32_t a_odd = (base + (vrow >> (CFG::FRAC - 2))) & ~3u;      // base points at the odd plane
-            const uint32_t a_even = a_odd + par4;
-            const float f1 = __uint_as_float(and_or(vrow, frac_mask, one_bits));  // 1 + t/2
-            u.fy = 1.0f - fabsf(fmaf(2.0f, f1, -3.0f));                           // 1 - |t - 1|
-            u.q11 = lds_f32(a_even - 4 * CFG::BVH);
-            u.q21 = lds_f32(a_even - 4 * CFG::BVH + 4 * CFG::BV);
-            u.q12 = lds_f32(a_odd);
-            u.q22 = lds_f32(a_odd + 4 * CFG::BV);
-        }
+        const uint32_t addr = base + (tb << 2);
+        u.q11 = lds_f32(addr);
+        u.q12 = lds_f32(addr + 4);
+        u.q21 = lds_f32(addr + 4 * CFG::BV);
+        u.q22 = lds_f32(addr + 4 * CFG::BV + 4);
         return u;
     }
 
-    // MIXED: the tile has voxels on both sides of the detector border (per-slice validity from the table);
-    // CLAMP: additionally the box may not cover the tile's rows (never the case for launches that passed the
-    // host-side footprint check; kept as the safe path)
-    // STRADDLE: the tile is anchored at the slab's own first slice and may cross one row anchor; slices beyond it
-    // (bit 2j / 2j+1 of `beyond` for the two slices of pair j) take the row word of the second anchor from tab_d.
-    template <class CFG, bool MIXED, bool CLAMP = false, bool STRADDLE = false>
+    // split layout: rows r = 2k + p and r + 1 are one even and one odd row; the odd one sits in the odd plane at pair
+    // index k = floor(v / 2), the even one in the even plane at k + p = round(v / 2).  q?1 = EVEN row, q?2 = ODD row
+    // whatever p is: every load instruction then reads ONE plane for all 32 lanes (lanes whose rows differ in parity
+    // would otherwise hop between planes inside one instruction and collide).  tb_odd / tb_even = magic bits + those
+    // two pair indices, straight from two additions of the magic number (round down / round to nearest): no shift,
+    // no mask, no parity test.
+    template <class CFG>
+    __device__ __forceinline__ update_samples fetch_split(uint32_t base_even, uint32_t tb_even, uint32_t tb_odd)
+    {
+        update_samples u;
+        const uint32_t a_even = base_even + (tb_even << 2);
+        const uint32_t a_odd = base_even + (tb_odd << 2);          // (+ the odd plane's offset, an immediate below)
+        u.q11 = lds_f32(a_even);
+        u.q21 = lds_f32(a_even + 4 * CFG::BV);
+        u.q12 = lds_f32(a_odd + 4 * CFG::BVH);
+        u.q22 = lds_f32(a_odd + 4 * CFG::BVH + 4 * CFG::BV);
+        return u;
+    }
+
+    // MIXED: the tile has voxels on both sides of the detector border: per-slice validity from the table, and row
+    // indices are kept inside the staged box (a slice whose row lies outside the detector may lie outside the box as
+    // well; its value is discarded by the validity select).
+    template <class CFG, bool MIXED>
     __device__ __forceinline__ void consume(uint64_t (&acc)[CFG::CPW][CFG::NZ / 2], const float4* __restrict__ tab_a,
-                                            const float* __restrict__ tab_b, const uint32_t* __restrict__ tab_c,
-                                            const uint32_t* __restrict__ tab_d, uint32_t beyond,
-                                            int col0, uint32_t lane, uint32_t lane_z)
+                                            const uint32_t* __restrict__ tab_c, const uint64_t (&zm)[CFG::NZ / 2],
+                                            const row_consts& rc, uint32_t ct, int col0, uint32_t lane)
     {
         static_assert(CFG::NZ % 2 == 0, "the slices of a lane are processed as packed f32x2 pairs (l + 64j, l + 64j + 32)");
-        // kept in registers so the fraction -> float assembly is a single three-input LOP3
-        uint32_t frac_mask = (1u << CFG::FRAC) - 1u, one_bits = 0x3f800000u;
-        asm volatile("" : "+r"(frac_mask), "+r"(one_bits));
         const uint64_t minus_one = pack2(-1.f, -1.f);
         #pragma unroll
         for(int i = 0; i < CFG::CPW; ++i)
         {
-            // {stage address of (column x1, row -BIAS), v_base (fixed point, biased), dv (fixed point), w*(1-fx)},
-            // w*fx, valid slices (first | count << 8; boundary tiles only): read ONCE for the NZ slices of the lane
+            // {address of the staged column x1, magnification d_sd / (s + d_so), w*(1-fx), w*fx}, valid slices (first |
+            // count << 8; boundary tiles only): read ONCE for the NZ slices of the lane
             const float4 ea = tab_a[col0 + i];
-            const float wb = tab_b[col0 + i];
-            const uint32_t base = __float_as_uint(ea.x);
-            const uint32_t dv = __float_as_uint(ea.z);
-            const uint64_t wa2 = pack2(ea.w, ea.w), wb2 = pack2(wb, wb);
+            const uint32_t colbase = __float_as_uint(ea.x);
+            // (an index arrives as magic bits + its value; the box origin and the magic are taken off the base once:
+            // ct = magic bits + the box's first row, or + its first row PAIR for the split layout)
+            const uint32_t base = colbase - 4u * ct;
+            const uint64_t f2 = pack2(ea.y, ea.y), wa2 = pack2(ea.z, ea.z), wb2 = pack2(ea.w, ea.w);
             uint32_t rel = 0, count = 0;
             if(MIXED)
             {
@@ -364,36 +384,74 @@ namespace pb
                 rel = lane - (vs & 0xffu);
                 count = vs >> 8;
             }
-            // slice `lane` (lane_z counts from the row anchor); with STRADDLE the anchor's row word is added per slice
-            uint32_t v0 = STRADDLE ? dv * lane_z : dv * lane_z + __float_as_uint(ea.y);
-            uint32_t vb_second = 0;
-            if(STRADDLE)
-                vb_second = tab_d[col0 + i];
             #pragma unroll
             for(int j = 0; j < CFG::NZ / 2; ++j)
             {
-                uint32_t v1 = v0 + (dv << 5);                    // slice `lane + 64j + 32`: 32 steps of dv further
-                uint32_t va = v0;
-                if(STRADDLE)
+                // the reference's float arithmetic of the detector row (src/openmp/backprojection.cpp:130-133, :45-50),
+                // both slices of the pair at once:  v = (z_m * factor - min_v) / l_px - 1/2
+                const uint64_t num = add2(fma2(zm[j], f2, rc.zero2), rc.neg_min_v2);
+                const uint64_t q0 = mul2(num, rc.inv_px2);
+                const uint64_t q = fma2(fma2(q0, rc.neg_px2, num), rc.inv_px2, q0);   // == num / l_px (IEEE), see header
+                const uint64_t v = add2(q, rc.neg_half2);
+                uint64_t wy;                 // weight of q?2 against q?1
+                update_samples s0, s1;
+                uint32_t b = base;
+                if(CFG::SPLIT)
                 {
-                    va += ((beyond >> (2 * j)) & 1u) ? vb_second : __float_as_uint(ea.y);
-                    v1 += ((beyond >> (2 * j + 1)) & 1u) ? vb_second : __float_as_uint(ea.y);
+                    // pair indices: k = floor(v/2) holds the odd row, round(v/2) = k + p the even one (a tie -- v an odd
+                    // integer -- may round either way: the even row's weight is then exactly 0).  With u = v - 2k in
+                    // [0, 2) the EVEN row's weight is |u - 1| whichever of the two rows comes first, the odd row's 1 - |u - 1|.
+                    // (v/2 is exact, so the fused multiply-adds round exactly like an addition of v/2 would)
+                    const uint64_t t_odd = fma2_rm(v, rc.half2, rc.magic2);            // magic + floor(v/2)
+                    const uint64_t t_even = fma2(v, rc.half2, rc.magic2);              // magic + round(v/2)
+                    const uint64_t um1 = add2(fma2(add2(t_odd, rc.neg_magic2), rc.neg_two2, v), rc.neg_one2);   // u - 1, exactly
+                    float o0, o1, e0, e1, w0, w1;
+                    unpack2(t_odd, o0, o1);
+                    unpack2(t_even, e0, e1);
+                    unpack2(um1, w0, w1);
+                    uint32_t to0 = __float_as_uint(o0), to1 = __float_as_uint(o1);
+                    uint32_t te0 = __float_as_uint(e0), te1 = __float_as_uint(e1);
+                    if(MIXED)
+                    {
+                        // box-relative pair indices, kept inside the box
+                        to0 = static_cast<uint32_t>(min(max(static_cast<int>(to0 - ct), 0), CFG::BVH - 1));
+                        to1 = static_cast<uint32_t>(min(max(static_cast<int>(to1 - ct), 0), CFG::BVH - 1));
+                        te0 = static_cast<uint32_t>(min(max(static_cast<int>(te0 - ct), 0), CFG::BVH - 1));
+                        te1 = static_cast<uint32_t>(min(max(static_cast<int>(te1 - ct), 0), CFG::BVH - 1));
+                        b = colbase;
+                    }
+                    s0 = fetch_split<CFG>(b, te0, to0);
+                    s1 = fetch_split<CFG>(b, te1, to1);
+                    // d = g_odd + |u - 1| * (g_even - g_odd): swap the roles so that the common lerp below applies
+                    wy = pack2(fabsf(w0), fabsf(w1));
+                    float tmp;
+                    tmp = s0.q11; s0.q11 = s0.q12; s0.q12 = tmp;
+                    tmp = s0.q21; s0.q21 = s0.q22; s0.q22 = tmp;
+                    tmp = s1.q11; s1.q11 = s1.q12; s1.q12 = tmp;
+                    tmp = s1.q21; s1.q21 = s1.q22; s1.q22 = tmp;
                 }
-                if(CLAMP)
+                else
                 {
-                    // rows may lie outside the staged box: keep the address inside, the value is discarded below
-                    const uint32_t lo = static_cast<uint32_t>(CFG::BIAS) << CFG::ROW_SHIFT;
-                    const uint32_t hi = static_cast<uint32_t>(CFG::BIAS + CFG::BV - 2) << CFG::ROW_SHIFT;
-                    va = min(max(va, lo), hi);
-                    v1 = min(max(v1, lo), hi);
+                    const uint64_t t = add2_rm(v, rc.magic2);                          // magic + floor(v), exactly
+                    wy = fma2(add2(t, rc.neg_magic2), minus_one, v);                    // v - floor(v), exactly
+                    float t0f, t1f;
+                    unpack2(t, t0f, t1f);
+                    uint32_t tb0 = __float_as_uint(t0f), tb1 = __float_as_uint(t1f);
+                    if(MIXED)
+                    {
+                        // box-relative row, kept inside the box
+                        tb0 = static_cast<uint32_t>(min(max(static_cast<int>(tb0 - ct), 0), CFG::BV - 2));
+                        tb1 = static_cast<uint32_t>(min(max(static_cast<int>(tb1 - ct), 0), CFG::BV - 2));
+                        b = colbase;
+                    }
+                    s0 = fetch_plain<CFG>(b, tb0);
+                    s1 = fetch_plain<CFG>(b, tb1);
                 }
-                const update_samples s0 = fetch<CFG>(base, va, frac_mask, one_bits);
-                const update_samples s1 = fetch<CFG>(base, v1, frac_mask, one_bits);
-                // both slices at once: g1 = wa*q11 + wb*q21, g2 = wa*q12 + wb*q22, d = g1 + fy*(g2 - g1)
+                // both slices at once: g1 = wa*q11 + wb*q21, g2 = wa*q12 + wb*q22, d = g1 + wy*(g2 - g1)
                 // (src/openmp/backprojection.cpp:73-83 with the weight 0.5*u^2 of :147 folded into wa, wb)
                 const uint64_t g1 = fma2(wb2, pack2(s0.q21, s1.q21), mul2(wa2, pack2(s0.q11, s1.q11)));
                 const uint64_t g2 = fma2(wb2, pack2(s0.q22, s1.q22), mul2(wa2, pack2(s0.q12, s1.q12)));
-                uint64_t d = fma2(pack2(s0.fy, s1.fy), fma2(g1, minus_one, g2), g1);
+                uint64_t d = fma2(wy, fma2(g1, minus_one, g2), g1);
                 if(MIXED)
                 {
                     float d0, d1;
@@ -401,8 +459,6 @@ namespace pb
                     d = pack2((rel + 64u * j) < count ? d0 : 0.f, (rel + 64u * j + 32u) < count ? d1 : 0.f);
                 }
                 acc[i][j] = add2(acc[i][j], d);
-                if(j + 1 < CFG::NZ / 2)
-                    v0 += dv << 6;                               // next pair of slices: 64 steps of dv further
             }
         }
     }
@@ -417,10 +473,8 @@ namespace pb
         unsigned char* stage_mem = smem;                                                   // STAGES x BH x BV floats
         float4* tab_a = reinterpret_cast<float4*>(smem + size_t(CFG::STAGES) * CFG::STAGE_BYTES);
         constexpr int TS = CFG::TABLE_SLOTS;
-        float* tab_b = reinterpret_cast<float*>(tab_a + TS * CFG::COLS);
-        uint32_t* tab_c = reinterpret_cast<uint32_t*>(tab_b + TS * CFG::COLS);
-        uint32_t* tab_d = tab_c + TS * CFG::COLS;   // (present only with STRADDLE)
-        box_origin* origin = reinterpret_cast<box_origin*>(tab_d + (STRADDLE ? TS * CFG::COLS : 0));
+        uint32_t* tab_c = reinterpret_cast<uint32_t*>(tab_a + TS * CFG::COLS);
+        box_origin* origin = reinterpret_cast<box_origin*>(tab_c + TS * CFG::COLS);
         uint64_t* bars = reinterpret_cast<uint64_t*>(reinterpret_cast<unsigned char*>(origin) + kMaxBatch * 8);
 
         const int tid = threadIdx.x;
@@ -552,39 +606,39 @@ namespace pb
             }
         }
 
+        // ---- the lane's slices: z_m exactly as the reference computes it (:39-43), packed in pairs ------------------
+        uint64_t zm[CFG::NZ / 2];
+        #pragma unroll
+        for(int j = 0; j < CFG::NZ / 2; ++j)
+            zm[j] = pack2(centered(z0 + lane + 64u * j, g.full_z, g.l_vx_z), centered(z0 + lane + 64u * j + 32u, g.full_z, g.l_vx_z));
+        row_consts rc;
+        {
+            // proj_real_coordinate (:45-50): min = -(dim * size/2) - offset, in the reference's float operations
+            const float min_v = __fsub_rn(-__fmul_rn(static_cast<float>(g.p_dim_y), g.l_px_y / 2.f), g.delta_t);
+            const float inv_px = __frcp_rn(g.l_px_y);
+            rc.neg_min_v2 = pack2(-min_v, -min_v);
+            rc.inv_px2 = pack2(inv_px, inv_px);
+            rc.neg_px2 = pack2(-g.l_px_y, -g.l_px_y);
+            rc.neg_half2 = pack2(-0.5f, -0.5f);
+            rc.magic2 = pack2(__uint_as_float(kMagicBits), __uint_as_float(kMagicBits));
+            rc.neg_magic2 = pack2(-__uint_as_float(kMagicBits), -__uint_as_float(kMagicBits));
+            rc.half2 = pack2(0.5f, 0.5f);
+            rc.neg_one2 = pack2(-1.f, -1.f);
+            rc.neg_two2 = pack2(-2.f, -2.f);
+            rc.zero2 = pack2(g.zero, g.zero);
+        }
+
         // table builder state: thread c < COLS owns tile column c
         const bool builder = tid < CFG::COLS;
         float bx_k = 0.f, by_l = 0.f;
-        double z_m0 = 0.0, z_ma = 0.0;
-        // The fixed-point rows are anchored at multiples of kRowAnchor slices in GLOBAL slice indices, not at the
-        // tile: v(z) = round(v(anchor)) + (z - anchor) * round(dv) whatever the tile height, so every tile shape
-        // (16x16x64, 16x8x64, 8x8x128) computes bit-identical voxels and slabs thinner than a tall tile remain
-        // bit-identical crops of the one-piece result.
-        constexpr uint32_t kRowAnchor = 128u;
-        static_assert(kRowAnchor % CFG::TZ == 0, "a tile crosses at most one row anchor");
-        const uint32_t z_anchor = (z0 / kRowAnchor) * kRowAnchor;
-        const uint32_t lane_z = lane + (z0 - z_anchor);
-        // slices of this lane that lie beyond the next anchor (STRADDLE only): bit 2j for slice lane + 64j, bit 2j+1
-        // for slice lane + 64j + 32
-        uint32_t beyond = 0;
-        double z_mb = 0.0;
-        if(STRADDLE)
-        {
-            const uint32_t zb_local = z_anchor + kRowAnchor - z0;   // 1 .. 128
-            #pragma unroll
-            for(int jj = 0; jj < CFG::NZ; ++jj)
-                beyond |= (lane + 32u * jj >= zb_local ? 1u : 0u) << jj;
-        }
+        double z_m0 = 0.0;
         if(builder)
         {
             bx_k = centered(x0 + tid % CFG::TX, g.full_x, g.l_vx_x);
             by_l = centered(y0 + tid / CFG::TX, g.full_y, g.l_vx_y);
             z_m0 = centered_d(z0, g.full_z, g.l_vx_z);
-            z_ma = centered_d(z_anchor, g.full_z, g.l_vx_z);
-            z_mb = centered_d(z_anchor + kRowAnchor, g.full_z, g.l_vx_z);
         }
         const uint32_t stage_base0 = smem_u32(stage_mem);
-        constexpr double kOne = static_cast<double>(1u << CFG::ROW_SHIFT);
 
         // entry of tile column `col` for projection p, into table set `slot`
         auto build = [&](int p, int col, int slot, float bx_k, float by_l) {
@@ -594,77 +648,41 @@ namespace pb
             const column_terms ct = project_column(bx_k, by_l, ang.sn[p], ang.cs[p], g);
             const float x1 = floorf(ct.h);
             const bool valid_x = x1 >= 0.f && x1 + 1.f < static_cast<float>(g.p_dim_x);
-            // A dead entry (detector column off the detector, or rows the fixed-point word cannot reach) reads row 0 of
-            // column 0 of the box with zero weights AND an empty interval of valid slices: dead entries only occur in
-            // tiles that take the MIXED path, whose select then yields an exact 0 whatever was staged there (0 * NaN
-            // from a bad pixel must not reach voxels the reference leaves untouched, src/openmp/backprojection.cpp:65-71).
-            float4 ea = make_float4(0.f, __uint_as_float(static_cast<uint32_t>(CFG::BIAS) << CFG::ROW_SHIFT),
-                                    __uint_as_float(0u), 0.f);
-            float eb = 0.f;
+            // A dead entry (detector column off the detector) reads column 0 of the box with zero weights AND an empty
+            // interval of valid slices: dead entries only occur in tiles that take the MIXED path, whose select then
+            // yields an exact 0 whatever was staged there (0 * NaN from a bad pixel must not reach voxels the reference
+            // leaves untouched, src/openmp/backprojection.cpp:65-71).
+            float4 ea = make_float4(0.f, ct.factor, 0.f, 0.f);
             uint32_t ec = 0u;                                    // no slice valid
-            uint32_t ed = static_cast<uint32_t>(CFG::BIAS) << CFG::ROW_SHIFT;   // (dead entry: same row as ea.y)
             int x1rel = 0;
             if(valid_x)
             {
                 const double fd = static_cast<double>(ct.factor);
                 const double dv = fd * g.dv_scale_d;   // l_vx_z * factor / l_px_y
-                // biased, box-relative row of the tile's first slice
-                const double vb = row_of(z_m0, fd, g) - static_cast<double>(o.v0) + static_cast<double>(CFG::BIAS);
-                const double vend = vb + dv * static_cast<double>(CFG::TZ - 1);
                 const float fx = ct.h - x1;
                 const float w = 0.5f * ct.u * ct.u;
                 ec = static_cast<uint32_t>(CFG::TZ) << 8;        // every slice valid, unless found otherwise below
                 x1rel = min(max(static_cast<int>(x1) - o.h0, 0), CFG::BH - 2);
-                ea.w = w * (1.f - fx);
-                eb = w * fx;
-                // representable in 9.23 unsigned for every slice of the tile: always, for a tile that is not
-                // skipped, when the host-side footprint check holds (the box then covers the tile's rows)
-                if(dv >= 0.0 && vb >= 0.0 && vend < static_cast<double>(2 * CFG::BV + 16))
-                {
-                    // biased row of the ANCHOR slice in fixed point (may wrap: the arithmetic is modulo 2^32 and the
-                    // rows of this tile's slices are in range), made box-relative by an exact integer shift
-                    const double va = row_of(z_ma, fd, g) + static_cast<double>(CFG::BIAS);
-                    ea.y = __uint_as_float(static_cast<uint32_t>(__double2ll_rn(va * kOne))
-                                           - (static_cast<uint32_t>(o.v0) << CFG::ROW_SHIFT));
-                    ea.z = __uint_as_float(static_cast<uint32_t>(__double2ll_rn(dv * kOne)));
-                    if(STRADDLE)
-                    {
-                        // the second anchor's row word, shifted so that the same dv * (z - first anchor) term applies
-                        const double vb2 = row_of(z_mb, fd, g) + static_cast<double>(CFG::BIAS);
-                        ed = static_cast<uint32_t>(__double2ll_rn(vb2 * kOne)) - (static_cast<uint32_t>(o.v0) << CFG::ROW_SHIFT)
-                           - __float_as_uint(ea.z) * kRowAnchor;
-                    }
-                    // detector rows of the first and last slice; one cell of slack against rounding
-                    const double first = vb + static_cast<double>(o.v0 - CFG::BIAS), last = first + dv * (CFG::TZ - 1);
-                    const bool safe = fmin(first, last) >= 1.0 && fmax(first, last) + 2.0 <= static_cast<double>(g.p_dim_y) - 1.0;
-                    if(!safe && o.all_valid == 0)
-                        ec = valid_slices<CFG::TZ>(z0, ct.factor, first, dv, g);
-                }
-                else
-                {
-                    ea.w = 0.f;         // unreachable rows: contributes nothing
-                    eb = 0.f;
-                    ec = 0u;
-                }
+                ea.z = w * (1.f - fx);
+                ea.w = w * fx;
+                // detector rows of the tile's first and last slice (affine model in double); one cell of slack
+                const double first = row_of(z_m0, fd, g), last = first + dv * (CFG::TZ - 1);
+                const bool safe = fmin(first, last) >= 1.0 && fmax(first, last) + 2.0 <= static_cast<double>(g.p_dim_y) - 1.0;
+                if(!safe && o.all_valid == 0)
+                    ec = valid_slices<CFG::TZ>(z0, ct.factor, first, dv, g);
             }
-            // plain: address of (column x1, row -BIAS), the biased row index is added as is;
-            // split: address of (column x1, odd plane, pair index -BIAS/2), 4 * (biased row >> 1) is added
+            // address of row 0 (of the box) of the staged column x1; split layout: in the even plane
             const uint32_t base = stage_base0 + static_cast<uint32_t>(p % CFG::STAGES) * CFG::STAGE_BYTES
-                                + 4u * static_cast<uint32_t>(x1rel * CFG::BV)
-                                + (CFG::SPLIT ? 4u * static_cast<uint32_t>(CFG::BVH) - 2u * static_cast<uint32_t>(CFG::BIAS)
-                                              : 0u - 4u * static_cast<uint32_t>(CFG::BIAS));
+                                + 4u * static_cast<uint32_t>(x1rel * CFG::BV);
             ea.x = __uint_as_float(base);
 #ifdef PB_BP_STATS
             atomicAdd(&g_bp_stats[3], 1ull);                                           // table entries built
             if(ec != (static_cast<uint32_t>(CFG::TZ) << 8)) atomicAdd(&g_bp_stats[4], 1ull);   // columns near the border
-            if(ea.w == 0.f && eb == 0.f) atomicAdd(&g_bp_stats[5], 1ull);              // dead columns
+            if(ea.z == 0.f && ea.w == 0.f) atomicAdd(&g_bp_stats[5], 1ull);            // dead columns
             if(o.all_valid == 0) atomicAdd(&g_bp_stats[6], 1ull);                      // entries in mixed tiles
 #endif
             tab_a[slot * CFG::COLS + col] = ea;
-            tab_b[slot * CFG::COLS + col] = eb;
             tab_c[slot * CFG::COLS + col] = ec;
-            if(STRADDLE)
-                tab_d[slot * CFG::COLS + col] = ed;
         };
 
         if(builder && count > 0)
@@ -683,18 +701,14 @@ namespace pb
 
             const box_origin o = origin[p];
             const float4* ta = tab_a + (p & 1) * CFG::COLS;
-            const float* tb = tab_b + (p & 1) * CFG::COLS;
             const uint32_t* tc = tab_c + (p & 1) * CFG::COLS;
-            const uint32_t* td = tab_d + (p & 1) * CFG::COLS;
+            // magic bits + the box's first row (split layout: first row PAIR; v0 is a multiple of 8): what an index
+            // carries beyond its place inside the box
+            const uint32_t ct = kMagicBits + static_cast<uint32_t>(CFG::SPLIT ? static_cast<int>(o.v0) / 2 : static_cast<int>(o.v0));
             if(o.all_valid == 1)
-                consume<CFG, false, false, STRADDLE>(acc, ta, tb, tc, td, beyond, col0, lane, lane_z);
+                consume<CFG, false>(acc, ta, tc, zm, rc, ct, col0, lane);
             else if(o.all_valid == 0)
-            {
-                if(o.fits)
-                    consume<CFG, true, false, STRADDLE>(acc, ta, tb, tc, td, beyond, col0, lane, lane_z);
-                else
-                    consume<CFG, true, true, STRADDLE>(acc, ta, tb, tc, td, beyond, col0, lane, lane_z);
-            }
+                consume<CFG, true>(acc, ta, tc, zm, rc, ct, col0, lane);
 
             __syncthreads(); // stage and table[p&1] are free again; table[(p+1)&1] is complete
             if(tid == 0 && p + CFG::STAGES < count)
