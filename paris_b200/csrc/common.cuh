@@ -146,6 +146,7 @@ struct paris_b200_ctx
         cudaError_t e_ = (expr);                                                                        \
         if(e_ != cudaSuccess)                                                                           \
         {                                                                                               \
+            (void)cudaGetLastError(); /* reported here: the next launch check must not see it again */  \
             pb::set_error("%s failed: %s (%s:%d)", #expr, cudaGetErrorString(e_), __FILE__, __LINE__);  \
             return e_ == cudaErrorMemoryAllocation ? PARIS_B200_ENOMEM : PARIS_B200_ECUDA;              \
         }                                                                                               \

@@ -574,6 +574,12 @@ namespace pb
         constexpr size_t twc_bytes = P::TW_SMEM ? sizeof(float2) * (3 * (2 * P::N - 8) / 4) : 0;
         const size_t smem = twc_bytes + sizeof(float2) * P::NPAD * P::PAIRS
                           + (transposed ? sizeof(float) * kStagePitch * dim_x : 0);
+        if(smem > 227u * 1024u)
+        {
+            set_error("a detector row of %u samples needs %zu bytes of shared memory in the fused filter kernel (transform of "
+                      "%d points, staging tile for the transposed slot): more than one SM has", dim_x, smem, P::N);
+            return PARIS_B200_EINVAL;
+        }
         const uint32_t items = ((dim_y + kRowsPerCta - 1) / kRowsPerCta) * count;
         // persistent grid: as many CTAs as can be resident (two per SM when threads/registers/shared memory allow)
         const uint32_t per_sm = (P::THREADS <= 256 && 2 * smem <= 220u * 1024u) ? 2u : 1u;
