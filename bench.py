@@ -316,11 +316,11 @@ class SharedHostVolume:
     volume is assembled by writing every slab at its offset).  One POSIX shared-memory segment, page-locked by every
     process; falls back to a pinned buffer of the member's own where that is not possible (then `kind` says so)."""
 
-    def __init__(self, capi, dist, rank, world, voxels, member):
+    def __init__(self, capi, dist, rank, world, voxels, member, shared, region_x):
         self.capi, self.kind, self.shm, self.registered = capi, "per-rank pinned buffers", None, False
         self.ptr = None
         ok = True
-        if world > 1 and voxels * 4 <= (8 << 30):   # (larger volumes: every member keeps its slabs in a buffer of its own)
+        if shared:   # (volumes beyond 8 GB: every member keeps its slabs in a buffer of its own)
             from multiprocessing import shared_memory
             name = f"paris_b200_bench_{os.environ.get('MASTER_PORT', '0')}_{os.getppid()}"
             try:
@@ -352,7 +352,9 @@ class SharedHostVolume:
             dist.all_reduce(flag, op=dist.ReduceOp.MIN)
             if flag.item() > 0:
                 self.kind = "one shared page-locked volume (POSIX shm), slabs written at their offsets"
-                self.ptr = self.array.ctypes.data + member.info.z_first * member.slice_floats * 4
+                self.ptr = self.array.ctypes.data + member.host_offset_bytes(region_x)
+            else:
+                raise RuntimeError("the shared host volume could not be set up (the members were configured for it)")
         elif world > 1:
             self.kind = "per-rank pinned buffers (volume larger than 8 GB)"
         if self.ptr is None:
@@ -390,7 +392,16 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     updates = voxels * n_proj
     spm = args.slabs_per_gpu if args.slabs_per_gpu else (2 if args.config == "c5" else 1)
 
-    member = GroupMember(local_rank, rank, world, det, vol, n_proj, roi=roi, slabs_per_member=spm,
+    # few slices per GPU (config 2 at N=8: 64): cut along x as well, so that every GPU keeps z-runs of >= 128 slices and
+    # with them the 8x8x128 tiles (one table entry per four updates of a lane instead of per two)
+    x_parts = args.x_parts
+    if x_parts == 0:
+        x_parts = 1
+        while x_parts < world and world % (2 * x_parts) == 0 and dims[2] * x_parts // world < 128 * spm:
+            x_parts *= 2
+    shared_volume = world > 1 and voxels * 4 <= (8 << 30)
+    member = GroupMember(local_rank, rank, world, det, vol, n_proj, roi=roi, slabs_per_member=spm, x_parts=x_parts,
+                         host_row_floats=dims[0] if shared_volume else 0,
                          whole_projections=bool(args.whole_projections),
                          exchange=capi.EXCHANGE_KERNEL if args.exchange == "kernel" else capi.EXCHANGE_COPY_ENGINE)
     if dist is not None:
@@ -401,7 +412,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     member.generate_inputs(ellipsoids(det))
     sc = np.array([angle_sin_cos(i, det) for i in range(n_proj)], dtype=np.float32)
     my_slices = info.z_count
-    slab_dims = (dims[0], dims[1], my_slices)
+    slab_dims = (info.x_count, dims[1], my_slices)
+    box_roi = member.box_roi(roi)          # (the ROI that shifts voxel indices to this member's columns)
     # stage kernels on their own (roofline legs): this member's share through the filter, all projections through the
     # backprojection into this member's slices, on ONE stream with events in between
     filt = ctx.filter_create(capi.filter_size(n), float(det.l_px_row))
@@ -419,7 +431,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         e1 = ctx.event()
         ctx.volume_clear(stage_vol, *slab_dims)
         ctx.backproject_stack(info.d_stack, 0, n_proj, sc[:, 0], sc[:, 1], stage_vol, slab_dims, info.z_first, det, vol,
-                              roi=roi, layout=info.layout)
+                              roi=box_roi, layout=info.layout)
         e2 = ctx.event()
         tf = ctx.elapsed_ms(e0, e1, destroy=False)
         tb = ctx.elapsed_ms(e1, e2, destroy=False)
@@ -481,9 +493,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                 dz = min(4, first_dz - z)
                 got = member.device_slab(z, dz)
                 ctx.set_option("bp_kernel", 1)
-                v = ctx.volume_alloc(dims[0], dims[1], dz)
-                ctx.backproject_stack(info.d_stack, 0, n_proj, sc[:, 0], sc[:, 1], v, (dims[0], dims[1], dz), info.z_first + z,
-                                      det, vol, roi=roi, layout=info.layout)
+                v = ctx.volume_alloc(info.x_count, dims[1], dz)
+                ctx.backproject_stack(info.d_stack, 0, n_proj, sc[:, 0], sc[:, 1], v, (info.x_count, dims[1], dz), info.z_first + z,
+                                      det, vol, roi=box_roi, layout=info.layout)
                 want = np.empty_like(got)
                 ctx.vol_d2h(v, want, want.size)
                 ctx.volume_free(v)
@@ -503,7 +515,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         barrier()
 
     # ---- end-to-end steps: pinned host projections -> the host volume --------------------------------------------------
-    host_vol = SharedHostVolume(capi, dist, rank, world, voxels, member) if world > 1 else None
+    host_vol = SharedHostVolume(capi, dist, rank, world, voxels, member, shared_volume, dims[0]) if world > 1 else None
     if world == 1:
         member.alloc_host_slabs()
 
@@ -548,7 +560,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         # backprojection: 4 point-fetched float samples per voxel update from shared memory
         bp_s = t_bp / args.steps / 1e3
         filt_s = t_filter / args.steps / 1e3
-        my_updates = my_slices * dims[0] * dims[1] * n_proj
+        my_updates = my_slices * info.x_count * dims[1] * n_proj
         bp_gbs = 16.0 * my_updates / bp_s / 1e9
         smem_peak = 148 * 128 * sm_mhz * 1e6 / 1e9
         filt_gbs = 8.0 * px * member.my_count / filt_s / 1e9
@@ -559,7 +571,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             "metric": "fdk_reconstruction_gups", "value": updates / (ms_step / 1e3) / 1e9, "unit": "GUPS",
             "n_gpus": world, "steps": args.steps, "warmup": args.warmup, "ms_per_step": ms_step,
             "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-            "config": {"workload": CONFIGS[args.config][3], "parallelism": f"z-slab x{world}" + (f", {spm} slabs per GPU" if spm > 1 else ""),
+            "config": {"workload": CONFIGS[args.config][3],
+                       "parallelism": (f"z-slab x{world}" if x_parts == 1 else f"{world // x_parts} z-runs x {x_parts} x-parts")
+                                      + (f", {spm} slabs per GPU" if spm > 1 else ""),
                        "l2": "inputs larger than L2 (raw + filtered stack = 48 GB at config 3)",
                        "bp_batch": 256,
                        "stack_layout": "transposed, v fastest, " + ("parity-split" if info.layout else "plain"),
@@ -650,6 +664,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--clock-interval-ms", type=int, default=100, help="NVML sampling period")
     ap.add_argument("--slabs-per-gpu", type=int, default=0, help="z-slabs every GPU streams (0: 2 for config 5, else 1)")
+    ap.add_argument("--x-parts", type=int, default=0, help="parts along x (0: automatic, keeps >= 128 slices per GPU)")
     ap.add_argument("--exchange", default="copy-engine", choices=["copy-engine", "kernel"])
     ap.add_argument("--whole-projections", action="store_true", help="exchange every detector row (an all-gather)")
     args = ap.parse_args()

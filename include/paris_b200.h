@@ -308,6 +308,12 @@ typedef struct paris_b200_group_config
     uint32_t whole_projections;           /* 1: exchange every detector row (an all-gather); 0: only the band of rows the
                                              receiving member's slabs can read */
     uint32_t exchange;                    /* PARIS_B200_EXCHANGE_* */
+    uint32_t x_parts;                     /* 0 or 1: members own whole slices (z-slabs).  n > 1 (n divides world): the region is
+                                             also cut into n equal parts along x (remainder on the last); member r owns x-part
+                                             r % n of z-run r / n.  For volumes with few slices per GPU: world / n taller
+                                             z-runs keep the 128-slice tiles */
+    uint32_t host_row_floats;             /* floats from one row to the next in the host memory handed to group_begin: 0 = the
+                                             member's own box, contiguous; region_x = a box inside one region-wide volume */
 } paris_b200_group_config;
 
 typedef struct paris_b200_group_info_t
@@ -315,6 +321,7 @@ typedef struct paris_b200_group_info_t
     uint32_t my_projections;              /* how many projections this member uploads and filters */
     uint32_t rounds, slabs;
     uint32_t z_first, z_count;            /* this member's slices of the region */
+    uint32_t x_first, x_count;            /* this member's columns of the region (everything unless x_parts > 1) */
     uint32_t region_x, region_y, region_z;
     uint32_t band_lo, band_hi;            /* detector rows [lo, hi) this member receives from its peers */
     uint32_t layout, pitch;               /* stack layout (PARIS_B200_LAYOUT_*) and line pitch in floats */
@@ -337,7 +344,8 @@ typedef struct paris_b200_group_plan_t
     uint32_t region_x, region_y, region_z;   /* the reconstructed region */
     uint32_t region_z0;                       /* its first slice in the full volume */
     uint32_t layout, pitch;                   /* stack layout and line pitch (floats) */
-    uint32_t slabs_total, slab_dz, slab_remainder;   /* world * slabs_per_member slabs of slab_dz slices, remainder on the last */
+    uint32_t slabs_total, slab_dz, slab_remainder;   /* (world / x_parts) * slabs_per_member slabs of slab_dz slices, remainder on the last */
+    uint32_t x_parts, x_dx, x_remainder;              /* x_parts parts of x_dx columns, remainder on the last */
     uint32_t rounds;
     uint32_t round_first[PARIS_B200_GROUP_MAX_ROUNDS], round_count[PARIS_B200_GROUP_MAX_ROUNDS];
     uint32_t band_lo[PARIS_B200_GROUP_MAX_MEMBERS], band_hi[PARIS_B200_GROUP_MAX_MEMBERS];   /* rows [lo, hi) member k receives */

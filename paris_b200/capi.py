@@ -59,20 +59,21 @@ class GroupConfig(C.Structure):
                 ("enable_roi", C.c_int32), ("roi", Roi), ("n_proj", C.c_uint32), ("angles_deg", C.POINTER(C.c_float)),
                 ("slabs_per_member", C.c_uint32), ("stream_slabs", C.c_uint32), ("sample_type", C.c_uint32),
                 ("first_round", C.c_uint32), ("max_round", C.c_uint32), ("whole_projections", C.c_uint32),
-                ("exchange", C.c_uint32)]
+                ("exchange", C.c_uint32), ("x_parts", C.c_uint32), ("host_row_floats", C.c_uint32)]
 
 
 class GroupPlan(C.Structure):
     _fields_ = [("region_x", C.c_uint32), ("region_y", C.c_uint32), ("region_z", C.c_uint32), ("region_z0", C.c_uint32),
                 ("layout", C.c_uint32), ("pitch", C.c_uint32), ("slabs_total", C.c_uint32), ("slab_dz", C.c_uint32),
-                ("slab_remainder", C.c_uint32), ("rounds", C.c_uint32),
+                ("slab_remainder", C.c_uint32), ("x_parts", C.c_uint32), ("x_dx", C.c_uint32), ("x_remainder", C.c_uint32),
+                ("rounds", C.c_uint32),
                 ("round_first", C.c_uint32 * GROUP_MAX_ROUNDS), ("round_count", C.c_uint32 * GROUP_MAX_ROUNDS),
                 ("band_lo", C.c_uint32 * GROUP_MAX_MEMBERS), ("band_hi", C.c_uint32 * GROUP_MAX_MEMBERS)]
 
 
 class GroupInfo(C.Structure):
     _fields_ = [("my_projections", C.c_uint32), ("rounds", C.c_uint32), ("slabs", C.c_uint32), ("z_first", C.c_uint32),
-                ("z_count", C.c_uint32), ("region_x", C.c_uint32), ("region_y", C.c_uint32), ("region_z", C.c_uint32),
+                ("z_count", C.c_uint32), ("x_first", C.c_uint32), ("x_count", C.c_uint32), ("region_x", C.c_uint32), ("region_y", C.c_uint32), ("region_z", C.c_uint32),
                 ("band_lo", C.c_uint32), ("band_hi", C.c_uint32), ("layout", C.c_uint32), ("pitch", C.c_uint32),
                 ("d_stack", C.c_void_p), ("slab_buffers", C.c_uint32), ("d_first_slab", C.c_void_p),
                 ("bytes_pushed", C.c_uint64), ("ctx", C.c_void_p), ("filter_ctx", C.c_void_p), ("memops", C.c_uint32)]
@@ -458,7 +459,8 @@ class Context:
 
 def group_config(rank: int, world: int, det: DetectorGeometry, vol_full: VolumeGeometry, n_proj: int, roi: Roi | None = None,
                  slabs_per_member: int = 1, stream_slabs: bool = False, first_round: int = 0, max_round: int = 0,
-                 whole_projections: bool = False, exchange: int = EXCHANGE_COPY_ENGINE, angles_deg=None) -> GroupConfig:
+                 whole_projections: bool = False, exchange: int = EXCHANGE_COPY_ENGINE, angles_deg=None, x_parts: int = 1,
+                 host_row_floats: int = 0) -> GroupConfig:
     cfg = GroupConfig()
     cfg.rank, cfg.world, cfg.det, cfg.vol_full, cfg.n_proj = rank, world, det, vol_full, n_proj
     cfg.enable_roi = int(roi is not None)
@@ -467,6 +469,7 @@ def group_config(rank: int, world: int, det: DetectorGeometry, vol_full: VolumeG
     cfg.slabs_per_member, cfg.stream_slabs, cfg.sample_type = slabs_per_member, int(stream_slabs), SAMPLES_F32
     cfg.first_round, cfg.max_round = first_round, max_round
     cfg.whole_projections, cfg.exchange = int(whole_projections), exchange
+    cfg.x_parts, cfg.host_row_floats = x_parts, host_row_floats
     if angles_deg is not None:
         a = np.ascontiguousarray(angles_deg, dtype=np.float32)
         assert a.size == n_proj

@@ -706,10 +706,14 @@ static int run_pending_filter(paris_b200_ctx* ctx);
 // and the result is bit-identical to the one-piece launch.  Returns with the host copy complete.
 // wait == false: returns with the last chunk's copy still in flight on the copy stream (group.cu overlaps it with the
 // next slab's backprojection).
+// h_row_floats: floats from one row of the host destination to the next (0 or v_dim_x: contiguous; larger: the slab is
+// a box inside a wider host volume).
 int pb::backproject_and_download(paris_b200_ctx* ctx, const float* d_stack, size_t slot_floats, uint32_t pitch,
                                  uint32_t first, uint32_t count, const float* sn, const float* cs, const bp_target& t,
-                                 uint32_t layout, float* h_dst, bool wait)
+                                 uint32_t layout, float* h_dst, bool wait, uint32_t h_row_floats)
 {
+    const size_t h_row = h_row_floats > t.v_dim_x ? h_row_floats : t.v_dim_x;
+    const size_t h_slice = h_row * t.v_dim_y;
     const uint32_t off0 = (t.enable_roi ? t.roi.z1 : 0u) + t.v_offset;
     const size_t slice = static_cast<size_t>(t.v_dim_x) * t.v_dim_y;
     uint32_t step = 64u;
@@ -732,8 +736,13 @@ int pb::backproject_and_download(paris_b200_ctx* ctx, const float* d_stack, size
         }
         PB_CUDA(cudaEventRecord(ctx->scratch_ev, ctx->compute));
         PB_CUDA(cudaStreamWaitEvent(ctx->copy, ctx->scratch_ev, 0));
-        PB_CUDA(cudaMemcpyAsync(h_dst + static_cast<size_t>(z) * slice, c.d_vol, static_cast<size_t>(end - z) * slice * sizeof(float),
-                                cudaMemcpyDeviceToHost, ctx->copy));
+        if(h_row == t.v_dim_x)
+            PB_CUDA(cudaMemcpyAsync(h_dst + static_cast<size_t>(z) * slice, c.d_vol, static_cast<size_t>(end - z) * slice * sizeof(float),
+                                    cudaMemcpyDeviceToHost, ctx->copy));
+        else
+            PB_CUDA(cudaMemcpy2DAsync(h_dst + static_cast<size_t>(z) * h_slice, h_row * sizeof(float), c.d_vol,
+                                      static_cast<size_t>(t.v_dim_x) * sizeof(float), static_cast<size_t>(t.v_dim_x) * sizeof(float),
+                                      static_cast<size_t>(end - z) * t.v_dim_y, cudaMemcpyDeviceToHost, ctx->copy));
         z = end;
     }
     if(wait)
@@ -756,7 +765,7 @@ extern "C" int paris_b200_vol_d2h(paris_b200_ctx* ctx, const float* d_src, float
         const uint32_t n = static_cast<uint32_t>(ctx->pending);
         ctx->pending = 0;
         return backproject_and_download(ctx, ctx->stack, ctx->stack_slot_floats, ctx->stack_pitch, 0u, n, ctx->pend_sin,
-                                        ctx->pend_cos, t, ctx->stack_layout, h_dst, true);
+                                        ctx->pend_cos, t, ctx->stack_layout, h_dst, true, 0u);
     }
     PB_TRY(paris_b200_flush(ctx));
     PB_CUDA(cudaMemcpyAsync(h_dst, d_src, n_voxels * sizeof(float), cudaMemcpyDeviceToHost, ctx->compute));
@@ -1299,7 +1308,7 @@ extern "C" int paris_b200_backproject_stack_d2h(paris_b200_ctx* ctx, const float
     t.delta_t_mm = det->delta_t * det->l_px_col;
     const uint32_t pitch = stack_pitch_for(det->n_col);
     const size_t slot_floats = static_cast<size_t>(pitch) * det->n_row;
-    return backproject_and_download(ctx, d_stack, slot_floats, pitch, first, count, sin_phi, cos_phi, t, layout, h_dst, true);
+    return backproject_and_download(ctx, d_stack, slot_floats, pitch, first, count, sin_phi, cos_phi, t, layout, h_dst, true, 0u);
 }
 
 extern "C" int paris_b200_phantom_project(paris_b200_ctx* ctx, const double* ellipsoids, uint32_t n_ellipsoids,

@@ -218,5 +218,5 @@ namespace pb
     // Backproject `count` stack slots into the target and bring the volume to the host, z-chunk by z-chunk (api.cu)
     int backproject_and_download(paris_b200_ctx* ctx, const float* d_stack, size_t slot_floats, uint32_t pitch, uint32_t first,
                                  uint32_t count, const float* sn, const float* cs, const bp_target& t, uint32_t layout,
-                                 float* h_dst, bool wait);
+                                 float* h_dst, bool wait, uint32_t h_row_floats);
 }

@@ -141,6 +141,8 @@ struct paris_b200_group
     paris_b200_filter* filter = nullptr;
 
     uint32_t region_x = 0, region_y = 0, region_z = 0, region_z0 = 0;   // region dims; first slice in the full volume
+    uint32_t x_first = 0, x_count = 0;          // this member's columns of the region
+    uint32_t host_row = 0;                      // floats per row of the host destination
     uint32_t layout = 0, pitch = 0;
     size_t slot_floats = 0, px = 0;
     std::vector<round_t> rounds;
@@ -289,7 +291,7 @@ namespace
     {
         bp_target t{};
         t.d_vol = d_vol;
-        t.v_dim_x = g->region_x;
+        t.v_dim_x = g->x_count;
         t.v_dim_y = g->region_y;
         t.v_dim_z = s.dz;
         t.v_offset = s.z_first;
@@ -298,6 +300,15 @@ namespace
         t.enable_roi = g->cfg.enable_roi ? 1 : 0;
         if(t.enable_roi)
             t.roi = g->cfg.roi;
+        if(g->x_first != 0u)
+        {
+            // a member that owns only part of the columns: the kernel shifts voxel indices by (roi.x1, roi.y1, roi.z1)
+            // (src/openmp/backprojection.cpp:105-109), so the part is one more shift of x
+            if(!t.enable_roi)
+                t.roi = paris_b200_roi{0u, 0u, 0u, 0u, 0u, 0u};
+            t.enable_roi = 1;
+            t.roi.x1 += g->x_first;
+        }
         t.delta_s_mm = g->cfg.det.delta_s * g->cfg.det.l_px_row;   // src/backprojection.cpp:49-50
         t.delta_t_mm = g->cfg.det.delta_t * g->cfg.det.l_px_col;
         return t;
@@ -385,7 +396,17 @@ extern "C" int paris_b200_group_plan(const paris_b200_group_config* cfg, paris_b
     plan->region_z0 = cfg->enable_roi ? cfg->roi.z1 : 0u;
     const uint32_t world = static_cast<uint32_t>(cfg->world);
     const uint32_t spr = std::max(1u, cfg->slabs_per_member);
-    const uint32_t total = world * spr;
+    const uint32_t xp = std::max(1u, cfg->x_parts);
+    if(world % xp != 0u || xp > region.dim_x)
+    {
+        set_error("x_parts = %u must divide the %u members and not exceed the region's %u columns", xp, world, region.dim_x);
+        return PARIS_B200_EINVAL;
+    }
+    const uint32_t world_z = world / xp;           // members along z
+    const uint32_t total = world_z * spr;
+    plan->x_parts = xp;
+    plan->x_dx = region.dim_x / xp;
+    plan->x_remainder = region.dim_x % xp;
     if(total > region.dim_z)
     {
         set_error("%u slabs for %u slices: every slab needs at least one slice", total, region.dim_z);
@@ -423,8 +444,9 @@ extern "C" int paris_b200_group_plan(const paris_b200_group_config* cfg, paris_b
     // bands: the detector rows each member's slabs can read
     for(uint32_t k = 0; k < world; ++k)
     {
-        const uint32_t zf = k * spr * plan->slab_dz;
-        const uint32_t zn = (k == world - 1u) ? region.dim_z - zf : spr * plan->slab_dz;
+        const uint32_t kz = k / xp;                // (members that share a z-run receive the same band)
+        const uint32_t zf = kz * spr * plan->slab_dz;
+        const uint32_t zn = (kz == world_z - 1u) ? region.dim_z - zf : spr * plan->slab_dz;
         const band_t b = cfg->whole_projections ? band_t{0u, plan->pitch}
                                                 : band_of(*cfg, region.dim_x, region.dim_y, plan->region_z0 + zf, zn, plan->pitch);
         plan->band_lo[k] = b.lo;
@@ -502,9 +524,18 @@ extern "C" int paris_b200_group_create(int device, const paris_b200_group_config
     const uint32_t world = static_cast<uint32_t>(cfg->world), me = static_cast<uint32_t>(cfg->rank);
     const uint32_t spr = std::max(1u, cfg->slabs_per_member);
     const uint32_t total = plan.slabs_total;
+    const uint32_t xp = plan.x_parts, mz = me / xp, mx = me % xp;
+    g->x_first = mx * plan.x_dx;
+    g->x_count = plan.x_dx + (mx == xp - 1u ? plan.x_remainder : 0u);
+    g->host_row = cfg->host_row_floats ? cfg->host_row_floats : g->x_count;
+    if(g->host_row < g->x_count)
+    {
+        set_error("host_row_floats = %u is less than the member's %u columns", cfg->host_row_floats, g->x_count);
+        return fail(PARIS_B200_EINVAL);
+    }
     for(uint32_t s = 0; s < spr; ++s)
     {
-        const uint32_t id = me * spr + s;
+        const uint32_t id = mz * spr + s;
         // src/main.cpp:96, src/make_volume.cpp:32-34
         g->slabs.push_back(slab_t{id * plan.slab_dz, plan.slab_dz + (id == total - 1u ? plan.slab_remainder : 0u)});
     }
@@ -572,7 +603,7 @@ extern "C" int paris_b200_group_create(int device, const paris_b200_group_config
         for(uint32_t s = b; s < spr; s += n_buf)
             need = std::max(need, g->slabs[s].dz);
         float* v = nullptr;
-        PB_GCUDA(cudaMalloc(reinterpret_cast<void**>(&v), static_cast<size_t>(g->region_x) * g->region_y * need * sizeof(float)));
+        PB_GCUDA(cudaMalloc(reinterpret_cast<void**>(&v), static_cast<size_t>(g->x_count) * g->region_y * need * sizeof(float)));
         g->vol.push_back(v);
         cudaEvent_t e = nullptr;
         PB_GCUDA(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
@@ -749,6 +780,8 @@ extern "C" int paris_b200_group_info(const paris_b200_group* g, paris_b200_group
     info->slabs = static_cast<uint32_t>(g->slabs.size());
     info->z_first = g->slabs.front().z_first;
     info->z_count = g->slabs.back().z_first + g->slabs.back().dz - g->slabs.front().z_first;
+    info->x_first = g->x_first;
+    info->x_count = g->x_count;
     info->region_x = g->region_x;
     info->region_y = g->region_y;
     info->region_z = g->region_z;
@@ -809,7 +842,7 @@ extern "C" int paris_b200_group_step_open(paris_b200_group* g, float* h_slabs)
     paris_b200_ctx* fctx = g->fctx;
     const uint32_t world = static_cast<uint32_t>(g->cfg.world), me = static_cast<uint32_t>(g->cfg.rank);
     const uint32_t step = g->steps;            // steps completed before this one
-    const size_t slice = static_cast<size_t>(g->region_x) * g->region_y;
+    const size_t slice = static_cast<size_t>(g->x_count) * g->region_y;
 
     // ---- write-after-read guards: the stack slots are rewritten ------------------------------------------------
     // my own previous backprojections have read my slots; every peer's must have read what I am about to push
@@ -921,7 +954,7 @@ extern "C" int paris_b200_group_step_round(paris_b200_group* g, uint32_t rd, con
         const bp_target t = target_of(g, s0, g->vol[0]);
         PB_TRY(backproject_and_download(ctx, g->stack, g->slot_floats, g->pitch, g->rounds[rd].first, g->rounds[rd].count,
                                         g->sn.data() + g->rounds[rd].first, g->cs.data() + g->rounds[rd].first, t,
-                                        g->layout, g->step_h_slabs, false));
+                                        g->layout, g->step_h_slabs, false, g->host_row));
         PB_CUDA(cudaEventRecord(g->slab_down[0], ctx->copy));
         g->slab_down_valid[0] = true;
     }
@@ -958,7 +991,8 @@ extern "C" int paris_b200_group_step_finish(paris_b200_group* g)
     paris_b200_ctx* ctx = g->ctx;
     const uint32_t world = static_cast<uint32_t>(g->cfg.world), me = static_cast<uint32_t>(g->cfg.rank);
     const uint32_t step = g->steps;
-    const size_t slice = static_cast<size_t>(g->region_x) * g->region_y;
+    const size_t slice = static_cast<size_t>(g->x_count) * g->region_y;
+    const size_t h_slice = static_cast<size_t>(g->host_row) * g->region_y;
     float* h_slabs = g->step_h_slabs;
     for(uint32_t s = 1; s < g->slabs.size(); ++s)
     {
@@ -977,7 +1011,7 @@ extern "C" int paris_b200_group_step_finish(paris_b200_group* g)
             const bp_target t = target_of(g, sl, g->vol[b]);
             PB_TRY(backproject_and_download(ctx, g->stack, g->slot_floats, g->pitch, head, n_proj - head, g->sn.data() + head,
                                             g->cs.data() + head, t, g->layout,
-                                            h_slabs + slice * (sl.z_first - g->slabs[0].z_first), false));
+                                            h_slabs + h_slice * (sl.z_first - g->slabs[0].z_first), false, g->host_row));
             PB_CUDA(cudaEventRecord(g->slab_down[b], ctx->copy));
             g->slab_down_valid[b] = true;
         }

@@ -40,7 +40,7 @@ class GroupMember:
                  n_proj: int, roi: capi.Roi | None = None, **options):
         """vol: the FULL volume geometry; roi: the reconstructed box (default: the whole volume); options: the
         remaining fields of capi.group_config (slabs_per_member, stream_slabs, first_round, max_round,
-        whole_projections, exchange, angles_deg)."""
+        whole_projections, exchange, angles_deg, x_parts, host_row_floats)."""
         self.det, self.vol, self.n_proj, self.rank, self.world, self.device = det, vol, n_proj, rank, world, device
         self.cfg = capi.group_config(rank, world, det, vol, n_proj, roi=roi, **options)
         self.plan = capi.group_plan(self.cfg)
@@ -50,7 +50,7 @@ class GroupMember:
         self.fctx = capi.Context(device, handle=self.info.filter_ctx)
         self.px = det.n_row * det.n_col
         self.my_count = self.info.my_projections
-        self.slice_floats = self.info.region_x * self.info.region_y
+        self.slice_floats = self.info.x_count * self.info.region_y      # of the member's device slabs
         # this member's projections: per round one run of consecutive scan indices
         self.runs = []
         for rd in range(self.plan.rounds):
@@ -97,7 +97,7 @@ class GroupMember:
 
     def alloc_host_slabs(self):
         """pinned host memory of this member's own (for callers without a shared host volume)"""
-        self.h_slabs = capi.PinnedArray((self.info.z_count, self.info.region_y, self.info.region_x))
+        self.h_slabs = capi.PinnedArray((self.info.z_count, self.info.region_y, self.info.x_count))
         return self.h_slabs
 
     # ---- steps -----------------------------------------------------------------------------------------------------
@@ -125,9 +125,21 @@ class GroupMember:
 
     def device_slab(self, z_first: int, dz: int) -> np.ndarray:
         """slices [z_first, z_first + dz) of this member's FIRST slab, from the device (resident slabs)"""
-        out = np.empty((dz, self.info.region_y, self.info.region_x), np.float32)
+        out = np.empty((dz, self.info.region_y, self.info.x_count), np.float32)
         self.ctx.vol_d2h(self.info.d_first_slab + z_first * self.slice_floats * 4, out, out.size)
         return out
+
+    def box_roi(self, roi: capi.Roi | None) -> capi.Roi | None:
+        """The ROI that shifts voxel indices to this member's columns (stack-level calls outside the group)."""
+        if self.info.x_first == 0:
+            return roi
+        r = capi.Roi(0, 0, 0, 0, 0, 0) if roi is None else capi.Roi(roi.x1, roi.x2, roi.y1, roi.y2, roi.z1, roi.z2)
+        r.x1 += self.info.x_first
+        return r
+
+    def host_offset_bytes(self, region_x: int) -> int:
+        """Where this member's box starts inside a region-wide host volume of `region_x` floats per row."""
+        return (self.info.z_first * self.info.region_y * region_x + self.info.x_first) * 4
 
     def close(self):
         self.group.end()

@@ -34,6 +34,16 @@ def raw(path):
     rows = list(csv.reader(out.splitlines()))
     return rows[0], rows[1], rows[2:]
 
+# what was captured (so that DRAM traffic is compared with the algorithmic bytes of THAT launch)
+CAPTURES = {
+    "r2": {
+        "backprojection": {"what": "second launch of scripts/quick_bench.py --det 2048 --vol 1024 --proj 480 --batch 256: 240 "
+                                   "projections of 2048^2 into the 1024^3 volume (config 3 geometry)",
+                           "algorithmic_bytes": 240 * 2048 * 2048 * 4 + 2 * 1024 ** 3 * 4},
+        "fused": {"what": "one launch of the fused weight+filter kernel over 256 projections of 2048^2 (N = 4096)",
+                  "algorithmic_bytes": 8 * 2048 * 2048 * 256},
+    },
+}
 summary = {}
 lines = [f"# ncu summaries, round {tag}", "",
          "Captured with `ncu --set full --clock-control none --import-source on` on a B200 through gpurun, after the",
@@ -59,6 +69,10 @@ for name, rep in (("backprojection (bp_tma_kernel)", f"gpurun_out/bp_{tag}_final
                 rec[m] = r[i]
             rec[m + "__unit"] = units[i]
     lines.append("")
+    cap = CAPTURES.get(tag, {}).get(name.split()[0])
+    if cap:
+        rec["capture"] = cap
+        lines += [f"Captured launch: {cap['what']}; algorithmic HBM bytes {cap['algorithmic_bytes']:.3e}.", ""]
     summary[name.split()[0]] = rec
 
 launch_csv = os.path.join(ROOT, f"gpurun_out/launches_{tag}.csv")
@@ -73,8 +87,8 @@ if os.path.exists(launch_csv):
         a[0] += 1
         a[1] += float(r[vi].replace(',', ''))
     tot = sum(v[1] for v in agg.values())
-    lines += ["## launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (first 400 launches)", "",
-              "`ncu --metrics gpu__time_duration.sum --clock-control none -c 400` -- shares, not absolutes.", "",
+    lines += ["## launch list of `python bench.py --steps 2 --warmup 3 --no-cpu-baseline` (first launches)", "",
+              "`ncu --metrics gpu__time_duration.sum --clock-control none -c 400/600` -- shares, not absolutes.", "",
               "| kernel | launches | total ms | share | avg us |", "|---|---|---|---|---|"]
     for k, v in agg.items():
         lines.append(f"| {k} | {v[0]} | {v[1]/1e6:.3f} | {v[1]/tot*100:.1f}% | {v[1]/v[0]/1e3:.1f} |")

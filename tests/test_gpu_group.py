@@ -72,6 +72,10 @@ def _poison(member):
 
 def _run_in_process(world, det, vol, n_proj, roi=None, e2e=True, **options):
     """`world` members on device 0 of this process; returns the assembled region"""
+    if options.get("x_parts", 1) > 1 or e2e:
+        # every member downloads its box straight into ONE region-wide host volume
+        region_x = capi.apply_roi(vol, roi).dim_x if roi is not None else vol.dim_x
+        options = dict(options, host_row_floats=region_x)
     members = [GroupMember(0, r, world, det, vol, n_proj, roi=roi, **options) for r in range(world)]
     handles = [m.export() for m in members]
     for m in members:
@@ -81,11 +85,10 @@ def _run_in_process(world, det, vol, n_proj, roi=None, e2e=True, **options):
     info0 = members[0].info
     region = capi.PinnedArray((info0.region_z, info0.region_y, info0.region_x))
     region.array[...] = np.nan
-    slice_bytes = info0.region_x * info0.region_y * 4
     for step in range(2):                       # a second step exercises the write-after-read guards
         if e2e:
             for m in members:
-                m.begin_e2e(region.ptr + m.info.z_first * slice_bytes)
+                m.begin_e2e(region.ptr + m.host_offset_bytes(info0.region_x))
         else:
             for m in members:
                 m.begin_resident()
@@ -94,7 +97,8 @@ def _run_in_process(world, det, vol, n_proj, roi=None, e2e=True, **options):
     if not e2e:
         for m in members:
             assert m.info.slabs == 1
-            region.array[m.info.z_first:m.info.z_first + m.info.z_count] = m.device_slab(0, m.info.z_count)
+            region.array[m.info.z_first:m.info.z_first + m.info.z_count, :,
+                         m.info.x_first:m.info.x_first + m.info.x_count] = m.device_slab(0, m.info.z_count)
     out = region.array.copy()
     stats = [(m.group.info().bytes_pushed, m.group.info().memops, m.info.band_lo, m.info.band_hi) for m in members]
     for m in members:
@@ -145,6 +149,22 @@ def test_roi_region_offset_detector_natural_volume(ctx):
     region = (reg.dim_x, reg.dim_y, reg.dim_z)
     want = _one_piece(ctx, det, vol, n_proj, roi=roi, region=region)
     got, _ = _run_in_process(3, det, vol, n_proj, roi=roi, first_round=6, max_round=12)
+    assert np.isfinite(got).all() and np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("e2e", [True, False])
+def test_members_own_boxes_in_x_and_z(ctx, e2e):
+    """x_parts = 2 with four members: two z-runs of twice the height, each cut in two along x (what keeps the
+    128-slice tiles on volumes with few slices per GPU); boxes land inside one region-wide host volume"""
+    det, vol, n_proj = _case(k=64, extra_z=3)
+    want = _one_piece(ctx, det, vol, n_proj)
+    got, _ = _run_in_process(4, det, vol, n_proj, e2e=e2e, x_parts=2, first_round=8, max_round=16)
+    assert np.isfinite(got).all() and np.array_equal(got, want)
+    # ROI with odd offsets on top of the x-parts, three x-parts with a remainder
+    roi = capi.Roi(5, 60, 3, 50, 2, 2 + 40)
+    reg = capi.apply_roi(vol, roi)
+    want = _one_piece(ctx, det, vol, n_proj, roi=roi, region=(reg.dim_x, reg.dim_y, reg.dim_z))
+    got, _ = _run_in_process(3, det, vol, n_proj, roi=roi, e2e=e2e, x_parts=3, first_round=6, max_round=12)
     assert np.isfinite(got).all() and np.array_equal(got, want)
 
 

@@ -186,6 +186,19 @@ def test_slab_plan_matches_reference_split(port, dim_z, world):
         SlabPlan(3, 4, 0)
 
 
+@pytest.mark.parametrize("name,world,xp", [("c2", 8, 2), ("c1", 8, 8), ("c3", 8, 1), ("c2", 4, 4)])
+def test_plan_with_x_parts(name, world, xp):
+    """x_parts cuts the region along x as well: world / x_parts z-runs, members of one z-run share its band"""
+    det, vol, n_proj, roi, region = _baseline(name)
+    p = capi.group_plan(capi.group_config(0, world, det, vol, n_proj, roi=roi, x_parts=xp))
+    assert (p.x_parts, p.x_dx * xp + p.x_remainder) == (xp, region[0])
+    assert p.slabs_total == world // xp and p.slab_dz * p.slabs_total + p.slab_remainder == region[2]
+    for k in range(world):
+        assert (p.band_lo[k], p.band_hi[k]) == (p.band_lo[(k // xp) * xp], p.band_hi[(k // xp) * xp])
+    with pytest.raises(capi.Error):
+        capi.group_plan(capi.group_config(0, world, det, vol, n_proj, roi=roi, x_parts=3))
+
+
 def test_plan_rejects_more_slabs_than_slices(port):
     odet, det = both_det(32, 8, n_proj=8)
     vol = to_capi_vol(port.calculate_volume_geometry(odet))
