@@ -47,3 +47,11 @@ clean:
 
 .PHONY: all lib oracle clean
 
+# Checked build of the library (compute-sanitizer is closed on the GPU pool): every shared-memory sample load of the
+# backprojection is tested against the CTA's ring of staged boxes (csrc/backproject_tma.cu, PB_BOUNDS_CHECK); select it
+# with PARIS_B200_LIB=paris_b200/libparis_b200_check.so, read the counters with scripts/sanitize_case.py
+check-lib: paris_b200/libparis_b200_check.so
+paris_b200/libparis_b200_check.so: $(SRCS) $(HDRS)
+	$(NVCC) $(NVFLAGS) -DPB_BOUNDS_CHECK -c $(CSRC)/backproject_tma.cu -o /tmp/pb_backproject_tma_check.o
+	$(NVCC) $(ARCH) -shared -ccbin $(HOSTCXX) -o $@ $(filter-out $(CSRC)/backproject_tma.o,$(OBJS)) /tmp/pb_backproject_tma_check.o -lcudart
+

@@ -190,12 +190,36 @@ namespace pb
         return d;
     }
 
+#ifdef PB_BOUNDS_CHECK
+    // Checked build (make check-lib; compute-sanitizer is closed on the GPU pool): every sample load of the
+    // backprojection must fall inside the CTA's ring of staged boxes.  [0] loads checked, [1] loads outside (skipped,
+    // they return 0), [2] / [3] lowest / highest offending offset relative to the ring.
+    __device__ unsigned long long g_bounds[4] = {0ull, 0ull, ~0ull, 0ull};
+    __device__ uint32_t g_ring_lo_of_cta, g_ring_bytes;   // (written by every CTA with the same values)
+
+    __device__ __forceinline__ float lds_f32(uint32_t addr)
+    {
+        float v = 0.f;
+        const uint32_t off = addr - g_ring_lo_of_cta;
+        atomicAdd(&g_bounds[0], 1ull);
+        if(off + 4u > g_ring_bytes || (addr & 3u) != 0u)
+        {
+            atomicAdd(&g_bounds[1], 1ull);
+            atomicMin(&g_bounds[2], static_cast<unsigned long long>(static_cast<long long>(static_cast<int>(off))));
+            atomicMax(&g_bounds[3], static_cast<unsigned long long>(off));
+            return v;
+        }
+        asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
+        return v;
+    }
+#else
     __device__ __forceinline__ float lds_f32(uint32_t addr)
     {
         float v;
         asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(addr));
         return v;
     }
+#endif
 
     // ---- per-projection geometry helpers ------------------------------------------------------------------
 
@@ -639,6 +663,14 @@ namespace pb
             z_m0 = centered_d(z0, g.full_z, g.l_vx_z);
         }
         const uint32_t stage_base0 = smem_u32(stage_mem);
+#ifdef PB_BOUNDS_CHECK
+        if(tid == 0)
+        {
+            g_ring_lo_of_cta = stage_base0;   // (dynamic shared memory starts at the same address in every CTA of a launch)
+            g_ring_bytes = CFG::STAGES * CFG::STAGE_BYTES;
+        }
+        __syncthreads();
+#endif
 
         // entry of tile column `col` for projection p, into table set `slot`
         auto build = [&](int p, int col, int slot, float bx_k, float by_l) {
@@ -912,6 +944,18 @@ namespace pb
         const footprint f = tile_footprint(g, CFG::TX, CFG::TY, CFG::TZ);
         return f.ok && f.need_h <= CFG::BH && f.need_v + (CFG::SPLIT ? 7 : 3) <= CFG::BV;
     }
+
+#ifdef PB_BOUNDS_CHECK
+    // out[0..3]: sample loads checked, loads outside the staged ring, lowest / highest offending offset; resets
+    extern "C" int paris_b200_debug_bounds(unsigned long long* out)
+    {
+        cudaDeviceSynchronize();
+        cudaMemcpyFromSymbol(out, g_bounds, sizeof(unsigned long long) * 4);
+        const unsigned long long fresh[4] = {0ull, 0ull, ~0ull, 0ull};
+        cudaMemcpyToSymbol(g_bounds, fresh, sizeof(fresh));
+        return 0;
+    }
+#endif
 
 #ifdef PB_BP_STATS
     extern "C" int paris_b200_debug_bp_stats(unsigned long long* out)

@@ -1,4 +1,8 @@
-"""Small cases for compute-sanitizer (memcheck / racecheck / synccheck, ONE tool per gpurun call):
+"""Small cases for a checked run.  compute-sanitizer is CLOSED on the GPU pool (gpurun refuses it: "runs under it have
+left GPUs needing a reset"), so the check is the library's own: `make check-lib` builds
+paris_b200/libparis_b200_check.so, whose backprojection tests every shared-memory sample load against the CTA's ring of
+staged boxes; run this script with PARIS_B200_LIB pointing at it and it prints the counters.  The cases (also what a
+compute-sanitizer run would use, ONE tool per gpurun call, where that tool is open):
   a  config-1-like coarse volume: fused weight+filter, parity-split stack, TMA kernel (interior, MIXED, skipped tiles)
   b  natural volume, ROI with odd offsets, detector shifted, three z-slabs: plain stack, STRADDLE tiles, chunked download
   c  a reconstruction group of two members sharing the GPU (bands pushed by the copy engine and by the copy kernel,
@@ -33,5 +37,20 @@ if "c" in which:
     for ex in (capi.EXCHANGE_COPY_ENGINE, capi.EXCHANGE_KERNEL):
         got, stats = T._run_in_process(2, det, vol, n_proj, first_round=4, max_round=8, exchange=ex)
         print("c: two members, exchange", ex, "equal one piece:", bool(np.array_equal(got, want)), flush=True)
+if "d" in which:
+    # config 1 at full size (128^3 from 256 x 256^2): tall split tiles, every kind of tile
+    det, vol, n_proj = T._case(k=128, extra_z=0, n=256, n_proj=256)
+    fast = T._one_piece(ctx, det, vol, n_proj)
+    print("d: config 1, 128^3 from 256 x 256^2, max |v|", float(np.abs(fast).max()), ctx.bp_kernel_info()["last"], flush=True)
+import ctypes
+L = capi.lib()
+if hasattr(L, "paris_b200_debug_bounds"):
+    out = (ctypes.c_ulonglong * 4)()
+    L.paris_b200_debug_bounds(out)
+    print(f"bounds check: {out[0]} sample loads checked, {out[1]} outside the staged ring"
+          + (f" (offsets {ctypes.c_longlong(out[2]).value} .. {out[3]})" if out[1] else ""), flush=True)
+    assert out[0] > 0 and out[1] == 0
+else:
+    print("(unchecked library: build `make check-lib` and set PARIS_B200_LIB)", flush=True)
 ctx.close()
 print("done", flush=True)
