@@ -353,8 +353,9 @@ class SharedHostVolume:
             if flag.item() > 0:
                 self.kind = "one shared page-locked volume (POSIX shm), slabs written at their offsets"
                 self.ptr = self.array.ctypes.data + member.host_offset_bytes(region_x)
+                member.group.set_host_row(region_x)    # the member's box sits inside the region-wide volume
             else:
-                raise RuntimeError("the shared host volume could not be set up (the members were configured for it)")
+                self.kind = "per-rank pinned buffers (the shared segment could not be page-locked by every rank)"
         elif world > 1:
             self.kind = "per-rank pinned buffers (volume larger than 8 GB)"
         if self.ptr is None:
@@ -401,7 +402,6 @@ def run_b200(args, rank: int, world: int, local_rank: int):
             x_parts *= 2
     shared_volume = world > 1 and voxels * 4 <= (8 << 30)
     member = GroupMember(local_rank, rank, world, det, vol, n_proj, roi=roi, slabs_per_member=spm, x_parts=x_parts,
-                         host_row_floats=dims[0] if shared_volume else 0,
                          whole_projections=bool(args.whole_projections),
                          exchange=capi.EXCHANGE_KERNEL if args.exchange == "kernel" else capi.EXCHANGE_COPY_ENGINE)
     if dist is not None:

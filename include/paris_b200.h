@@ -364,6 +364,8 @@ int paris_b200_group_export(paris_b200_group* group, unsigned char* handle, size
  * their pointers (peer access is enabled), members of other processes through CUDA IPC. */
 int paris_b200_group_connect(paris_b200_group* group, const unsigned char* handles, size_t handle_bytes);
 int paris_b200_group_info(const paris_b200_group* group, paris_b200_group_info_t* info);
+/* change host_row_floats for the following steps (0: the member's own box, contiguous) */
+int paris_b200_group_set_host_row(paris_b200_group* group, uint32_t host_row_floats);
 /* scan index of this member's local projection `local` (0 <= local < my_projections): the order in which its raw
  * projections are handed to group_begin */
 int paris_b200_group_projection_index(const paris_b200_group* group, uint32_t local, uint32_t* index);

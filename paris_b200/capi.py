@@ -159,6 +159,7 @@ SIGNATURES = {
     "paris_b200_group_export": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
     "paris_b200_group_connect": (C.c_int, [_vp, C.c_char_p, C.c_size_t]),
     "paris_b200_group_info": (C.c_int, [_vp, _P(GroupInfo)]),
+    "paris_b200_group_set_host_row": (C.c_int, [_vp, _u32]),
     "paris_b200_group_projection_index": (C.c_int, [_vp, _u32, _P(_u32)]),
     "paris_b200_group_begin": (C.c_int, [_vp, _P(_vp), _vp, _vp]),
     "paris_b200_group_step_open": (C.c_int, [_vp, _vp]),
@@ -517,6 +518,9 @@ class Group:
         out = GroupInfo()
         check(self._L.paris_b200_group_info(self.h, C.byref(out)))
         return out
+
+    def set_host_row(self, host_row_floats: int):
+        check(self._L.paris_b200_group_set_host_row(self.h, host_row_floats))
 
     def projection_index(self, local: int) -> int:
         out = _u32(0)

@@ -799,6 +799,20 @@ extern "C" int paris_b200_group_info(const paris_b200_group* g, paris_b200_group
     return PARIS_B200_OK;
 }
 
+// floats from one row to the next in the host memory handed to the following steps (0: the member's own box)
+extern "C" int paris_b200_group_set_host_row(paris_b200_group* g, uint32_t host_row_floats)
+{
+    PB_CHECK_ARG(g != nullptr);
+    if(g->in_step || g->step_open)
+    {
+        set_error("group_set_host_row while a step is in flight");
+        return PARIS_B200_ESTATE;
+    }
+    PB_CHECK_ARG(host_row_floats == 0u || host_row_floats >= g->x_count);
+    g->host_row = host_row_floats ? host_row_floats : g->x_count;
+    return PARIS_B200_OK;
+}
+
 // scan index of this member's local projection `local` (the order its raw projections are handed over in)
 extern "C" int paris_b200_group_projection_index(const paris_b200_group* g, uint32_t local, uint32_t* index)
 {
