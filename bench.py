@@ -372,7 +372,7 @@ class SharedHostVolume:
 
 
 def run_b200(args, rank: int, world: int, local_rank: int):
-    from paris_b200 import capi, dropin
+    from paris_b200 import capi, dropin, phantom
     from paris_b200.multi import GroupMember
     from paris_b200.pipeline import angle_sin_cos
 
@@ -401,15 +401,18 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         while x_parts < world and world % (2 * x_parts) == 0 and dims[2] * x_parts // world < 128 * spm:
             x_parts *= 2
     shared_volume = world > 1 and voxels * 4 <= (8 << 30)
+    u16 = args.samples == "u16"
     member = GroupMember(local_rank, rank, world, det, vol, n_proj, roi=roi, slabs_per_member=spm, x_parts=x_parts,
                          whole_projections=bool(args.whole_projections),
+                         sample_type=capi.SAMPLES_U16 if u16 else capi.SAMPLES_F32,
                          exchange=capi.EXCHANGE_KERNEL if args.exchange == "kernel" else capi.EXCHANGE_COPY_ENGINE)
     if dist is not None:
         handles = [None] * world
         dist.all_gather_object(handles, member.export())
         member.connect(handles)
     ctx, info = member.ctx, member.info
-    member.generate_inputs(ellipsoids(det))
+    # --samples u16: the phantom's line integrals as 16-bit detector counts (the longest chord stays below 65536)
+    member.generate_inputs(ellipsoids(det), counts_scale=phantom.counts_scale(ellipsoids(det)) if u16 else None)
     sc = np.array([angle_sin_cos(i, det) for i in range(n_proj)], dtype=np.float32)
     my_slices = info.z_count
     slab_dims = (info.x_count, dims[1], my_slices)
@@ -425,8 +428,8 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         for first, count in member.runs:
             for done in range(0, count, 64):
                 c = min(64, count - done)
-                ctx.filter_to_stack_batch(member.d_raw + (local + done) * px * 4, px, c, det, filt, info.d_stack, first + done,
-                                          info.layout)
+                (ctx.filter_to_stack_batch_u16 if u16 else ctx.filter_to_stack_batch)(
+                    member.d_raw + (local + done) * member.proj_bytes, px, c, det, filt, info.d_stack, first + done, info.layout)
             local += count
         e1 = ctx.event()
         ctx.volume_clear(stage_vol, *slab_dims)
@@ -485,7 +488,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     if world > 1:
         # the volumes, not just the speed: two 4-slice bands of this member's slab recomputed from its own stack by the
         # exact kernel (the reference's arithmetic operation for operation, tests/test_gpu_parity.py)
-        c = float(n_proj) / (8.0 * np.pi)
+        c = float(n_proj) / (8.0 * np.pi) * (phantom.counts_scale(ellipsoids(det)) if u16 else 1.0)
         worst = [0.0, 0.0]
         first_dz = member.plan.slab_dz if info.slabs > 1 else my_slices   # (bands of the member's FIRST slab)
         if True:
@@ -520,7 +523,9 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         member.alloc_host_slabs()
 
     def e2e_step():
-        if world == 1:
+        if world == 1 and u16:
+            member.step_e2e()        # (the drop-in loop takes the reference's float projections; counts go through the group)
+        elif world == 1:
             # the reference-shaped per-projection loop in C++ (paris_b200/cpp/pipeline.cpp: reconstruct_task)
             dropin.reconstruct(member.h_raw.ptr, n_proj, det, vol, member.h_slabs.ptr, dims, roi=roi, device=local_rank)
         else:
@@ -563,7 +568,7 @@ def run_b200(args, rank: int, world: int, local_rank: int):
         my_updates = my_slices * info.x_count * dims[1] * n_proj
         bp_gbs = 16.0 * my_updates / bp_s / 1e9
         smem_peak = 148 * 128 * sm_mhz * 1e6 / 1e9
-        filt_gbs = 8.0 * px * member.my_count / filt_s / 1e9
+        filt_gbs = (4.0 + member.sample_bytes) * px * member.my_count / filt_s / 1e9
         ncu_bp, ncu_filt = ncu_record("backprojection"), ncu_record("fused")
         gp = gather_peak()
         bands = [(member.plan.band_lo[k], member.plan.band_hi[k]) for k in range(world)]
@@ -610,10 +615,11 @@ def run_b200(args, rank: int, world: int, local_rank: int):
                                 "note": f"8 B per detector pixel; peak {peak_src} (MEASURED_PEAKS.json hbm_gbs); ~110 flop and "
                                         "~30 shared-memory accesses per pixel keep it on the FP32/shared-memory side of the ridge"},
             "e2e": {"value": updates / (e2e_step_ms / 1e3) / 1e9, "unit": "GUPS", "seconds": e2e_step_ms / 1e3,
-                    "h2d_bytes_per_step": 4 * px * n_proj, "d2h_bytes_per_step": 4 * voxels,
+                    "h2d_bytes_per_step": member.proj_bytes * n_proj, "d2h_bytes_per_step": 4 * voxels,
+                    "samples": "u16 detector counts, widened by the filter kernel" if u16 else "f32",
                     "ms_steps": [round(x, 2) for x in e2e_ms],
                     "path": ("paris_b200_dropin_reconstruct: per-projection load/weight/filter/backproject + copy_d2h"
-                             if world == 1 else
+                             if world == 1 and not u16 else
                              "paris_b200_group_reconstruct per rank: upload + filter of 1/N of the projections round by round, "
                              "exchange over peer memory, backprojection of all projections into the rank's slabs, download"),
                     "host_volume": ("one pinned buffer" if world == 1 else host_vol.kind)},
@@ -666,6 +672,8 @@ def main():
     ap.add_argument("--slabs-per-gpu", type=int, default=0, help="z-slabs every GPU streams (0: 2 for config 5, else 1)")
     ap.add_argument("--x-parts", type=int, default=0, help="parts along x (0: automatic, keeps >= 128 slices per GPU)")
     ap.add_argument("--exchange", default="copy-engine", choices=["copy-engine", "kernel"])
+    ap.add_argument("--samples", default="f32", choices=["f32", "u16"],
+                    help="raw projections as floats (what the reference's reader hands on) or as 16-bit detector counts")
     ap.add_argument("--whole-projections", action="store_true", help="exchange every detector row (an all-gather)")
     args = ap.parse_args()
 

@@ -247,6 +247,11 @@ int paris_b200_filter_to_stack(paris_b200_ctx* ctx, const float* d_raw, const pa
 int paris_b200_filter_to_stack_batch(paris_b200_ctx* ctx, const float* d_raw, size_t raw_stride, uint32_t count,
                                      const paris_b200_detector_geometry* det, const paris_b200_filter* filter,
                                      float* d_stack, uint32_t first_slot, uint32_t layout);
+/* the same for detector-native 16-bit samples (raw_stride in samples): the widening the HIS reader does on the host
+ * (src/his.cpp:169-185) becomes the kernel's first load, so that half the bytes cross PCIe and HBM */
+int paris_b200_filter_to_stack_batch_u16(paris_b200_ctx* ctx, const uint16_t* d_raw, size_t raw_stride, uint32_t count,
+                                         const paris_b200_detector_geometry* det, const paris_b200_filter* filter,
+                                         float* d_stack, uint32_t first_slot, uint32_t layout);
 /* backproject slots [first, first+count) of an external stack into d_vol; sin_phi/cos_phi are host
  * arrays of `count` entries (slot first+i uses entry i). */
 int paris_b200_backproject_stack(paris_b200_ctx* ctx, const float* d_stack, uint32_t first, uint32_t count,
@@ -284,6 +289,7 @@ int paris_b200_backproject_stack_d2h(paris_b200_ctx* ctx, const float* d_stack, 
  *   connect  ->  reconstruct / begin + end, any number of times  ->  destroy
  */
 #define PARIS_B200_SAMPLES_F32 0u
+#define PARIS_B200_SAMPLES_U16 1u           /* detector-native counts: h_raw / d_raw address uint16_t samples */
 #define PARIS_B200_EXCHANGE_COPY_ENGINE 0u   /* cudaMemcpy2DAsync into peer memory on a stream of its own (default) */
 #define PARIS_B200_EXCHANGE_KERNEL 1u        /* a small copy kernel on a high-priority stream */
 #define PARIS_B200_GROUP_HANDLE_BYTES 256
@@ -303,7 +309,7 @@ typedef struct paris_b200_group_config
                                              the last), member r owns slabs [r * spm, (r + 1) * spm) */
     uint32_t stream_slabs;                /* 1: at most two slab buffers on the device, slabs go to the host one by one (a host
                                              destination is then required); 0: every slab stays resident */
-    uint32_t sample_type;                 /* PARIS_B200_SAMPLES_F32 */
+    uint32_t sample_type;                 /* PARIS_B200_SAMPLES_F32 or _U16 (raw projections as 16-bit counts: half the upload) */
     uint32_t first_round, max_round;      /* projections per exchanged round: first one, upper bound (0 = 64 / 256) */
     uint32_t whole_projections;           /* 1: exchange every detector row (an all-gather); 0: only the band of rows the
                                              receiving member's slabs can read */
@@ -375,6 +381,7 @@ int paris_b200_group_projection_index(const paris_b200_group* group, uint32_t lo
  * region_y floats, pinned), or NULL to leave the slabs on the device.  begin() only enqueues -- members that share a
  * host thread begin one after the other and then end; end() returns when this member's slabs are complete. */
 int paris_b200_group_begin(paris_b200_group* group, const float* const* h_raw, const float* d_raw, float* h_slabs);
+/* (with PARIS_B200_SAMPLES_U16 the h_raw[j] / d_raw pointers address uint16_t samples, n_col x n_row per projection) */
 /* The same step piece by piece, for callers that produce their projections while the device works (the command-line
  * driver reads the next round's frames from disk meanwhile): open, then every round in order -- h_raw[j] / d_raw now
  * address only the member's share of THAT round (paris_b200_group_share tells which projections those are) -- then

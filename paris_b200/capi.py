@@ -50,7 +50,7 @@ class SubvolumeInfo(C.Structure):
 
 
 GROUP_HANDLE_BYTES, GROUP_MAX_MEMBERS, GROUP_MAX_ROUNDS = 256, 64, 256
-SAMPLES_F32 = 0
+SAMPLES_F32, SAMPLES_U16 = 0, 1
 EXCHANGE_COPY_ENGINE, EXCHANGE_KERNEL = 0, 1
 
 
@@ -146,6 +146,7 @@ SIGNATURES = {
     "paris_b200_filter_to_stack": (C.c_int, [_vp, _fp, _P(DetectorGeometry), _vp, _fp, _u32, _u32]),
     "paris_b200_filter_to_stack_batch": (C.c_int, [_vp, _fp, C.c_size_t, _u32, _P(DetectorGeometry), _vp, _fp, _u32,
                                                    _u32]),
+    "paris_b200_filter_to_stack_batch_u16": (C.c_int, [_vp, _vp, C.c_size_t, _u32, _P(DetectorGeometry), _vp, _fp, _u32, _u32]),
     "paris_b200_backproject_stack": (C.c_int, [_vp, _fp, _u32, _u32, _P(_f), _P(_f), _fp, _u32, _u32, _u32, _u32,
                                                _P(DetectorGeometry), _P(VolumeGeometry), C.c_int, _P(Roi), _u32]),
     "paris_b200_backproject_stack_d2h": (C.c_int, [_vp, _fp, _u32, _u32, _P(_f), _P(_f), _fp, _u32, _u32, _u32, _u32,
@@ -242,14 +243,15 @@ def stack_slot_bytes(n_row: int, n_col: int):
 
 
 class PinnedArray:
-    """A float32 numpy view over pinned host memory from paris_b200_host_alloc."""
+    """A float32 (or uint16) numpy view over pinned host memory from paris_b200_host_alloc."""
 
-    def __init__(self, shape, zero=False):
+    def __init__(self, shape, zero=False, dtype=np.float32):
         n = int(np.prod(shape))
         p = _vp()
-        check(lib().paris_b200_host_alloc(n * 4, int(zero), C.byref(p)))
+        ctype = {np.dtype(np.float32): C.c_float, np.dtype(np.uint16): C.c_uint16}[np.dtype(dtype)]
+        check(lib().paris_b200_host_alloc(n * C.sizeof(ctype), int(zero), C.byref(p)))
         self.ptr = p.value
-        self.array = np.ctypeslib.as_array((C.c_float * n).from_address(self.ptr)).reshape(shape)
+        self.array = np.ctypeslib.as_array((ctype * n).from_address(self.ptr)).reshape(shape)
 
     def free(self):
         if self.ptr:
@@ -424,6 +426,12 @@ class Context:
         check(self._L.paris_b200_filter_to_stack_batch(self.h, d_raw, raw_stride, count, C.byref(det), filt, d_stack,
                                                        first_slot, layout))
 
+    def filter_to_stack_batch_u16(self, d_raw: int, raw_stride: int, count: int, det: DetectorGeometry, filt: int,
+                                  d_stack: int, first_slot: int, layout: int = LAYOUT_PLAIN):
+        """d_raw: uint16 samples, raw_stride in samples"""
+        check(self._L.paris_b200_filter_to_stack_batch_u16(self.h, d_raw, raw_stride, count, C.byref(det), filt,
+                                                           d_stack, first_slot, layout))
+
     def backproject_stack(self, d_stack: int, first: int, count: int, sin_phi: np.ndarray, cos_phi: np.ndarray,
                           d_vol: int, v_dims, v_offset: int, det: DetectorGeometry, vol_full: VolumeGeometry,
                           roi: Roi | None = None, layout: int = LAYOUT_PLAIN):
@@ -461,13 +469,13 @@ class Context:
 def group_config(rank: int, world: int, det: DetectorGeometry, vol_full: VolumeGeometry, n_proj: int, roi: Roi | None = None,
                  slabs_per_member: int = 1, stream_slabs: bool = False, first_round: int = 0, max_round: int = 0,
                  whole_projections: bool = False, exchange: int = EXCHANGE_COPY_ENGINE, angles_deg=None, x_parts: int = 1,
-                 host_row_floats: int = 0) -> GroupConfig:
+                 host_row_floats: int = 0, sample_type: int = SAMPLES_F32) -> GroupConfig:
     cfg = GroupConfig()
     cfg.rank, cfg.world, cfg.det, cfg.vol_full, cfg.n_proj = rank, world, det, vol_full, n_proj
     cfg.enable_roi = int(roi is not None)
     if roi is not None:
         cfg.roi = roi
-    cfg.slabs_per_member, cfg.stream_slabs, cfg.sample_type = slabs_per_member, int(stream_slabs), SAMPLES_F32
+    cfg.slabs_per_member, cfg.stream_slabs, cfg.sample_type = slabs_per_member, int(stream_slabs), sample_type
     cfg.first_round, cfg.max_round = first_round, max_round
     cfg.whole_projections, cfg.exchange = int(whole_projections), exchange
     cfg.x_parts, cfg.host_row_floats = x_parts, host_row_floats

@@ -213,6 +213,20 @@ namespace paris
             return true;
         }
 
+        auto read_frame_u16(const std::string& path, const file_info& info, std::uint32_t frame, std::uint16_t* dst) -> bool
+        {
+            if(!info.valid || info.number_type != 4 || frame >= info.frames || dst == nullptr)
+                return false;
+            auto file = std::unique_ptr<std::FILE, file_closer>{std::fopen(path.c_str(), "rb")};
+            if(!file)
+                return false;
+            const auto bytes = static_cast<std::size_t>(info.width) * info.height * sizeof(std::uint16_t);
+            const auto frame_bytes = static_cast<unsigned long long>(info.image_header_size) + bytes;
+            const auto pos = file_header_bytes + frame_bytes * frame + info.image_header_size;
+            // straight from the file into the caller's (pinned) memory: the samples are widened on the GPU
+            return fseeko(file.get(), static_cast<off_t>(pos), SEEK_SET) == 0 && std::fread(dst, 1, bytes, file.get()) == bytes;
+        }
+
         auto load(const std::string& path) -> std::vector<image_type>
         {
             auto images = std::vector<image_type>{};

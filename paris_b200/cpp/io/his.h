@@ -49,5 +49,8 @@ namespace paris
         // Frame `frame` of a file probe() accepted, widened to float into dst (width*height floats).  False if the
         // frame cannot be read.  Lets several readers share one scan without decoding each other's frames.
         auto read_frame(const std::string& path, const file_info& info, std::uint32_t frame, float* dst) -> bool;
+        // The same for a file of 16-bit samples (number_type 4), WITHOUT widening: width*height uint16 values, as the
+        // detector wrote them (little endian, like the host).  False for any other sample type.
+        auto read_frame_u16(const std::string& path, const file_info& info, std::uint32_t frame, std::uint16_t* dst) -> bool;
     }
 }

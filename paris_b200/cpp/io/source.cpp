@@ -98,6 +98,27 @@ namespace paris
         return his::read_frame(index.paths[fr.file], info, fr.frame, dst);
     }
 
+    auto load_scan_frame_u16(const scan_index& index, std::size_t i, std::uint16_t* dst) -> bool
+    {
+        if(i >= index.frames.size())
+            return false;
+        const auto& fr = index.frames[i];
+        const auto& info = index.infos[fr.file];
+        if(info.width != index.dim_x || info.height != index.dim_y)
+            return false;
+        return his::read_frame_u16(index.paths[fr.file], info, fr.frame, dst);
+    }
+
+    auto scan_is_u16(const scan_index& index) -> bool
+    {
+        if(index.frames.empty())
+            return false;
+        for(const auto& fr : index.frames)
+            if(index.infos[fr.file].number_type != 4)
+                return false;
+        return true;
+    }
+
     source::source(const std::string& proj_dir, bool enable_angles, const std::string& angle_file,
                    std::uint16_t quality) noexcept
     : enable_angles_{enable_angles}, quality_{quality == 0 ? std::uint16_t{1} : quality}

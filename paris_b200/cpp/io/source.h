@@ -51,6 +51,11 @@ namespace paris
     // decodes projection i of the index into dst (dim_x * dim_y floats); false if the frame cannot be read
     auto load_scan_frame(const scan_index& index, std::size_t i, float* dst) -> bool;
 
+    // every projection of the scan sits in a file of 16-bit samples: the group can take them as they are
+    auto scan_is_u16(const scan_index& index) -> bool;
+    // projection i of such a scan, not widened (dim_x * dim_y uint16 values)
+    auto load_scan_frame_u16(const scan_index& index, std::size_t i, std::uint16_t* dst) -> bool;
+
     class source
     {
         private:

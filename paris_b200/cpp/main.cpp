@@ -158,7 +158,12 @@ namespace
         cfg.angles_deg = angles.data();
         cfg.slabs_per_member = slabs_per_member;
         cfg.stream_slabs = slabs_per_member > 1u ? 1u : 0u;
-        cfg.sample_type = PARIS_B200_SAMPLES_F32;
+        // 16-bit detector files go to the GPU as they are (half the PCIe bytes; the filter kernel widens them with the
+        // very conversion src/his.cpp:98-99 does on the host); PARIS_B200_SAMPLES=f32 keeps the host conversion
+        const auto* samples_env = std::getenv("PARIS_B200_SAMPLES");
+        const auto native_u16 = paris::scan_is_u16(scan) && !(samples_env != nullptr && std::string{samples_env} == "f32");
+        const auto sample_bytes = native_u16 ? sizeof(std::uint16_t) : sizeof(float);
+        cfg.sample_type = native_u16 ? PARIS_B200_SAMPLES_U16 : PARIS_B200_SAMPLES_F32;
         cfg.exchange = PARIS_B200_EXCHANGE_COPY_ENGINE;
 
         try
@@ -194,7 +199,8 @@ namespace
                     largest = std::max(largest, count);
                 }
                 // two sets of pinned frames: the disk fills one while the upload of the other is in flight
-                pinned_floats frames[2] = {pinned_floats{px * largest}, pinned_floats{px * largest}};
+                const auto set_floats = (px * largest * sample_bytes + sizeof(float) - 1u) / sizeof(float);
+                pinned_floats frames[2] = {pinned_floats{set_floats}, pinned_floats{set_floats}};
                 pinned_floats slabs{static_cast<std::size_t>(info.region_x) * info.region_y * info.z_count};
 
                 must(paris_b200_group_step_open(group, slabs.p), "paris_b200_group_step_open");
@@ -204,7 +210,7 @@ namespace
                     auto first = 0u, count = 0u;
                     must(paris_b200_group_share(&plan, static_cast<std::uint32_t>(world), rd, static_cast<std::uint32_t>(rank),
                                                 &first, &count), "paris_b200_group_share");
-                    auto* set = frames[rd & 1u].p;
+                    auto* set = reinterpret_cast<unsigned char*>(frames[rd & 1u].p);
                     if(rd >= 2u)
                     {
                         auto done = 0;
@@ -218,9 +224,12 @@ namespace
                     auto ptrs = std::vector<const float*>(count);
                     for(auto j = 0u; j < count; ++j)
                     {
-                        if(!paris::load_scan_frame(scan, first + j, set + px * j))
+                        auto* frame = set + px * sample_bytes * j;
+                        const auto ok = native_u16 ? paris::load_scan_frame_u16(scan, first + j, reinterpret_cast<std::uint16_t*>(frame))
+                                                   : paris::load_scan_frame(scan, first + j, reinterpret_cast<float*>(frame));
+                        if(!ok)
                             throw paris::stage_runtime_error{"could not read projection " + std::to_string(first + j)};
-                        ptrs[j] = set + px * j;
+                        ptrs[j] = reinterpret_cast<const float*>(frame);
                         ++loaded;
                     }
                     must(paris_b200_group_step_round(group, rd, count > 0u ? ptrs.data() : nullptr, nullptr),
@@ -229,7 +238,7 @@ namespace
                 must(paris_b200_group_step_finish(group), "paris_b200_group_step_finish");
                 must(paris_b200_group_end(group), "paris_b200_group_end");
                 paris::log::info() << "device " << device << ": member " << rank + 1u << "/" << world << ", " << loaded
-                                   << " of " << scan.frames.size() << " projections filtered here, slices [" << info.z_first
+                                   << " of " << scan.frames.size() << (native_u16 ? " 16-bit" : "") << " projections filtered here, slices [" << info.z_first
                                    << ", " << info.z_first + info.z_count << ") in " << info.slabs << (info.slabs == 1u ? " slab" : " slabs")
                                    << ", detector rows [" << info.band_lo << ", " << info.band_hi << ") received";
                 sink.save(slabs.p, info.region_x, info.region_y, info.z_count, info.z_first);

@@ -1228,6 +1228,33 @@ extern "C" int paris_b200_filter_to_stack_batch(paris_b200_ctx* ctx, const float
     return PARIS_B200_OK;
 }
 
+// the same for detector-native 16-bit samples (raw_stride in samples): widened to float by the kernel's first load
+extern "C" int paris_b200_filter_to_stack_batch_u16(paris_b200_ctx* ctx, const uint16_t* d_raw, size_t raw_stride,
+                                                    uint32_t count, const paris_b200_detector_geometry* det,
+                                                    const paris_b200_filter* filter, float* d_stack, uint32_t first_slot,
+                                                    uint32_t layout)
+{
+    PB_CHECK_ARG(layout == kLayoutPlain || layout == kLayoutSplit2);
+    PB_CHECK_ARG(ctx != nullptr && d_raw != nullptr && det != nullptr && filter != nullptr && d_stack != nullptr);
+    PB_CHECK_ARG(det->n_row <= filter->size);
+    PB_CHECK_ARG(count <= 1u || raw_stride >= static_cast<size_t>(det->n_row) * det->n_col);
+    PB_TRY(bind(ctx));
+    const uint32_t pitch = stack_pitch_for(det->n_col);
+    const size_t slot_floats = static_cast<size_t>(pitch) * det->n_row;
+    const weight_params w = weighting_from_detector(det);
+    const float* src[kMaxBatch];
+    for(uint32_t done = 0; done < count;)
+    {
+        const uint32_t n = std::min<uint32_t>(count - done, static_cast<uint32_t>(kMaxBatch));
+        for(uint32_t i = 0; i < n; ++i)
+            src[i] = reinterpret_cast<const float*>(d_raw + raw_stride * (done + i));
+        PB_TRY(launch_filter_batch(ctx, src, nullptr, n, d_stack, first_slot + done, slot_floats, det->n_row, det->n_col,
+                                   filter, w, true, pitch, layout, true));
+        done += n;
+    }
+    return PARIS_B200_OK;
+}
+
 extern "C" int paris_b200_filter_to_stack(paris_b200_ctx* ctx, const float* d_raw,
                                           const paris_b200_detector_geometry* det, const paris_b200_filter* filter,
                                           float* d_stack, uint32_t slot, uint32_t layout)

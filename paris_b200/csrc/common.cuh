@@ -187,7 +187,7 @@ namespace pb
     int launch_filter_batch(paris_b200_ctx* ctx, const float* const* d_src, float* const* d_dst, uint32_t count,
                             float* d_stack, uint32_t first_slot, size_t slot_floats, uint32_t dim_x, uint32_t dim_y,
                             const paris_b200_filter* f, const weight_params& w, bool transposed, uint32_t pitch,
-                            uint32_t layout = kLayoutPlain);
+                            uint32_t layout = kLayoutPlain, bool src_u16 = false);
 
     // frequency index stored at position p after the forward passes of the size-2^log2n transform
     int frequency_of_position(int log2n, int p);

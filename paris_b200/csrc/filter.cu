@@ -337,8 +337,10 @@ namespace pb
 
     struct filter_batch
     {
-        const float* src[kMaxBatch];
-        float* dst[kMaxBatch];   // row-major destinations (TRANSPOSED == false)
+        const float* src[kMaxBatch];   // raw projections: float samples, or (src_u16) detector-native 16-bit counts
+        float* dst[kMaxBatch];         // row-major destinations (TRANSPOSED == false)
+        uint32_t src_u16;              // the HIS reader widens u16 -> float on the host (src/his.cpp:169-185); here the
+                                       // widening is the kernel's first load, so that half the bytes cross PCIe and HBM
     };
 
     template <int LOG2N, bool TRANSPOSED>
@@ -376,6 +378,20 @@ namespace pb
             const uint32_t proj = item / blocks_per_proj;
             const uint32_t row0 = (item % blocks_per_proj) * kRowsPerCta + 2u * static_cast<uint32_t>(round * P::PAIRS + lp);
             const bool has0 = row0 < dim_y, has1 = row0 + 1u < dim_y;
+            if(io.src_u16)
+            {
+                const unsigned short* const s0 = reinterpret_cast<const unsigned short*>(io.src[proj])
+                                               + static_cast<size_t>(row0) * dim_x + b;
+                const unsigned short* const s1 = s0 + dim_x;
+                #pragma unroll
+                for(int k = 0; k < 8; ++k)
+                {
+                    const uint32_t i = b + k * (N / 16);
+                    pa[k] = (i < dim_x && has0) ? static_cast<float>(__ldg(s0 + k * (N / 16))) : 0.f;
+                    pc[k] = (i < dim_x && has1) ? static_cast<float>(__ldg(s1 + k * (N / 16))) : 0.f;
+                }
+                return;
+            }
             const float* const src0 = io.src[proj] + static_cast<size_t>(row0) * dim_x + b;
             const float* const src1 = src0 + dim_x;
             #pragma unroll
@@ -632,7 +648,7 @@ namespace pb
     int launch_filter_batch(paris_b200_ctx* ctx, const float* const* d_src, float* const* d_dst, uint32_t count,
                             float* d_stack, uint32_t first_slot, size_t slot_floats, uint32_t dim_x, uint32_t dim_y,
                             const paris_b200_filter* f, const weight_params& w, bool transposed, uint32_t pitch,
-                            uint32_t layout)
+                            uint32_t layout, bool src_u16)
     {
         if(transposed && layout != kLayoutPlain && (f->size < 256 || (pitch & 7u) != 0u))
         {
@@ -660,9 +676,9 @@ namespace pb
                 int rc = PARIS_B200_EINVAL;
                 switch(f->size)
                 {
-                    case 32: rc = launch_filter_small<5>(ctx, d_src[i], dst, dim_x, dim_y, f, w, transposed, pitch); break;
-                    case 64: rc = launch_filter_small<6>(ctx, d_src[i], dst, dim_x, dim_y, f, w, transposed, pitch); break;
-                    case 128: rc = launch_filter_small<7>(ctx, d_src[i], dst, dim_x, dim_y, f, w, transposed, pitch); break;
+                    case 32: rc = launch_filter_small<5>(ctx, d_src[i], dst, dim_x, dim_y, f, w, transposed, pitch, src_u16); break;
+                    case 64: rc = launch_filter_small<6>(ctx, d_src[i], dst, dim_x, dim_y, f, w, transposed, pitch, src_u16); break;
+                    case 128: rc = launch_filter_small<7>(ctx, d_src[i], dst, dim_x, dim_y, f, w, transposed, pitch, src_u16); break;
                     default: set_error("unsupported filter size %u", f->size); break;
                 }
                 PB_TRY(rc);
@@ -670,6 +686,7 @@ namespace pb
             return PARIS_B200_OK;
         }
         filter_batch io{};
+        io.src_u16 = src_u16 ? 1u : 0u;
         for(uint32_t i = 0; i < count; ++i)
         {
             io.src[i] = d_src[i];

@@ -124,8 +124,13 @@ namespace pb
     template <int LOG2N, bool TRANSPOSED>
     __global__ void __launch_bounds__(((1 << LOG2N) / 4 > 1024) ? 1024 : (1 << LOG2N) / 4)
     filter_small_kernel(const float* src, float* dst, uint32_t dim_x, uint32_t dim_y,
-                  const float* __restrict__ kn, const float2* __restrict__ tw, weight_params w, uint32_t dst_pitch)
+                  const float* __restrict__ kn, const float2* __restrict__ tw, weight_params w, uint32_t dst_pitch,
+                  uint32_t src_u16)
     {
+        // 16-bit source samples (detector counts) are widened by the load, like the grouped kernel does
+        const auto sample = [&](size_t at) -> float {
+            return src_u16 ? static_cast<float>(__ldg(reinterpret_cast<const unsigned short*>(src) + at)) : __ldg(src + at);
+        };
         constexpr int N = 1 << LOG2N;
         constexpr int PAIRS = TRANSPOSED ? kStageRows / 2 : 1;
         extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -154,13 +159,13 @@ namespace pb
                 {
                     if(has0)
                     {
-                        a = __ldg(src + static_cast<size_t>(row0) * dim_x + i);
+                        a = sample(static_cast<size_t>(row0) * dim_x + i);
                         if(w.enable)
                             a = __fmul_rn(a, pixel_weight(i, row0, w.h_min, w.v_min, w.d_sd, w.l_px_row, w.l_px_col));
                     }
                     if(has1)
                     {
-                        b = __ldg(src + static_cast<size_t>(row1) * dim_x + i);
+                        b = sample(static_cast<size_t>(row1) * dim_x + i);
                         if(w.enable)
                             b = __fmul_rn(b, pixel_weight(i, row1, w.h_min, w.v_min, w.d_sd, w.l_px_row, w.l_px_col));
                     }
@@ -224,7 +229,8 @@ namespace pb
 
     template <int LOG2N>
     static int launch_filter_small(paris_b200_ctx* ctx, const float* d_src, float* d_dst, uint32_t dim_x, uint32_t dim_y,
-                               const paris_b200_filter* f, const weight_params& w, bool transposed, uint32_t pitch)
+                               const paris_b200_filter* f, const weight_params& w, bool transposed, uint32_t pitch,
+                               bool src_u16 = false)
     {
         constexpr int N = 1 << LOG2N;
         constexpr int threads = (N / 4 > 1024) ? 1024 : N / 4;
@@ -234,7 +240,7 @@ namespace pb
             auto kern = filter_small_kernel<LOG2N, true>;
             PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             const uint32_t grid = (dim_y + kStageRows - 1) / kStageRows;
-            kern<<<grid, threads, smem, ctx->compute>>>(d_src, d_dst, dim_x, dim_y, f->d_kn, f->d_tw, w, pitch);
+            kern<<<grid, threads, smem, ctx->compute>>>(d_src, d_dst, dim_x, dim_y, f->d_kn, f->d_tw, w, pitch, src_u16 ? 1u : 0u);
         }
         else
         {
@@ -242,7 +248,7 @@ namespace pb
             auto kern = filter_small_kernel<LOG2N, false>;
             PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             const uint32_t grid = (dim_y + 1) / 2;
-            kern<<<grid, threads, smem, ctx->compute>>>(d_src, d_dst, dim_x, dim_y, f->d_kn, f->d_tw, w, 0u);
+            kern<<<grid, threads, smem, ctx->compute>>>(d_src, d_dst, dim_x, dim_y, f->d_kn, f->d_tw, w, 0u, src_u16 ? 1u : 0u);
         }
         PB_CUDA(cudaGetLastError());
         ++ctx->launches;

@@ -145,6 +145,7 @@ struct paris_b200_group
     uint32_t host_row = 0;                      // floats per row of the host destination
     uint32_t layout = 0, pitch = 0;
     size_t slot_floats = 0, px = 0;
+    size_t sample_bytes = 4;                    // of a raw sample: 4 (float) or 2 (detector-native counts)
     std::vector<round_t> rounds;
     std::vector<uint32_t> local_first;          // index of a round's first projection among this member's own
     uint32_t my_count = 0;
@@ -470,7 +471,7 @@ extern "C" int paris_b200_group_create(int device, const paris_b200_group_config
     *out = nullptr;
     PB_CHECK_ARG(cfg->world >= 1 && cfg->world <= PARIS_B200_GROUP_MAX_MEMBERS && cfg->rank >= 0 && cfg->rank < cfg->world);
     PB_CHECK_ARG(cfg->n_proj >= 1 && cfg->det.n_row > 0 && cfg->det.n_col > 0);
-    PB_CHECK_ARG(cfg->sample_type == PARIS_B200_SAMPLES_F32);
+    PB_CHECK_ARG(cfg->sample_type == PARIS_B200_SAMPLES_F32 || cfg->sample_type == PARIS_B200_SAMPLES_U16);
     PB_CHECK_ARG(cfg->exchange == PARIS_B200_EXCHANGE_COPY_ENGINE || cfg->exchange == PARIS_B200_EXCHANGE_KERNEL);
 
     auto* g = new paris_b200_group{};
@@ -545,6 +546,7 @@ extern "C" int paris_b200_group_create(int device, const paris_b200_group_config
     g->pitch = plan.pitch;
     g->slot_floats = static_cast<size_t>(g->pitch) * cfg->det.n_row;
     g->px = static_cast<size_t>(cfg->det.n_row) * cfg->det.n_col;
+    g->sample_bytes = cfg->sample_type == PARIS_B200_SAMPLES_U16 ? 2u : 4u;
     PB_GTRY(paris_b200_filter_create(g->fctx, paris_b200_filter_size(cfg->det.n_row), cfg->det.l_px_row, &g->filter));
     g->sn.resize(cfg->n_proj);
     g->cs.resize(cfg->n_proj);
@@ -924,8 +926,8 @@ extern "C" int paris_b200_group_step_round(paris_b200_group* g, uint32_t rd, con
             if(g->raw_free_valid[b])
                 PB_CUDA(cudaStreamWaitEvent(fctx->copy, g->raw_free[b], 0));
             for(uint32_t j = 0; j < count; ++j)
-                PB_CUDA(cudaMemcpyAsync(g->raw[b] + g->px * j, h_raw[j], g->px * sizeof(float), cudaMemcpyHostToDevice,
-                                        fctx->copy));
+                PB_CUDA(cudaMemcpyAsync(reinterpret_cast<unsigned char*>(g->raw[b]) + g->px * g->sample_bytes * j, h_raw[j],
+                                        g->px * g->sample_bytes, cudaMemcpyHostToDevice, fctx->copy));
             PB_CUDA(cudaEventRecord(g->uploaded[rd], fctx->copy));
             PB_CUDA(cudaStreamWaitEvent(fctx->compute, g->uploaded[rd], 0));
             src = g->raw[b];
@@ -935,9 +937,10 @@ extern "C" int paris_b200_group_step_round(paris_b200_group* g, uint32_t rd, con
         {
             const uint32_t n = std::min<uint32_t>(count - done, 64u);   // (persistent CTAs: 64 projections fill the GPU)
             for(uint32_t i = 0; i < n; ++i)
-                ptrs[i] = src + g->px * (done + i);
+                ptrs[i] = reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(src)
+                                                         + g->px * g->sample_bytes * (done + i));
             PB_TRY(launch_filter_batch(fctx, ptrs, nullptr, n, g->stack, first + done, g->slot_floats, g->cfg.det.n_row,
-                                       g->cfg.det.n_col, g->filter, w, true, g->pitch, g->layout));
+                                       g->cfg.det.n_col, g->filter, w, true, g->pitch, g->layout, g->sample_bytes == 2u));
             done += n;
         }
         if(h_raw != nullptr)
@@ -1052,7 +1055,9 @@ extern "C" int paris_b200_group_begin(paris_b200_group* g, const float* const* h
     {
         const uint32_t local = g->local_first[rd];
         PB_TRY(paris_b200_group_step_round(g, rd, h_raw != nullptr ? h_raw + local : nullptr,
-                                           d_raw != nullptr ? d_raw + g->px * local : nullptr));
+                                           d_raw != nullptr ? reinterpret_cast<const float*>(reinterpret_cast<const unsigned char*>(d_raw)
+                                                                                              + g->px * g->sample_bytes * local)
+                                                            : nullptr));
     }
     return paris_b200_group_step_finish(g);
 }

@@ -40,7 +40,7 @@ class GroupMember:
                  n_proj: int, roi: capi.Roi | None = None, **options):
         """vol: the FULL volume geometry; roi: the reconstructed box (default: the whole volume); options: the
         remaining fields of capi.group_config (slabs_per_member, stream_slabs, first_round, max_round,
-        whole_projections, exchange, angles_deg, x_parts, host_row_floats)."""
+        whole_projections, exchange, angles_deg, x_parts, host_row_floats, sample_type)."""
         self.det, self.vol, self.n_proj, self.rank, self.world, self.device = det, vol, n_proj, rank, world, device
         self.cfg = capi.group_config(rank, world, det, vol, n_proj, roi=roi, **options)
         self.plan = capi.group_plan(self.cfg)
@@ -49,6 +49,8 @@ class GroupMember:
         self.ctx = capi.Context(device, handle=self.info.ctx)          # the backprojection context (events, options)
         self.fctx = capi.Context(device, handle=self.info.filter_ctx)
         self.px = det.n_row * det.n_col
+        self.sample_bytes = 2 if self.cfg.sample_type == capi.SAMPLES_U16 else 4
+        self.proj_bytes = self.px * self.sample_bytes
         self.my_count = self.info.my_projections
         self.slice_floats = self.info.x_count * self.info.region_y      # of the member's device slabs
         # this member's projections: per round one run of consecutive scan indices
@@ -72,28 +74,46 @@ class GroupMember:
     def projection_indices(self):
         return [i for first, count in self.runs for i in range(first, first + count)]
 
-    def generate_inputs(self, ellipsoids_mm: np.ndarray, host: bool = True):
+    def generate_inputs(self, ellipsoids_mm: np.ndarray, host: bool = True, counts_scale: float | None = None):
         """This member's raw projections on the device (phantom kernel, local order) and, for the end-to-end steps,
-        mirrored in pinned host memory."""
+        mirrored in pinned host memory.  counts_scale: turn the line integrals into detector counts,
+        rint(value * scale) clipped to 16 bits -- what a 16-bit member needs, and what a float member is given when
+        the two are compared (the same numbers in the other sample type)."""
         n = max(self.my_count, 1)
-        self.d_raw = self.ctx.dev_alloc(n * self.px * 4)
+        d_float = self.ctx.dev_alloc(n * self.px * 4)
         local = 0
         for first, count in self.runs:
-            self.ctx.phantom_project(ellipsoids_mm, self.det, first, count, self.d_raw + local * self.px * 4)
+            self.ctx.phantom_project(ellipsoids_mm, self.det, first, count, d_float + local * self.px * 4)
             local += count
-        if host:
-            self.h_raw = capi.PinnedArray((n, self.det.n_col, self.det.n_row))
-            for i in range(self.my_count):
-                self.ctx.proj_d2h(self.d_raw + i * self.px * 4, self.h_raw.ptr + i * self.px * 4, self.det.n_row,
-                                  self.det.n_col)
+        if counts_scale is None:
+            if self.sample_bytes != 4:
+                raise ValueError("16-bit samples need counts_scale")
+            self.d_raw = d_float
+            if host:
+                self.h_raw = capi.PinnedArray((n, self.det.n_col, self.det.n_row))
+                for i in range(self.my_count):
+                    self.ctx.proj_d2h(d_float + i * self.px * 4, self.h_raw.ptr + i * self.px * 4, self.det.n_row,
+                                      self.det.n_col)
+            self.ctx.sync()
+            return
+        dtype = np.uint16 if self.sample_bytes == 2 else np.float32
+        self.h_raw = capi.PinnedArray((n, self.det.n_col, self.det.n_row), dtype=dtype)
+        line = np.empty((self.det.n_col, self.det.n_row), np.float32)
+        for i in range(self.my_count):
+            self.ctx.proj_d2h(d_float + i * self.px * 4, line, self.det.n_row, self.det.n_col)
+            self.ctx.sync()
+            self.h_raw.array[i] = np.clip(np.rint(line * np.float32(counts_scale)), 0, 65535).astype(dtype)
+        self.ctx.dev_free(d_float)
+        self.d_raw = self.ctx.dev_alloc(n * self.proj_bytes)
+        self.ctx.vol_h2d(self.h_raw.ptr, self.d_raw, n * self.proj_bytes // 4)
         self.ctx.sync()
 
     def host_sample(self, count: int, stride: int = 1) -> np.ndarray:
         """(count, n_col, n_row) raw projections, every stride-th of this member's (world == 1: of the scan)"""
-        return np.ascontiguousarray(self.h_raw.array[::stride][:count])
+        return np.ascontiguousarray(self.h_raw.array[::stride][:count], dtype=np.float32)
 
     def host_pointers(self):
-        return [self.h_raw.ptr + i * self.px * 4 for i in range(self.my_count)]
+        return [self.h_raw.ptr + i * self.proj_bytes for i in range(self.my_count)]
 
     def alloc_host_slabs(self):
         """pinned host memory of this member's own (for callers without a shared host volume)"""

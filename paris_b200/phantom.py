@@ -51,3 +51,15 @@ def scaled_ellipsoids(table: np.ndarray, radius_mm: float) -> np.ndarray:
     e = np.array(table, dtype=np.float64, copy=True)
     e[:, 1:7] *= radius_mm
     return e
+
+
+def line_integral_bound(ellipsoids_mm: np.ndarray) -> float:
+    """No ray through the phantom integrates to more than this: every ellipsoid of positive density at its longest
+    chord.  counts_scale(...) turns it into the factor that maps line integrals onto 16-bit detector counts."""
+    e = np.asarray(ellipsoids_mm, dtype=np.float64)
+    pos = e[e[:, 0] > 0]
+    return float((pos[:, 0] * 2.0 * pos[:, 1:4].max(axis=1)).sum())
+
+
+def counts_scale(ellipsoids_mm: np.ndarray, full_scale: float = 60000.0) -> float:
+    return full_scale / line_integral_bound(ellipsoids_mm)

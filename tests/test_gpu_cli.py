@@ -169,10 +169,17 @@ def test_cli_group_u16_roi_angles_quality_against_the_oracle(tmp_path, port):
     af.write_text("\n".join(repr(float(a)) for a in angles[:31]) + "\n")     # shorter than the scan: idx*delta_phi after it
     roi = oracle.Roi(5, 40, 8, 50, 3, 30)
     out = tmp_path / "out"
-    run_cli(["--geometry", geo, "--input", scan, "--output", str(out), "--angles", str(af), "--quality", "2", "--roi",
-             "--roi-x1", "5", "--roi-x2", "40", "--roi-y1", "8", "--roi-y2", "50", "--roi-z1", "3", "--roi-z2", "30"],
-            env={"PARIS_B200_GROUP": "1", "PARIS_B200_GROUP_MEMBERS": "3", "PARIS_B200_GROUP_TIMEOUT_S": "20"})
+    args = ["--geometry", geo, "--input", scan, "--angles", str(af), "--quality", "2", "--roi",
+            "--roi-x1", "5", "--roi-x2", "40", "--roi-y1", "8", "--roi-y2", "50", "--roi-z1", "3", "--roi-z2", "30"]
+    env = {"PARIS_B200_GROUP": "1", "PARIS_B200_GROUP_MEMBERS": "3", "PARIS_B200_GROUP_TIMEOUT_S": "20"}
+    r = run_cli(args + ["--output", str(out)], env=env)
+    # a scan of 16-bit files is uploaded as it is and widened by the filter kernel ...
+    assert r.stderr.count("16-bit projections filtered here") == 3
     got = formats.read_ddbvf(str(out / "vol.ddbvf"))
+    # ... which is the same volume, bit for bit, as widening on the host like src/his.cpp:98-99
+    r = run_cli(args + ["--output", str(tmp_path / "widened")], env=dict(env, PARIS_B200_SAMPLES="f32"))
+    assert "16-bit projections" not in r.stderr
+    assert np.array_equal(got, formats.read_ddbvf(str(tmp_path / "widened" / "vol.ddbvf")))
     used = list(range(0, N_PROJ, 2))
     full_angles = np.array([angles[i] if i < 31 else np.float32(i) * np.float32(odet.delta_phi) for i in range(N_PROJ)],
                            np.float32)

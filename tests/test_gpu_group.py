@@ -70,7 +70,7 @@ def _poison(member):
     member.ctx.sync()
 
 
-def _run_in_process(world, det, vol, n_proj, roi=None, e2e=True, **options):
+def _run_in_process(world, det, vol, n_proj, roi=None, e2e=True, counts_scale=None, **options):
     """`world` members on device 0 of this process; returns the assembled region"""
     if options.get("x_parts", 1) > 1 or e2e:
         # every member downloads its box straight into ONE region-wide host volume
@@ -80,7 +80,7 @@ def _run_in_process(world, det, vol, n_proj, roi=None, e2e=True, **options):
     handles = [m.export() for m in members]
     for m in members:
         m.connect(handles)
-        m.generate_inputs(_ellipsoids(det))
+        m.generate_inputs(_ellipsoids(det), counts_scale=counts_scale)
         _poison(m)
     info0 = members[0].info
     region = capi.PinnedArray((info0.region_z, info0.region_y, info0.region_x))
@@ -173,6 +173,54 @@ def test_whole_projection_exchange_is_the_same_volume(ctx):
     want = _one_piece(ctx, det, vol, n_proj)
     got, stats = _run_in_process(2, det, vol, n_proj, whole_projections=True, first_round=8, max_round=16)
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("world,e2e", [(1, True), (1, False), (2, True)])
+def test_sixteen_bit_samples_equal_the_same_counts_as_floats(ctx, world, e2e):
+    """Detector-native 16-bit counts (PARIS_B200_SAMPLES_U16: half the upload, widened by the filter kernel's first
+    load) against the very same counts handed over as floats (what the reference's reader produces on the host,
+    src/his.cpp:169-185): bit for bit, from host pointers and from device-resident samples."""
+    det, vol, n_proj = _case()
+    scale = phantom.counts_scale(_ellipsoids(det))          # the longest chord of the phantom stays inside 16 bits
+    as_f32, _ = _run_in_process(world, det, vol, n_proj, e2e=e2e, counts_scale=scale, first_round=8, max_round=16)
+    as_u16, _ = _run_in_process(world, det, vol, n_proj, e2e=e2e, counts_scale=scale, first_round=8, max_round=16,
+                                sample_type=capi.SAMPLES_U16)
+    assert np.isfinite(as_f32).all() and np.abs(as_f32).max() > 10.0
+    assert np.array_equal(as_u16, as_f32)
+
+
+def test_sixteen_bit_stage_call_equals_float_stage_call(ctx):
+    """paris_b200_filter_to_stack_batch_u16 against paris_b200_filter_to_stack_batch on the same counts, both stack
+    layouts, a batch of more projections than one launch takes"""
+    rng = np.random.default_rng(5)
+    n_proj = 70
+    for n, layout in ((128, capi.LAYOUT_PLAIN), (320, capi.LAYOUT_SPLIT2)):
+        det = capi.DetectorGeometry(n, n - 6, 0.4, 0.4, 0.0, 0.0, 500.0, 500.0, 360.0 / n_proj)
+        px = det.n_row * det.n_col
+        counts = rng.integers(0, 65536, size=(n_proj, det.n_col, det.n_row), dtype=np.uint16)
+        counts[0, 0, :4] = (0, 1, 65535, 32768)
+        as_float = counts.astype(np.float32)
+        d_u16, d_f32 = ctx.dev_alloc(n_proj * px * 2), ctx.dev_alloc(n_proj * px * 4)
+        ctx.vol_h2d(counts.view(np.float32), d_u16, counts.size // 2)
+        ctx.vol_h2d(as_float, d_f32, as_float.size)
+        filt = ctx.filter_create(capi.filter_size(det.n_row), float(det.l_px_row))
+        slot_bytes, _ = capi.stack_slot_bytes(det.n_row, det.n_col)
+        stacks = []
+        for u16 in (False, True):
+            stack = ctx.stack_alloc(det.n_row, det.n_col, n_proj)
+            ctx.vol_h2d(np.zeros(n_proj * slot_bytes // 4, np.float32), stack, n_proj * slot_bytes // 4)  # the pad columns
+            if u16:
+                ctx.filter_to_stack_batch_u16(d_u16, px, n_proj, det, filt, stack, 0, layout)
+            else:
+                ctx.filter_to_stack_batch(d_f32, px, n_proj, det, filt, stack, 0, layout)
+            out = np.empty(n_proj * slot_bytes // 4, np.float32)
+            ctx.vol_d2h(stack, out, out.size)
+            stacks.append(out)
+            ctx.stack_free(stack)
+        assert np.abs(stacks[0]).max() > 0 and np.array_equal(stacks[0], stacks[1])
+        ctx.filter_destroy(filt)
+        ctx.dev_free(d_u16)
+        ctx.dev_free(d_f32)
 
 
 # ---- one process per GPU over CUDA IPC (needs two devices) ---------------------------------------------------------
