@@ -182,6 +182,45 @@ extern "C"
         return r == paris::parse_result::ok ? 0 : r == paris::parse_result::exit_success ? 1 : 2;
     }
 
+    // The scan index the group driver plans with (no decoding, no device): per kept projection its frame counter,
+    // its angle and whether that came from the angle file; scan3 = {dim_x, dim_y, 1 if every file holds 16-bit
+    // samples}.  Returns the count.
+    int paris_b200_io_scan_index(const char* dir, int enable_angles, const char* angle_file, std::uint32_t quality,
+                                 std::uint32_t* idx, float* phi, int* from_file, std::uint32_t capacity, std::uint32_t* scan3,
+                                 char* err, std::size_t err_len)
+    {
+        return guarded(err, err_len, [&] {
+            const auto scan = paris::make_scan_index(dir, enable_angles != 0, angle_file ? angle_file : "",
+                                                     static_cast<std::uint16_t>(quality));
+            for(auto i = std::size_t{0}; i < scan.frames.size() && i < capacity; ++i)
+            {
+                idx[i] = scan.frames[i].idx;
+                phi[i] = scan.frames[i].phi;
+                from_file[i] = scan.frames[i].has_angle ? 1 : 0;
+            }
+            scan3[0] = scan.dim_x;
+            scan3[1] = scan.dim_y;
+            scan3[2] = paris::scan_is_u16(scan) ? 1u : 0u;
+            return static_cast<int>(scan.frames.size());
+        });
+    }
+
+    // projection i of that scan: widened to float into out_f32 and / or as 16-bit counts into out_u16 (either may be
+    // null); bit 0 / bit 1 of the result say which of the two reads succeeded
+    int paris_b200_io_scan_frame(const char* dir, std::uint32_t quality, std::uint32_t i, float* out_f32,
+                                 std::uint16_t* out_u16, char* err, std::size_t err_len)
+    {
+        return guarded(err, err_len, [&] {
+            const auto scan = paris::make_scan_index(dir, false, "", static_cast<std::uint16_t>(quality));
+            auto got = 0;
+            if(out_f32 != nullptr && paris::load_scan_frame(scan, i, out_f32))
+                got |= 1;
+            if(out_u16 != nullptr && paris::load_scan_frame_u16(scan, i, out_u16))
+                got |= 2;
+            return got;
+        });
+    }
+
     // drains a projection source (pinned host memory: needs a CUDA device) and reports, per projection handed out,
     // its index, angle and whether the angle came from the file; returns the count
     int paris_b200_io_source_walk(const char* dir, int enable_angles, const char* angle_file, std::uint32_t quality,

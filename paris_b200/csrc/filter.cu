@@ -387,8 +387,10 @@ namespace pb
                 for(int k = 0; k < 8; ++k)
                 {
                     const uint32_t i = b + k * (N / 16);
-                    pa[k] = (i < dim_x && has0) ? static_cast<float>(__ldg(s0 + k * (N / 16))) : 0.f;
-                    pc[k] = (i < dim_x && has1) ? static_cast<float>(__ldg(s1 + k * (N / 16))) : 0.f;
+                    // (the counts stay integers in the prefetch registers: converting here would make the warp wait
+                    // for its loads right away instead of one round later, where they are used)
+                    pa[k] = __uint_as_float((i < dim_x && has0) ? static_cast<uint32_t>(__ldg(s0 + k * (N / 16))) : 0u);
+                    pc[k] = __uint_as_float((i < dim_x && has1) ? static_cast<uint32_t>(__ldg(s1 + k * (N / 16))) : 0u);
                 }
                 return;
             }
@@ -434,6 +436,12 @@ namespace pb
                 {
                     a = pa[k];
                     c = pc[k];
+                    if(io.src_u16)
+                    {
+                        // src/his.cpp:98-99: the detector's 16-bit count as a float
+                        a = static_cast<float>(__float_as_uint(a));
+                        c = static_cast<float>(__float_as_uint(c));
+                    }
                     if(w.enable)
                     {
                         const uint32_t i = b + k * (N / 16);

@@ -11,9 +11,10 @@
 //              peer memory, copy engines (cudaMemcpy2DAsync on a stream of its own: no SM-resident collective next
 //              to the backprojection) -- and only the BAND of detector rows the peer's slabs can ever read (the
 //              scheme sketched in doc "Geometrie - Definitionen fuer Subvolumen", never implemented in the reference):
-//              ~1/world of the bytes of an all-gather.  Arrival is announced by a stream memory operation on a flag
-//              word in the peer's memory; the consumer's backprojection stream waits on its own flags
-//              (cuStreamWaitValue32).  No host synchronisation anywhere inside a step;
+//              ~1/world of the bytes of an all-gather.  Arrival is announced by a stream memory operation
+//              (cuStreamWriteValue32) on a flag word in the peer's memory; the consumer's backprojection stream waits
+//              on its own flags with a one-thread polling kernel that gives up after a timeout (wait_flag_kernel).
+//              No host synchronisation anywhere inside a step;
 //   member r   backprojects ALL projections into its z-slabs (no reduction) and streams them to the host: several
 //              slabs per member loop over the ONE gathered stack, the download of slab k running behind the
 //              backprojection of slab k + 1; the host volume is assembled by writing every slab at its offset.
@@ -88,12 +89,12 @@ namespace pb
     }
 
     // The consumer's side of an arrival flag: ONE thread polls the word (flags only grow: cyclic comparison) and the
-    // stream continues when it has reached `value`.  A kernel rather than a stream memory operation for the wait: a
-    // cuStreamWaitValue32 blocks the hardware queue its stream is mapped to, and whatever other stream shares that
-    // queue -- the exchange stream whose signal a peer is waiting for, say -- stalls behind it (measured: members
-    // that share one GPU deadlocked that way).  A polling thread holds nothing but one warp slot.  It also cannot
-    // wait for ever: after `timeout_ns` it records the failure in *error and lets the stream go on, so a member that
-    // died takes the step down with an error instead of hanging the GPU.
+    // stream continues when it has reached `value`.  A kernel rather than cuStreamWaitValue32 for two reasons: it
+    // cannot wait for ever -- after `timeout_ns` it records the failure in *error and lets the stream go on, so a
+    // member that died takes the step down with an error instead of hanging the GPU -- and it holds nothing but one
+    // warp slot, where a memory-operation wait occupies the hardware queue its stream is mapped to together with
+    // whatever other stream shares that queue (with members sharing one GPU that can be the exchange stream whose
+    // signal a peer is waiting for).  PARIS_B200_GROUP_WAIT=memop selects the memory operation for comparison.
     __global__ void wait_flag_kernel(const uint32_t* flag, uint32_t value, unsigned long long timeout_ns, uint32_t* error,
                                      uint32_t code)
     {
@@ -160,8 +161,8 @@ struct paris_b200_group
     std::vector<bool> peer_ipc;
     bool connected = false;
 
-    float* raw[2] = {nullptr, nullptr};         // upload buffers, one round each
-    size_t raw_floats = 0;
+    float* raw[2] = {nullptr, nullptr};         // upload buffers, one round each (floats or 16-bit counts)
+    size_t raw_bytes = 0;
     cudaEvent_t raw_free[2] = {nullptr, nullptr};      // the filter launch that read raw[i] has run
     bool raw_free_valid[2] = {false, false};
     std::vector<cudaEvent_t> filtered;          // per round: this member's share is in the stack
@@ -573,10 +574,10 @@ extern "C" int paris_b200_group_create(int device, const paris_b200_group_config
     PB_GCUDA(cudaMemsetAsync(g->stack, 0, g->slot_floats * cfg->n_proj * sizeof(float), g->ctx->compute));
     PB_GCUDA(cudaMalloc(reinterpret_cast<void**>(&g->flags), 2u << 20));   // (an allocation of its own: exportable)
     PB_GCUDA(cudaMemsetAsync(g->flags, 0, 2u << 20, g->ctx->compute));
-    g->raw_floats = std::max<size_t>(max_share, 1u) * g->px;
+    g->raw_bytes = std::max<size_t>(max_share, 1u) * g->px * g->sample_bytes;
     for(int i = 0; i < 2; ++i)
     {
-        PB_GCUDA(cudaMalloc(reinterpret_cast<void**>(&g->raw[i]), g->raw_floats * sizeof(float)));
+        PB_GCUDA(cudaMalloc(reinterpret_cast<void**>(&g->raw[i]), g->raw_bytes));
         PB_GCUDA(cudaEventCreateWithFlags(&g->raw_free[i], cudaEventDisableTiming));
     }
     PB_GCUDA(cudaEventCreateWithFlags(&g->pushed, cudaEventDisableTiming));
@@ -758,14 +759,14 @@ extern "C" int paris_b200_group_connect(paris_b200_group* g, const unsigned char
             PB_CUDA(cudaIpcOpenMemHandle(&ps, h.stack_ipc, cudaIpcMemLazyEnablePeerAccess));
             PB_CUDA(cudaIpcOpenMemHandle(&pf, h.flags_ipc, cudaIpcMemLazyEnablePeerAccess));
             g->peer_ipc[k] = true;
+            g->peer_stack[k] = static_cast<float*>(ps);   // (recorded first: group_destroy unmaps whatever was mapped)
+            g->peer_flags[k] = static_cast<uint32_t*>(pf);
             if(h.stack_off != 0 || h.flags_off != 0)
             {
                 set_error("peer %u exported pointers inside larger allocations (offsets %llu, %llu): unsupported", k,
                           static_cast<unsigned long long>(h.stack_off), static_cast<unsigned long long>(h.flags_off));
                 return PARIS_B200_ESTATE;
             }
-            g->peer_stack[k] = static_cast<float*>(ps);
-            g->peer_flags[k] = static_cast<uint32_t*>(pf);
         }
     }
     g->connected = true;

@@ -44,6 +44,9 @@ def _lib() -> C.CDLL:
                                                   C.c_size_t]
         L.paris_b200_io_source_walk.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_uint32, _u32p, _fp,
                                                 C.POINTER(C.c_int), _fp, C.c_uint32] + err
+        L.paris_b200_io_scan_index.argtypes = [C.c_char_p, C.c_int, C.c_char_p, C.c_uint32, _u32p, _fp,
+                                               C.POINTER(C.c_int), C.c_uint32, _u32p] + err
+        L.paris_b200_io_scan_frame.argtypes = [C.c_char_p, C.c_uint32, C.c_uint32, _fp, C.POINTER(C.c_uint16)] + err
         _ready = True
     return L
 
@@ -162,3 +165,29 @@ def source_walk(directory: str, angle_file: str | None, quality: int, capacity: 
     if n < 0:
         raise IoError(e.value.decode())
     return idx[:n].copy(), phi[:n].copy(), from_file[:n].copy(), first[:n].copy()
+
+
+def scan_index(directory: str, angle_file: str | None, quality: int, capacity: int = 4096):
+    """The scan as the group driver indexes it (no decoding, no device): (idx, phi, angle_from_file) per kept
+    projection and (dim_x, dim_y, every file holds 16-bit samples)."""
+    idx, phi = np.zeros(capacity, np.uint32), np.zeros(capacity, np.float32)
+    from_file, scan3 = np.zeros(capacity, np.int32), np.zeros(3, np.uint32)
+    e = _err()
+    n = _lib().paris_b200_io_scan_index(directory.encode(), int(angle_file is not None), (angle_file or "").encode(),
+                                        quality, idx.ctypes.data_as(_u32p), phi.ctypes.data_as(_fp),
+                                        from_file.ctypes.data_as(C.POINTER(C.c_int)), capacity,
+                                        scan3.ctypes.data_as(_u32p), e, len(e))
+    if n < 0:
+        raise IoError(e.value.decode())
+    return idx[:n].copy(), phi[:n].copy(), from_file[:n].copy(), (int(scan3[0]), int(scan3[1]), bool(scan3[2]))
+
+
+def scan_frame(directory: str, quality: int, i: int, dim_x: int, dim_y: int):
+    """Projection i of the scan: (widened to float or None, as 16-bit counts or None)"""
+    f32, u16 = np.zeros((dim_y, dim_x), np.float32), np.zeros((dim_y, dim_x), np.uint16)
+    e = _err()
+    got = _lib().paris_b200_io_scan_frame(directory.encode(), quality, i, f32.ctypes.data_as(_fp),
+                                          u16.ctypes.data_as(C.POINTER(C.c_uint16)), e, len(e))
+    if got < 0:
+        raise IoError(e.value.decode())
+    return (f32 if got & 1 else None), (u16 if got & 2 else None)

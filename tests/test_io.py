@@ -75,6 +75,51 @@ def test_his_truncated_file_keeps_complete_frames(tmp_path):
     assert got.shape[0] == 2 and np.array_equal(got, src[:2].astype(np.float32))
 
 
+# ---- the scan index of the group driver (which file and frame is projection i; 16-bit frames as they are) -----------
+
+def _write_scan(tmp_path, types=(4, 4, 4), frames=(3, 5, 2), h=6, w=8):
+    d = tmp_path / "scan"
+    d.mkdir()
+    all_frames = []
+    for k, (t, n) in enumerate(zip(types, frames)):
+        src = frames_for(t, n=n, h=h, w=w, seed=77 + k)
+        formats.write_his(str(d / f"p_{k:02d}.his"), src, t, image_header_size=(0, 32, 100)[k % 3])
+        all_frames += [src[i] for i in range(n)]
+    (d / "p_00x.his").write_bytes(b"garbage")              # invalid files are skipped (src/source.cpp:97)
+    return str(d), all_frames
+
+
+@pytest.mark.parametrize("quality", [1, 2, 3])
+def test_scan_index_numbers_frames_like_the_source(tmp_path, quality):
+    d, frames = _write_scan(tmp_path)
+    af = tmp_path / "angles.txt"
+    af.write_text("\n".join(f"{1.5 * i}" for i in range(7)) + "\n")         # shorter than the scan (10 frames)
+    idx, phi, from_file, (dim_x, dim_y, is_u16) = pio.scan_index(d, str(af), quality)
+    kept = [i for i in range(len(frames)) if i % quality == 0]               # src/source.cpp:105
+    assert list(idx) == kept and (dim_x, dim_y, is_u16) == (8, 6, True)
+    assert [bool(f) for f in from_file] == [i < 7 for i in kept]
+    assert all(phi[k] == np.float32(1.5 * i) for k, i in enumerate(kept) if i < 7)
+    for k, i in enumerate(kept):
+        f32, u16 = pio.scan_frame(d, quality, k, dim_x, dim_y)
+        assert np.array_equal(u16, frames[i]) and u16.dtype == np.uint16      # the file's own samples
+        assert np.array_equal(f32, frames[i].astype(np.float32))              # src/his.cpp:98-99
+    assert pio.scan_frame(d, quality, len(kept), dim_x, dim_y) == (None, None)
+
+
+def test_scan_of_mixed_sample_types_is_not_taken_as_sixteen_bit(tmp_path):
+    d, frames = _write_scan(tmp_path, types=(4, 128, 4))
+    _, _, _, (dim_x, dim_y, is_u16) = pio.scan_index(d, None, 1)
+    assert not is_u16
+    f32, u16 = pio.scan_frame(d, 1, 0, dim_x, dim_y)                          # a frame of a 16-bit file
+    assert np.array_equal(u16, frames[0]) and np.array_equal(f32, frames[0].astype(np.float32))
+    f32, u16 = pio.scan_frame(d, 1, 4, dim_x, dim_y)                          # a frame of the float file
+    assert u16 is None and np.array_equal(f32, frames[4])
+    # every-other-frame scans whose kept frames all sit in 16-bit files ARE 16-bit scans
+    d2, _ = _write_scan(tmp_path / "b", types=(4, 128, 4), frames=(2, 1, 2)) if (tmp_path / "b").mkdir() is None else None
+    idx, _, _, (_, _, is_u16) = pio.scan_index(d2, None, 4)
+    assert list(idx) == [0, 4] and is_u16
+
+
 def test_his_golden_written_for_the_reference_reader():
     p = os.path.join(GOLDEN, "io_u16.his")
     want = np.load(os.path.join(GOLDEN, "io_u16_frames.npy"))      # what the reference's his::load returned
