@@ -371,6 +371,16 @@ class SharedHostVolume:
                 self.shm.unlink()
 
 
+def auto_x_parts(world: int, dims, spm: int, full_region: bool) -> int:
+    """Parts along x of the boxes the GPUs own (see the comment where run_b200 calls it)."""
+    x_parts = 1
+    if world >= 4 and world % 2 == 0 and spm == 1 and full_region and dims[0] // (world // 2) >= 64:
+        x_parts = world // 2
+    while x_parts < world and world % (2 * x_parts) == 0 and dims[2] * x_parts // world < 128 * spm:
+        x_parts *= 2
+    return x_parts
+
+
 def run_b200(args, rank: int, world: int, local_rank: int):
     from paris_b200 import capi, dropin, phantom
     from paris_b200.multi import GroupMember
@@ -393,13 +403,14 @@ def run_b200(args, rank: int, world: int, local_rank: int):
     updates = voxels * n_proj
     spm = args.slabs_per_gpu if args.slabs_per_gpu else (2 if args.config == "c5" else 1)
 
-    # few slices per GPU (config 2 at N=8: 64): cut along x as well, so that every GPU keeps z-runs of >= 128 slices and
-    # with them the 8x8x128 tiles (one table entry per four updates of a lane instead of per two)
-    x_parts = args.x_parts
-    if x_parts == 0:
-        x_parts = 1
-        while x_parts < world and world % (2 * x_parts) == 0 and dims[2] * x_parts // world < 128 * spm:
-            x_parts *= 2
+    # Which box of the region a GPU owns.  Plain z-slabs are not equally expensive: the outermost 128 slices cost 11 %
+    # more than inner ones (profiles/r2_slab_times_c3.json: their near-source voxels project beyond the detector's
+    # top and bottom rows, so their tiles run the boundary path), and the step is as long as its slowest slab.  From
+    # four GPUs on the region is therefore cut into TWO mirror z-runs, each of which holds one outermost block, times
+    # world/2 parts along x (measured at N=8: config 3 174.9 instead of 181.8 ms, config 2 unchanged; at N=4 the
+    # four boxes are mirror images of each other).  It also keeps z-runs of >= 128 slices and with them the 8x8x128
+    # tiles on volumes with few slices per GPU (config 2 at N=8: 64).
+    x_parts = args.x_parts if args.x_parts else auto_x_parts(world, dims, spm, roi is None)
     shared_volume = world > 1 and voxels * 4 <= (8 << 30)
     u16 = args.samples == "u16"
     member = GroupMember(local_rank, rank, world, det, vol, n_proj, roi=roi, slabs_per_member=spm, x_parts=x_parts,
@@ -670,7 +681,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--clock-interval-ms", type=int, default=100, help="NVML sampling period")
     ap.add_argument("--slabs-per-gpu", type=int, default=0, help="z-slabs every GPU streams (0: 2 for config 5, else 1)")
-    ap.add_argument("--x-parts", type=int, default=0, help="parts along x (0: automatic, keeps >= 128 slices per GPU)")
+    ap.add_argument("--x-parts", type=int, default=0, help="parts along x (0: automatic -- from 4 GPUs on two mirror z-runs x N/2 x-parts for full regions)")
     ap.add_argument("--exchange", default="copy-engine", choices=["copy-engine", "kernel"])
     ap.add_argument("--samples", default="f32", choices=["f32", "u16"],
                     help="raw projections as floats (what the reference's reader hands on) or as 16-bit detector counts")

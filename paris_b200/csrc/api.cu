@@ -77,6 +77,8 @@ extern "C" int paris_b200_ctx_create(int device, paris_b200_ctx** out)
     auto* ctx = new paris_b200_ctx{};
     ctx->device = device;
     ctx->sm_count = prop.multiProcessorCount;
+    if(const char* e = std::getenv("PARIS_B200_FILTER_WIDE"))   // (A/B of the 4096-point filter's CTA shape)
+        ctx->filter_wide = std::atoi(e) != 0 ? 1 : 0;
     // (a context whose streams or events cannot all be created is taken apart again, not leaked)
     const auto build = [&]() -> int {
         PB_CUDA(cudaStreamCreateWithFlags(&ctx->compute, cudaStreamNonBlocking));
@@ -261,6 +263,12 @@ extern "C" int paris_b200_ctx_set_option(paris_b200_ctx* ctx, const char* name, 
         PB_CHECK_ARG(value >= 0 && value <= 64);
         PB_TRY(paris_b200_flush(ctx));
         ctx->bp_swizzle = static_cast<int>(value);
+        return PARIS_B200_OK;
+    }
+    if(std::strcmp(name, "filter_wide") == 0)
+    {
+        PB_CHECK_ARG(value == 0 || value == 1);
+        ctx->filter_wide = static_cast<int>(value);
         return PARIS_B200_OK;
     }
     if(std::strcmp(name, "bp_tile") == 0)

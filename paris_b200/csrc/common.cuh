@@ -107,6 +107,7 @@ struct paris_b200_ctx
     int bp_batch = 256;
     int bp_kernel = 0;
     int bp_tile = 0;     // 0: half tiles (two CTAs per SM) when the footprint fits, 1: full tiles only
+    int filter_wide = 1; // 4096-point transforms: two row pairs per 512-thread CTA (16 warps per SM) instead of one per 256
     int bp_swizzle = 16; // CTAs numbered in bp_swizzle x bp_swizzle super-blocks of (x, y) tiles; 0: row-major
 
     // pooled raw projection buffers (dev_alloc / dev_free)

@@ -317,7 +317,11 @@ namespace pb
     // ---- group plan ------------------------------------------------------------------------------------------
     // Passes with span > 16 ("outer"), first to last: 2^LOG2N, 2^(LOG2N-2), ... down to 2^6 (LOG2N even) or
     // 2^5 (odd).  They are taken two at a time from the top; an odd one out is a lone radix-4 group.
-    template <int LOG2N>
+    // WIDE: twice the row pairs side by side (512 threads).  Only the 4096-point transform uses it: its 256-thread
+    // CTA needs 165 KB of shared memory (twiddles, one transform, the staging tile), so ONE CTA = 8 warps lives on
+    // an SM and the kernel waits on latencies; two transforms in one 512-thread CTA share the twiddles and the
+    // staging tile (181 KB) and give the schedulers 16 warps.
+    template <int LOG2N, bool WIDE = false>
     struct plan
     {
         static_assert(LOG2N >= 8 && LOG2N <= 13, "register-grouped kernel covers 256..8192 points");
@@ -328,7 +332,8 @@ namespace pb
         static constexpr int OUTER = (LOG2N - LOW) / 2 + 1;               // 2 (256) .. 5 (8192)
         static constexpr int DOUBLES = OUTER / 2;                         // 1 or 2
         static constexpr bool LONE = (OUTER % 2) != 0;
-        static constexpr int PAIRS = (256 / T) < 4 ? ((256 / T) < 1 ? 1 : 256 / T) : 4;  // row pairs side by side (<= 256 threads: two CTAs per SM in different phases)
+        static constexpr int NARROW = (256 / T) < 4 ? ((256 / T) < 1 ? 1 : 256 / T) : 4;
+        static constexpr int PAIRS = (WIDE && NARROW * T == 256 && NARROW < 4) ? 2 * NARROW : NARROW;  // row pairs side by side (<= 256 threads: two CTAs per SM in different phases)
         static constexpr int ROUNDS = 4 / PAIRS;
         static constexpr int THREADS = PAIRS * T;
         static constexpr int NPAD = pad(N);
@@ -343,13 +348,13 @@ namespace pb
                                        // widening is the kernel's first load, so that half the bytes cross PCIe and HBM
     };
 
-    template <int LOG2N, bool TRANSPOSED>
-    __global__ void __launch_bounds__(plan<LOG2N>::THREADS, plan<LOG2N>::THREADS <= 256 ? 2 : 1)
+    template <int LOG2N, bool TRANSPOSED, bool WIDE = false>
+    __global__ void __launch_bounds__((plan<LOG2N, WIDE>::THREADS), (plan<LOG2N, WIDE>::THREADS <= 256 ? 2 : 1))
     filter_kernel(const filter_batch io, float* dst_stack, uint32_t first_slot, size_t slot_floats, uint32_t dim_x,
                   uint32_t dim_y, uint32_t n_proj, const float* __restrict__ knp, const float2* __restrict__ tw,
                   weight_params w, uint32_t dst_pitch, uint32_t layout)
     {
-        using P = plan<LOG2N>;
+        using P = plan<LOG2N, WIDE>;
         constexpr int N = P::N;
         constexpr int TWC = P::TW_SMEM ? 3 * (2 * N - 8) / 4 : 0;   // entries of the compact twiddle tables kept on chip
         extern __shared__ __align__(16) unsigned char smem_raw[];
@@ -588,13 +593,13 @@ namespace pb
         }
     }
 
-    template <int LOG2N>
+    template <int LOG2N, bool WIDE = false>
     static int launch_grouped(paris_b200_ctx* ctx, const filter_batch& io, uint32_t count, float* d_stack,
                               uint32_t first_slot, size_t slot_floats, uint32_t dim_x, uint32_t dim_y,
                               const paris_b200_filter* f, const weight_params& w, bool transposed, uint32_t pitch,
                               uint32_t layout)
     {
-        using P = plan<LOG2N>;
+        using P = plan<LOG2N, WIDE>;
         constexpr size_t twc_bytes = P::TW_SMEM ? sizeof(float2) * (3 * (2 * P::N - 8) / 4) : 0;
         const size_t smem = twc_bytes + sizeof(float2) * P::NPAD * P::PAIRS
                           + (transposed ? sizeof(float) * kStagePitch * dim_x : 0);
@@ -610,14 +615,14 @@ namespace pb
         const uint32_t grid = std::min<uint32_t>(items, per_sm * static_cast<uint32_t>(ctx->sm_count));
         if(transposed)
         {
-            auto kern = filter_kernel<LOG2N, true>;
+            auto kern = filter_kernel<LOG2N, true, WIDE>;
             PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             kern<<<grid, P::THREADS, smem, ctx->compute>>>(io, d_stack, first_slot, slot_floats, dim_x, dim_y, count, f->d_knp,
                                                           f->d_twc, w, pitch, layout);
         }
         else
         {
-            auto kern = filter_kernel<LOG2N, false>;
+            auto kern = filter_kernel<LOG2N, false, WIDE>;
             PB_CUDA(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, static_cast<int>(smem)));
             kern<<<grid, P::THREADS, smem, ctx->compute>>>(io, nullptr, 0u, 0, dim_x, dim_y, count, f->d_knp, f->d_twc, w, 0u,
                                                           kLayoutPlain);
@@ -644,7 +649,14 @@ namespace pb
             case 512: preload_grouped<9>(); break;
             case 1024: preload_grouped<10>(); break;
             case 2048: preload_grouped<11>(); break;
-            case 4096: preload_grouped<12>(); break;
+            case 4096:
+            {
+                preload_grouped<12>();
+                cudaFuncAttributes a{};
+                (void)cudaFuncGetAttributes(&a, filter_kernel<12, true, true>);
+                (void)cudaFuncGetAttributes(&a, filter_kernel<12, false, true>);
+                break;
+            }
             case 8192: preload_grouped<13>(); break;
             default: preload_filter_small_kernels(size); break;
         }
@@ -706,7 +718,15 @@ namespace pb
             case 512: return launch_grouped<9>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch, layout);
             case 1024: return launch_grouped<10>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch, layout);
             case 2048: return launch_grouped<11>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch, layout);
-            case 4096: return launch_grouped<12>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch, layout);
+            case 4096:
+            {
+                // two transforms per CTA when the staging tile leaves room for them ("filter_wide", default on)
+                const size_t wide_smem = sizeof(float2) * (3 * (2 * 4096 - 8) / 4) + sizeof(float2) * plan<12, true>::NPAD * 2
+                                       + (transposed ? sizeof(float) * kStagePitch * dim_x : 0);
+                if(ctx->filter_wide != 0 && wide_smem <= 227u * 1024u)
+                    return launch_grouped<12, true>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch, layout);
+                return launch_grouped<12>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch, layout);
+            }
             case 8192: return launch_grouped<13>(ctx, io, count, d_stack, first_slot, slot_floats, dim_x, dim_y, f, w, transposed, pitch, layout);
             default: break;
         }

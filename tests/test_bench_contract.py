@@ -51,3 +51,24 @@ def test_final_single_gpu_line_has_clocks_and_cpu_baseline():
     assert d["clocks"]["sm_mhz"] and d["clocks"]["sm_max_mhz"] and isinstance(d["clocks"]["reasons"], list)
     assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["value"] > 0
     assert "512^3" in d["config"]["workload"]
+
+
+def test_boxes_of_the_gpus_are_balanced_from_four_gpus_on():
+    """bench.auto_x_parts: z-slabs up to two GPUs (two halves are mirror images), two mirror z-runs x N/2 x-parts from
+    four GPUs on for full regions, z-slabs for ROI regions and streamed slabs, and never fewer than 128 slices per
+    GPU where the GPU count allows it; the plan accepts every choice."""
+    import bench
+    from paris_b200 import capi
+    assert [bench.auto_x_parts(n, (1024, 1024, 1024), 1, True) for n in (1, 2, 4, 8)] == [1, 1, 2, 4]
+    assert [bench.auto_x_parts(n, (512, 512, 512), 1, True) for n in (1, 2, 4, 8)] == [1, 1, 2, 4]
+    assert bench.auto_x_parts(8, (1024, 1024, 1024), 1, False) == 1          # ROI regions keep their z-slabs
+    assert bench.auto_x_parts(8, (2048, 2048, 2048), 2, True) == 1           # streamed slabs (config 5)
+    assert bench.auto_x_parts(8, (512, 512, 512), 1, False) == 2             # 64 slices per GPU otherwise
+    assert bench.auto_x_parts(3, (1024, 1024, 1024), 1, True) == 1
+    for name in ("c2", "c3"):
+        det, vol, n_proj, roi, dims = bench.geometry(name)
+        for world in (4, 8):
+            xp = bench.auto_x_parts(world, dims, 1, roi is None)
+            plans = [capi.group_plan(capi.group_config(r, world, det, vol, n_proj, roi=roi, x_parts=xp)) for r in range(world)]
+            assert all(p.x_parts == xp and p.slabs_total == world // xp for p in plans)
+            assert plans[0].slab_dz * (world // xp) == dims[2] and plans[0].x_dx * xp == dims[0]

@@ -71,6 +71,58 @@ def test_weight_filter_fused_equals_stages(ctx, port):
     assert np.abs(ga - ref).max() <= 2e-6 * np.abs(ref).max()
 
 
+@pytest.mark.parametrize("layout", [capi.LAYOUT_PLAIN, capi.LAYOUT_SPLIT2])
+def test_filter_two_row_pairs_per_cta_equals_one(ctx, port, layout):
+    """4096-point transforms run two row pairs per 512-thread CTA ("filter_wide", the default) or one per 256 threads:
+    the same arithmetic per transform, so the same bits -- rows that do not fill the last 8-row block, both stack
+    layouts, float and 16-bit samples, and the row-major form against the oracle."""
+    n_row, n_col, n_proj = 2048, 43, 3
+    odet, det = both_det(n_row, n_col, l_px=0.2, n_proj=n_proj)
+    rng = np.random.default_rng(11)
+    counts = rng.integers(0, 65536, size=(n_proj, n_col, n_row), dtype=np.uint16)
+    as_float = counts.astype(np.float32)
+    px = n_row * n_col
+    d_f32, d_u16 = ctx.dev_alloc(as_float.nbytes), ctx.dev_alloc(counts.nbytes)
+    ctx.vol_h2d(as_float, d_f32, as_float.size)
+    ctx.vol_h2d(counts.view(np.float32), d_u16, counts.size // 2)
+    filt = ctx.filter_create(capi.filter_size(n_row), float(det.l_px_row))
+    slot_bytes, _ = capi.stack_slot_bytes(n_row, n_col)
+    got = {}
+    try:
+        for wide in (1, 0):
+            ctx.set_option("filter_wide", wide)
+            for u16 in (False, True):
+                stack = ctx.stack_alloc(n_row, n_col, n_proj)
+                ctx.vol_h2d(np.zeros(n_proj * slot_bytes // 4, np.float32), stack, n_proj * slot_bytes // 4)
+                if u16:
+                    ctx.filter_to_stack_batch_u16(d_u16, px, n_proj, det, filt, stack, 0, layout)
+                else:
+                    ctx.filter_to_stack_batch(d_f32, px, n_proj, det, filt, stack, 0, layout)
+                out = np.empty(n_proj * slot_bytes // 4, np.float32)
+                ctx.vol_d2h(stack, out, out.size)
+                ctx.stack_free(stack)
+                got[(wide, u16)] = out
+            # the row-major form (apply_filter of the contract) against the oracle
+            pl = Pipeline(ctx, det)
+            d = pl.load(as_float[0])
+            pl.filter(d)
+            rm = pl.download(d)
+            pl.release(d)
+            pl.close()
+            ref = port.filter(as_float[0], odet)
+            assert np.abs(rm - ref).max() <= 2e-6 * np.abs(ref).max()
+            got[(wide, "rows")] = rm
+    finally:
+        ctx.set_option("filter_wide", 1)
+        ctx.filter_destroy(filt)
+        ctx.dev_free(d_f32)
+        ctx.dev_free(d_u16)
+    assert np.abs(got[(1, False)]).max() > 0
+    assert np.array_equal(got[(1, False)], got[(0, False)]) and np.array_equal(got[(1, True)], got[(0, True)])
+    assert np.array_equal(got[(1, False)], got[(1, True)])
+    assert np.array_equal(got[(1, "rows")], got[(0, "rows")])
+
+
 def _recon_case(n, n_proj, coarse=None, delta_s=0.0):
     odet, det = both_det(n, n, n_proj=n_proj, delta_s=delta_s)
     P = oracle.Port()
