@@ -115,7 +115,9 @@ int paris_b200_event_destroy(paris_b200_event* ev);
 
 /* Tunables.  "bp_batch": projections accumulated per backprojection launch (default 256, max 256);
  * "bp_kernel": 0 = auto, 1 = generic L1-gather kernel, 2 = TMA-staged kernel.
- * "bp_tile": 0 = auto (16x8x64 voxel tiles, two CTAs per SM, when the footprint fits), 1 = 16x16x64 tiles only. */
+ * "bp_tile": 0 = auto (16x8x64 voxel tiles, two CTAs per SM, when the footprint fits), 1 = 16x16x64 tiles only.
+ * "bp_swizzle": backprojection CTAs are numbered in n x n super-blocks of (x, y) tiles (default 16; 0 = row-major).
+ * "filter_wide": 4096-point transforms with two row pairs per 512-thread CTA (1, default) or one per 256 (0). */
 int paris_b200_ctx_set_option(paris_b200_ctx* ctx, const char* name, int64_t value);
 
 /* ---- geometry (host-side, pure arithmetic) ------------------------------------------------ */
