@@ -40,8 +40,12 @@ CAPTURES = {
         "backprojection": {"what": "second launch of scripts/quick_bench.py --det 2048 --vol 1024 --proj 480 --batch 256: 240 "
                                    "projections of 2048^2 into the 1024^3 volume (config 3 geometry)",
                            "algorithmic_bytes": 240 * 2048 * 2048 * 4 + 2 * 1024 ** 3 * 4},
-        "fused": {"what": "one launch of the fused weight+filter kernel over 256 projections of 2048^2 (N = 4096)",
+        "fused": {"what": "one launch of the fused weight+filter kernel over 256 projections of 2048^2 (N = 4096), one "
+                          "transform per 256-thread CTA (filter_wide = 0, the shape before the last kernel change)",
                   "algorithmic_bytes": 8 * 2048 * 2048 * 256},
+        "fused-wide": {"what": "the same launch with two transforms per 512-thread CTA (filter_wide = 1, the default), "
+                               "scripts/quick_bench.py --det 2048 --vol 256 --proj 256 --batch 256 --reps 1",
+                       "algorithmic_bytes": 8 * 2048 * 2048 * 256},
     },
 }
 summary = {}
@@ -50,7 +54,8 @@ lines = [f"# ncu summaries, round {tag}", "",
          "same command had exited 0 without ncu.  Durations under ncu are serialised and cold-cache: use the bench's",
          "CUDA-event numbers for speed, these for WHERE the time goes.", ""]
 for name, rep in (("backprojection (bp_tma_kernel)", f"gpurun_out/bp_{tag}_final.ncu-rep"),
-                  ("fused weight+filter (filter_kernel)", f"gpurun_out/filter_{tag}_final.ncu-rep")):
+                  ("fused weight+filter (filter_kernel)", f"gpurun_out/filter_{tag}_final.ncu-rep"),
+                  ("fused-wide weight+filter, two transforms per CTA (filter_kernel<12, 1, 1>)", f"gpurun_out/filter_{tag}_wide.ncu-rep")):
     path = os.path.join(ROOT, rep)
     if not os.path.exists(path):
         continue
