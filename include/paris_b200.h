@@ -318,8 +318,9 @@ typedef struct paris_b200_group_config
     uint32_t exchange;                    /* PARIS_B200_EXCHANGE_* */
     uint32_t x_parts;                     /* 0 or 1: members own whole slices (z-slabs).  n > 1 (n divides world): the region is
                                              also cut into n equal parts along x (remainder on the last); member r owns x-part
-                                             r % n of z-run r / n.  For volumes with few slices per GPU: world / n taller
-                                             z-runs keep the 128-slice tiles */
+                                             r % n of z-run r / n.  Two uses: world / n = 2 mirror z-runs give every member
+                                             the same mix of cheap inner and costly outermost slices (bench.py from 4 GPUs
+                                             on), and volumes with few slices per GPU keep z-runs of >= 128 slices */
     uint32_t host_row_floats;             /* floats from one row to the next in the host memory handed to group_begin: 0 = the
                                              member's own box, contiguous; region_x = a box inside one region-wide volume */
 } paris_b200_group_config;
