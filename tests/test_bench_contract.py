@@ -72,3 +72,22 @@ def test_boxes_of_the_gpus_are_balanced_from_four_gpus_on():
             plans = [capi.group_plan(capi.group_config(r, world, det, vol, n_proj, roi=roi, x_parts=xp)) for r in range(world)]
             assert all(p.x_parts == xp and p.slabs_total == world // xp for p in plans)
             assert plans[0].slab_dz * (world // xp) == dims[2] and plans[0].x_dx * xp == dims[0]
+
+
+def test_reference_arm_runs_here_and_loads_nothing_of_the_product():
+    """`bench.py --impl reference` is CPU work (the reference's OpenMP backend from oracle/_ref, else the oracle port): it
+    runs in this container, prints the contract's line with the reference-arm keys, and -- asserted inside bench.py --
+    never imports paris_b200."""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--config", "c1", "--steps", "2",
+                        "--warmup", "1", "--cpu-budget", "0.5"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert r.returncode == 0, r.stderr[-2000:]
+    line = json.loads([l for l in r.stdout.splitlines() if l.startswith("{")][-1])
+    assert line["impl"] == "reference" and line["metric"] == "fdk_reconstruction_gups" and line["unit"] == "GUPS"
+    assert line["value"] > 0 and line["higher_is_better"] is True and line["steps"] == 2 and line["warmup"] == 1
+    assert line["cpu_baseline"]["kind"] in ("reference", "port") and line["cpu_baseline"]["cores"] >= 1
+    assert line["cpu_baseline"]["value"] == line["value"] == line["e2e"]["value"]
+    assert line["e2e"]["h2d_bytes_per_step"] == 0 and line["e2e"]["d2h_bytes_per_step"] == 0
