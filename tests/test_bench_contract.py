@@ -53,6 +53,22 @@ def test_final_single_gpu_line_has_clocks_and_cpu_baseline():
     assert "512^3" in d["config"]["workload"]
 
 
+def test_round_two_lines_are_on_the_north_star_config_with_green_parity():
+    d = last_line(os.path.join(ROOT, "profiles", "r2_bench_c3_1gpu.json"))
+    assert "1024^3" in d["config"]["workload"] and "2048^2" in d["config"]["workload"]      # BASELINE.json's configs[2]
+    assert d["roofline"]["kernel"].startswith("bp_tma_kernel<") and d["roofline"]["launches_by_kernel"]["exact"] == 0
+    assert d["cpu_baseline"]["kind"] == "reference" and d["cpu_baseline"]["cores"] >= 1
+    assert not {"hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown"} & set(d["clocks"]["reasons"])
+    many = [p for p in LINES if os.path.basename(p).startswith("r2_scale_")]
+    assert many
+    for path in many:
+        m = last_line(path)
+        assert m["n_gpus"] > 1 and m["scaling"] == "strong"
+        # every multi-GPU line certifies its volume: bands of every rank's slab against the exact kernel
+        assert m["parity_check"]["ok"] is True and m["parity_check"]["max"] <= 1e-4 and m["parity_check"]["rmse"] <= 1e-5
+        assert m["exchange"]["bytes_pushed_per_step_rank0"] < m["exchange"]["all_gather_bytes_per_step_rank0"]
+
+
 def test_boxes_of_the_gpus_are_balanced_from_four_gpus_on():
     """bench.auto_x_parts: z-slabs up to two GPUs (two halves are mirror images), two mirror z-runs x N/2 x-parts from
     four GPUs on for full regions, z-slabs for ROI regions and streamed slabs, and never fewer than 128 slices per
